@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the similarity-weighted NT-Xent hot path (BASELINE.json metric):
+
+    weighted NT-Xent fwd+bwd steps/sec @ 2N = 16384, d = 128 on N B200s, with % of roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine tf32|fp32]
+
+One "step" = everything between (z1, z2, joints1, joints2) and (loss, dz1, dz2): prep, MPJPE tiles, forward
+sweep, backward sweep, finalize (+ the collectives when N > 1).  Prints ONE JSON line on rank 0.
+`--impl reference` times the reference algorithm's CPU port (oracle/restate.py: the same torch ops as
+src/models/utils.py:218-261, :391-427) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_VIEW = 8192
+DIM = 128
+TAU = 0.5
+METRIC = "weighted NT-Xent fwd+bwd steps/sec @2N=16384,d=128"
+UNIT = "steps/s"
+MUFU_LANES_PER_SM = 16
+NUM_SMS = 148
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(hbm_gbs=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)",
+                    sm_max_mhz=d.get("sm_max_mhz", 1965.0))
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)", sm_max_mhz=1965.0)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(self.samples))
+
+
+def _make_batch(n):
+    from simhand_b200 import synth
+    return synth.make_batch(n, DIM, 5, "hand")
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (the only place bench.py touches oracle/)
+# --------------------------------------------------------------------------------------------------
+def cpu_port_sample(rows: int = 128, repeats: int = 3, warmup: int = 1):
+    """Times the reference's torch ops on a row block of the 2N = 16384 problem and extrapolates to a step.
+    The reference itself cannot run this size on a host (63 GiB of temporaries)."""
+    from oracle import restate as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    z1, z2, j1, j2 = _make_batch(N_PER_VIEW)
+    z = torch.cat([z1, z2], 0)
+    bj = torch.cat((j1[:, :, :2], j2[:, :, :2]), dim=0)
+    m = z.shape[0]
+    dmax = 70.0   # value only scales the weights; timing is data independent
+    times = []
+    for it in range(warmup + repeats):
+        r0 = (it * rows) % (m - rows)
+        t0 = time.perf_counter()
+        R.port_step_rows(z, bj, r0, r0 + rows, dmax, TAU)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t_sample = statistics.median(times)
+    steps_per_s = 1.0 / (t_sample * (m / rows))
+    return dict(value=steps_per_s, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"{rows} of {m} rows of one fwd+bwd step (weights, logits, exp, row sums, autograd) "
+                       f"x{repeats}, extrapolated x{m // rows}; median {t_sample * 1e3:.0f} ms per sample",
+                pairs_per_s=rows * m / t_sample)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_port_sample(rows=128, repeats=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 / base["value"], higher_is_better=True, scaling="strong",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="handclr_w loss fwd+bwd, global batch 8192 (2N=16384), d=128, 21 joints, "
+                                     "mpjpe/linear/pos_neg, tau 0.5", global_batch=N_PER_VIEW, proj_dim=DIM),
+                cpu_baseline=dict(value=base["value"], unit=UNIT, cores=base["cores"], kind=base["kind"],
+                                  sample=base["sample"]),
+                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from simhand_b200 import _lib, ops
+    from simhand_b200.dist import run_step_sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    n_local = N_PER_VIEW // world
+    z1, z2, j1, j2 = _make_batch(N_PER_VIEW)
+    sl = slice(rank * n_local, (rank + 1) * n_local)
+    hz1, hz2 = z1[sl].contiguous().pin_memory(), z2[sl].contiguous().pin_memory()
+    hj1, hj2 = j1[sl].contiguous().pin_memory(), j2[sl].contiguous().pin_memory()
+    dz1_, dz2_, dj1, dj2 = hz1.to(dev), hz2.to(dev), hj1.to(dev), hj2.to(dev)
+    engine = args.engine
+
+    def step(a, b, c, e):
+        if world == 1:
+            return ops.run_step(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True)
+        return run_step_sharded(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True, group)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(group)
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        loss, g1, g2 = step(dz1_, dz2_, dj1, dj2)
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # ---- device-resident timing: exactly K steps between two synchronised points
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss, g1, g2 = step(dz1_, dz2_, dj1, dj2)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    # ---- end to end: host buffers in, loss out, copies inside the timed region
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        a = hz1.to(dev, non_blocking=True)
+        b = hz2.to(dev, non_blocking=True)
+        c = hj1.to(dev, non_blocking=True)
+        e = hj2.to(dev, non_blocking=True)
+        loss, g1, g2 = step(a, b, c, e)
+        host_loss.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the loss every step
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    ms_total, ms_e2e = t.tolist()
+    ms_step = ms_total / args.steps
+    value = 1e3 / ms_step
+
+    # ---- per-kernel durations of the same step (instrumented pass; N = 1 only)
+    kernels = None
+    if world == 1:
+        kernels = time_kernels(ops, _lib, dz1_, dz2_, dj1, dj2, engine, max(3, min(args.steps, 10)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = _peaks()
+    clocks = sampler.summary() if sampler else None
+    m = 2 * N_PER_VIEW
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="tf32" if engine == "tf32" else "f32", data="synthetic",
+                config=dict(workload="handclr_w loss fwd+bwd, global batch 8192 (2N=16384), d=128, 21 joints, "
+                                     "mpjpe/linear/pos_neg, tau 0.5", global_batch=N_PER_VIEW, proj_dim=DIM,
+                            engine=engine, parallelism=f"row/tile-sharded x{world}" if world > 1 else "single GPU",
+                            l2="per-step working set (MPJPE tile workspace, 0.5 GiB at 1 GPU) exceeds the 126 MB L2; "
+                               "no explicit flush"),
+                clocks=clocks,
+                e2e=dict(value=1e3 / (ms_e2e / args.steps), unit=UNIT,
+                         h2d_bytes_per_step=int(hz1.numel() * 8 + hj1.numel() * 8), d2h_bytes_per_step=4),
+                gpu_launches=6 * args.steps * 1)
+    if kernels is not None:
+        f_clk = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
+        xu_peak = NUM_SMS * MUFU_LANES_PER_SM * f_clk * 1e6 / 1e9          # G special-function ops / s
+        t_mpjpe = kernels["mpjpe_kernel"] * 1e-3
+        achieved = 21.0 * m * m / t_mpjpe / 1e9
+        line["roofline"] = dict(
+            kernel="mpjpe_kernel", bound="xu (MUFU pipe; neither HBM nor tensor binds this path, SURVEY.md 8d)",
+            achieved=achieved, peak=xu_peak, unit="Gop/s (sqrt, algorithmic: 21 per ordered pair)",
+            frac=achieved / xu_peak, traffic=None,
+            peak_source=f"148 SMs x 16 MUFU lanes/clk x {f_clk:.0f} MHz (median SM clock under load)",
+            step_frac=(22.0 * m * m / (ms_step * 1e-3) / 1e9) / xu_peak,
+            note="step_frac = SURVEY 8d figure: (21 sqrt + 1 exp) M^2 / step time over the MUFU peak; values > "
+                 "the kernel's own frac are possible because symmetry halves the executed sqrt count")
+        hbm_bytes = 8256 * 65536.0 * 2          # each stored tile is read direct + transposed
+        for k in ("sweep_fwd", "sweep_bwd"):
+            kernels[k + "_hbm_frac"] = hbm_bytes / (kernels[k] * 1e-3) / 1e9 / peaks["hbm_gbs"]
+        line["kernels_ms"] = kernels
+        line["peaks"] = peaks
+        line["cpu_baseline"] = cpu_port_sample(rows=128, repeats=3, warmup=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_kernels(ops, _lib, z1, z2, j1, j2, engine, iters):
+    """CUDA-event duration of every launch of one step (same stream, same inputs), averaged."""
+    import ctypes
+    lib = _lib.load()
+    eng = _lib.ENGINES[engine]
+    dev = z1.device
+    n, d = z1.shape
+    ctx = ops.get_context(n, d, 1, 0, dev)
+    inp, keep = ops.make_inputs(z1, z2, j1[:, :, :2], j2[:, :, :2])
+    ws = torch.empty(int(ctx.layout.ws_bytes), dtype=torch.uint8, device=dev)
+    loss = torch.empty((), device=dev)
+    g1, g2 = torch.empty((n, d), device=dev), torch.empty((n, d), device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    pd, pi, plan = ctypes.byref(ctx.dims), ctypes.byref(inp), ctx.plan_dev.data_ptr()
+    calls = [
+        ("prep", lambda: lib.smh_prep(pd, pi, ws.data_ptr(), eng, st)),
+        ("mpjpe_kernel", lambda: lib.smh_mpjpe(pd, plan, ws.data_ptr(), st)),
+        ("sweep_fwd", lambda: lib.smh_forward(pd, plan, ws.data_ptr(), TAU, eng, st)),
+        ("sweep_bwd", lambda: lib.smh_backward(pd, plan, ws.data_ptr(), TAU, eng, st)),
+        ("finalize", lambda: lib.smh_finalize(pd, pi, ws.data_ptr(), None, TAU, 1.0, loss.data_ptr(), g1.data_ptr(),
+                                              g2.data_ptr(), d, st)),
+    ]
+    acc = {k: 0.0 for k, _ in calls}
+    for it in range(iters + 1):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(calls) + 1)]
+        evs[0].record()
+        for i, (_, fn) in enumerate(calls):
+            _lib.check(fn())
+            evs[i + 1].record()
+        torch.cuda.synchronize(dev)
+        if it == 0:
+            continue
+        for i, (k, _) in enumerate(calls):
+            acc[k] += evs[i].elapsed_time(evs[i + 1])
+    return {k: v / iters for k, v in acc.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="tf32", choices=["tf32", "fp32"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = min(args.steps, 30)
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

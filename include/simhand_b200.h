@@ -1,0 +1,174 @@
+/*
+ * simhand_b200 -- C ABI of the B200-native similarity-weighted NT-Xent hot path.
+ *
+ * This is the drop-in boundary for the loss operator of ut-vision/SiMHand.  The reference has no
+ * native code: its boundary is two Python functions,
+ *     get_weights_linear(joints1, joints2, diff_type)                    src/models/utils.py:218-261
+ *     vanila_weights_contrastive_loss(z1, z2, pos_w, neg_w, temperature)  src/models/utils.py:391-427
+ * called from contrastive_step() (src/models/unsupervised/simhand_w_model.py:122-136,
+ * peclr_w_model.py:110-123, simclr_w_model.py:71-96).  The host mirror of those two functions lives in
+ * simhand_b200/ops.py and binds the entry points below with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer named *_dev is a CUDA device pointer owned by the caller (PyTorch's caching
+ *     allocator); the library never allocates, frees or retains device memory;
+ *   - every call is asynchronous on the given stream and never synchronises the device;
+ *   - return value: 0 = ok, < 0 = argument error (SMH_E_*), > 0 = cudaError_t of a failed launch;
+ *     smh_last_error() returns a thread-local description of the last failure;
+ *   - re-entrant: no global mutable state (safe under nn.DataParallel's one-thread-per-device use,
+ *     src/experiments/main.py:155);
+ *   - built for sm_100a only.  There is no CPU path and no other backend.
+ *
+ * One training step of the path is the sequence
+ *     smh_prep -> smh_mpjpe -> [all-reduce MAX of stats, world > 1] -> smh_forward ->
+ *     [all-reduce SUM of neg] -> smh_backward -> [reduce-scatter of dz] -> smh_finalize
+ * over one workspace blob whose layout smh_layout() reports ("Data layout in HBM").
+ */
+#ifndef SIMHAND_B200_H
+#define SIMHAND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMH_VERSION 100          /* 0.1.0 */
+#define SMH_NUM_JOINTS 21        /* src/data_loader: joints are [B, 21, 3], the path uses [:, :, :2] */
+#define SMH_MAX_DIM 128          /* projection width d <= 128 (reference: output_dim 128) */
+
+/* error codes (negative) */
+#define SMH_E_ARG (-1)           /* null pointer / non-positive size */
+#define SMH_E_DIM (-2)           /* unsupported d, J or world/rank combination */
+#define SMH_E_ALIGN (-3)         /* pointer or stride not aligned as documented */
+#define SMH_E_SIZE (-4)          /* caller buffer too small */
+#define SMH_E_ARCH (-5)          /* device is not sm_100 */
+#define SMH_E_MODE (-6)          /* unknown engine / mode */
+
+/* engine of the forward/backward sweeps (the dense contraction S = z z^T and dz = G z) */
+#define SMH_ENGINE_TC_TF32 0     /* tcgen05.mma kind::tf32, TMEM accumulators, bulk-async staged tiles */
+#define SMH_ENGINE_FP32 1        /* CUDA-core FFMA, fp32 accumulate (exact-fp32 mode) */
+
+/* problem description shared by all calls */
+typedef struct smh_dims {
+    int32_t n;                   /* global per-view batch N; the loss sees M = 2N samples */
+    int32_t d;                   /* projection width, 1..SMH_MAX_DIM */
+    int32_t world;               /* ranks sharing the batch (1 = single GPU) */
+    int32_t rank;                /* this rank, 0..world-1 */
+    int32_t strip_len;           /* sweep tasks per strip (<= 0: library default) */
+} smh_dims_t;
+
+/* byte offsets into the workspace blob (all 256-byte aligned) and table sizes */
+typedef struct smh_layout {
+    int64_t ws_bytes;            /* total workspace size */
+    int64_t plan_bytes;          /* size of the task plan (host build, device copy by the caller) */
+    int64_t off_stats;           /* smh_stats_t */
+    int64_t off_zt;              /* [Tp*128][128] fp32, tf32-rounded z, pre-swizzled 64-row blocks */
+    int64_t off_jp;              /* [Tp*128][44] fp32 packed joints */
+    int64_t off_posd;            /* [N] fp32 positive-pair MPJPE */
+    int64_t off_neg;             /* [Tp*128] fp32 off-diagonal row sums (partial until all-reduced) */
+    int64_t off_rn;              /* [Tp*128] fp32 1/neg */
+    int64_t off_rowloss;         /* [Tp*128] fp32 per-row loss terms */
+    int64_t off_dzacc;           /* [M][128] fp32 unscaled gradient accumulator (rank-major rows) */
+    int64_t off_dist;            /* stored MPJPE tiles of this rank, 64 KiB each */
+    int32_t m;                   /* 2N */
+    int32_t tiles_per_side;      /* Tp = ceil(M / 128) */
+    int32_t n_stored_tiles;      /* upper-triangular 128x128 tiles assigned to this rank */
+    int32_t n_tasks;             /* 128x64 sweep tasks of this rank */
+    int32_t n_strips;            /* groups of consecutive tasks sharing a row block */
+    int32_t strip_len;           /* max tasks per strip */
+} smh_layout_t;
+
+/* device-resident scalars.  The first three words are order-preserving integer images of the
+ * floats, so a multi-rank run combines them with one all-reduce(MAX) on int32[3]. */
+typedef struct smh_stats {
+    uint32_t dmax_bits;          /* float bits of max_ij D_ij (D >= 0)            (utils.py:255) */
+    uint32_t pmax_bits;          /* float bits of max_k D_{k,k+N}                 (utils.py:233) */
+    uint32_t pmin_inv;           /* 0x7fffffff - float bits of min_k D_{k,k+N}    (utils.py:234) */
+    uint32_t flags;              /* SMH_FLAG_* */
+    float loss;                  /* final loss (also written to the caller's pointer) */
+    uint32_t counter;            /* internal: last-block-done ticket */
+    uint32_t fail_site;          /* != 0: a bounded pipeline wait timed out (result invalid) */
+    uint32_t pad;
+} smh_stats_t;
+
+#define SMH_FLAG_SLOW_DOMAIN 1u  /* joints outside the fast exact-sqrt domain: IEEE slow path used */
+#define SMH_FLAG_NONFINITE 2u    /* a joint coordinate is NaN/Inf: loss is NaN, as in the reference */
+
+/* inputs as the reference hands them over: two projections and two joint views.
+ * joints are fp32 views [N, 21, 2] with arbitrary element strides (the callers pass the
+ * non-contiguous joints[:, :, :2] slice of a [N, 21, 3] tensor, simhand_w_model.py:103-104).
+ * For world > 1 the buffers are the all-gathered ones: sample k of view v lives at
+ *   base_v + (k / n_local) * rank_stride + (k % n_local) * row_stride            (elements). */
+typedef struct smh_inputs {
+    const float *z1_dev, *z2_dev;        /* [N, d] fp32, rows L2-normalised by the caller */
+    int64_t z_row_stride;                /* elements between consecutive samples (>= d) */
+    const float *j1_dev, *j2_dev;        /* [N, 21, 2] fp32 views */
+    int64_t j_sample_stride, j_joint_stride, j_coord_stride;   /* elements */
+    int32_t n_local;                     /* samples per rank per view (N when world == 1) */
+    int64_t z_rank_stride, j_rank_stride;/* elements between rank chunks (ignored when world == 1) */
+} smh_inputs_t;
+
+int smh_version(void);
+const char *smh_last_error(void);
+
+/* sizes and offsets for a problem. */
+int smh_layout(const smh_dims_t *dims, smh_layout_t *out);
+
+/* builds the task plan of this rank into caller-owned host memory (layout.plan_bytes); the caller
+ * copies it to the device once per dims and passes the device copy to the sweeps. */
+int smh_plan_build(const smh_dims_t *dims, void *plan_host, int64_t plan_bytes);
+
+/* K3a: packs joints, stages z into sweep tiles (rounded to tf32 for SMH_ENGINE_TC_TF32, unrounded for
+ * SMH_ENGINE_FP32), positive-pair MPJPE (utils.py:229-231), zeroes the accumulators.  Replaces the
+ * torch.cat calls of utils.py:237-239 and :407. */
+int smh_prep(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, int engine, void *stream);
+
+/* K0: all-pairs MPJPE tiles of this rank (upper triangle) + running max (utils.py:251-255). */
+int smh_mpjpe(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, void *stream);
+
+/* K1: weighted logits, exp and off-diagonal row sums (utils.py:411-417) -> ws.neg (partial sums of
+ * this rank's tasks for all M rows). */
+int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature,
+                int engine, void *stream);
+
+/* K2: dz accumulation (autograd of utils.py:411-426) -> ws.dzacc (partial sums of
+ * this rank's tasks for all M rows, rows in rank-major order).  Needs ws.neg complete. */
+int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature,
+                 int engine, void *stream);
+
+/* loss (utils.py:420-426) over all M rows and, if dz1_dev != NULL, the gradients of the local
+ * samples: dz = dzacc_src / (M tau) - 2 Wp z_partner / (M tau), scaled by grad_scale.
+ * dzacc_src_dev is ws.dzacc (world == 1) or the reduce-scattered [2 * n_local][128] block. */
+int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev,
+                 const float *dzacc_src_dev, float temperature, float grad_scale,
+                 float *loss_dev, float *dz1_dev, float *dz2_dev, int64_t dz_row_stride,
+                 void *stream);
+
+/* materialised weights with the reference's return shapes: pos_w [N], neg_w [M, M] row-major
+ * (utils.py:235, :259).  world == 1 only.  Needs smh_prep + smh_mpjpe. */
+int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev,
+                      float *pos_w_dev, float *neg_w_dev, void *stream);
+
+/* K3: row-wise L2 normalisation y = x / max(||x||, eps) and its backward
+ * (F.normalize in simhand_w_model.py:56-58,91-93). */
+int smh_l2norm_fwd(const float *x_dev, float *y_dev, float *norm_dev, int64_t rows, int32_t d,
+                   float eps, void *stream);
+int smh_l2norm_bwd(const float *y_dev, const float *norm_dev, const float *dy_dev, float *dx_dev,
+                   int64_t rows, int32_t d, float eps, void *stream);
+
+/* device self-tests used by tests/ (exhaustive exact-sqrt / exact-division checks, tcgen05 tile
+ * checks).  out_dev receives test-specific counters. */
+int smh_selftest(int which, uint64_t *out_dev, int64_t out_words, void *stream);
+
+/* diagnostic: one tcgen05 tile S = A B^T and dZ = tf32(S) Z_B on staged z blocks with caller-supplied
+ * descriptor fields (see smh_selftest.cu); tests/ pins the encodings hard-coded in the sweeps with it. */
+int smh_tc_probe(const float *zt_dev, int blk_a, int blk_b, const uint32_t *params16_host, float *s_out_dev,
+                 float *dz_out_dev, uint32_t *fail_dev, void *stream);
+void smh_tc_default_params(uint32_t *params16_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMHAND_B200_H */

@@ -1,0 +1,9 @@
+"""simhand_b200 -- B200-native similarity-weighted NT-Xent loss (SiMHand handclr_w / peclr_w / simclr_w).
+
+Public API (mirrors `src/models/utils.py` of the reference):
+    get_weights_linear, vanila_weights_contrastive_loss, weighted_ntxent, l2_normalize, install
+"""
+from .ops import (LazyWeights, get_weights_linear, install, l2_normalize, mpjpe_weights, run_step,  # noqa: F401
+                  vanila_weights_contrastive_loss, weighted_ntxent)
+
+__version__ = "0.1.0"

@@ -1,0 +1,99 @@
+"""ctypes binding of libsimhand_b200.so (the C ABI declared in include/simhand_b200.h).
+
+The library is the product: if it is missing the import fails loudly -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsimhand_b200.so")
+
+ENGINE_TC_TF32 = 0
+ENGINE_FP32 = 1
+ENGINES = {"tf32": ENGINE_TC_TF32, "tc": ENGINE_TC_TF32, "fp32": ENGINE_FP32}
+
+FLAG_SLOW_DOMAIN = 1
+FLAG_NONFINITE = 2
+
+
+class Dims(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("d", ctypes.c_int32), ("world", ctypes.c_int32),
+                ("rank", ctypes.c_int32), ("strip_len", ctypes.c_int32)]
+
+
+class Layout(ctypes.Structure):
+    _fields_ = [("ws_bytes", ctypes.c_int64), ("plan_bytes", ctypes.c_int64), ("off_stats", ctypes.c_int64),
+                ("off_zt", ctypes.c_int64), ("off_jp", ctypes.c_int64), ("off_posd", ctypes.c_int64),
+                ("off_neg", ctypes.c_int64), ("off_rn", ctypes.c_int64), ("off_rowloss", ctypes.c_int64),
+                ("off_dzacc", ctypes.c_int64), ("off_dist", ctypes.c_int64),
+                ("m", ctypes.c_int32), ("tiles_per_side", ctypes.c_int32), ("n_stored_tiles", ctypes.c_int32),
+                ("n_tasks", ctypes.c_int32), ("n_strips", ctypes.c_int32), ("strip_len", ctypes.c_int32)]
+
+
+class Inputs(ctypes.Structure):
+    _fields_ = [("z1", ctypes.c_void_p), ("z2", ctypes.c_void_p), ("z_row_stride", ctypes.c_int64),
+                ("j1", ctypes.c_void_p), ("j2", ctypes.c_void_p),
+                ("j_sample_stride", ctypes.c_int64), ("j_joint_stride", ctypes.c_int64),
+                ("j_coord_stride", ctypes.c_int64), ("n_local", ctypes.c_int32),
+                ("z_rank_stride", ctypes.c_int64), ("j_rank_stride", ctypes.c_int64)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("dmax_bits", ctypes.c_uint32), ("pmax_bits", ctypes.c_uint32), ("pmin_inv", ctypes.c_uint32),
+                ("flags", ctypes.c_uint32), ("loss", ctypes.c_float), ("counter", ctypes.c_uint32),
+                ("fail_site", ctypes.c_uint32), ("pad", ctypes.c_uint32)]
+
+
+# every symbol include/simhand_b200.h declares (tests check that the library exports all of them)
+EXPORTS = ("smh_version", "smh_last_error", "smh_layout", "smh_plan_build", "smh_prep", "smh_mpjpe",
+           "smh_forward", "smh_backward", "smh_finalize", "smh_weights_dense", "smh_l2norm_fwd",
+           "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params")
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m simhand_b200.build` "
+            "(nvcc, sm_100a).  simhand_b200 has no fallback path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+    pd, pl, pi = ctypes.POINTER(Dims), ctypes.POINTER(Layout), ctypes.POINTER(Inputs)
+    lib.smh_version.restype = ctypes.c_int
+    lib.smh_last_error.restype = ctypes.c_char_p
+    lib.smh_layout.argtypes = [pd, pl]
+    lib.smh_plan_build.argtypes = [pd, vp, i64]
+    lib.smh_prep.argtypes = [pd, pi, vp, ctypes.c_int, vp]
+    lib.smh_mpjpe.argtypes = [pd, vp, vp, vp]
+    lib.smh_forward.argtypes = [pd, vp, vp, f32, ctypes.c_int, vp]
+    lib.smh_backward.argtypes = [pd, vp, vp, f32, ctypes.c_int, vp]
+    lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, vp]
+    lib.smh_weights_dense.argtypes = [pd, vp, vp, vp, vp, vp]
+    lib.smh_l2norm_fwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
+    lib.smh_l2norm_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]
+    lib.smh_selftest.argtypes = [ctypes.c_int, vp, i64, vp]
+    lib.smh_tc_probe.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), vp, vp, vp, vp]
+    lib.smh_tc_default_params.argtypes = [ctypes.POINTER(ctypes.c_uint32)]
+    lib.smh_tc_default_params.restype = None
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("smh_version", "smh_last_error", "smh_tc_default_params"):
+            fn.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+class SmhError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().smh_last_error().decode(errors="replace")
+        raise SmhError(f"{what or 'simhand_b200'} failed with code {rc}: {msg}")

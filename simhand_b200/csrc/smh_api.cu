@@ -1,0 +1,357 @@
+// simhand_b200: extern "C" entry points, workspace layout and the host-side task plan.
+//
+// The plan decides which 128x128 MPJPE tiles a rank stores (upper triangle, balanced over ranks)
+// and which 128x64 sweep tasks it runs in the forward/backward sweeps; see DESIGN.md "Task plan".
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "smh_common.cuh"
+#include "smh_internal.h"
+
+namespace smh {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error((int)e, "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static int validate_dims(const smh_dims_t *dims)
+{
+    if (!dims) return set_error(SMH_E_ARG, "dims is null");
+    if (dims->n <= 0) return set_error(SMH_E_ARG, "n must be positive (got %d)", dims->n);
+    if (dims->d <= 0 || dims->d > SMH_MAX_DIM)
+        return set_error(SMH_E_DIM, "d must be in 1..%d (got %d)", SMH_MAX_DIM, dims->d);
+    if (dims->world <= 0 || dims->rank < 0 || dims->rank >= dims->world)
+        return set_error(SMH_E_DIM, "bad world/rank %d/%d", dims->world, dims->rank);
+    if (dims->n % dims->world != 0)
+        return set_error(SMH_E_DIM, "n (%d) must be a multiple of world (%d)", dims->n, dims->world);
+    if ((int64_t)dims->n * 2 > (1 << 22)) return set_error(SMH_E_DIM, "2N too large (%d)", dims->n * 2);
+    return 0;
+}
+
+// owner of row block I: rows I and Tp-1-I are paired so every rank stores ~the same number of tiles
+static inline int row_owner(int I, int tp, int world) { return std::min(I, tp - 1 - I) % world; }
+
+struct HostPlan {
+    std::vector<int2> tiles;
+    std::vector<int4> tasks;
+    std::vector<int2> strips;
+};
+
+static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out, int *n_stored, int *n_tasks,
+                           int *n_strips)
+{
+    const int m = 2 * dims.n;
+    const int tp = (m + kTile - 1) / kTile;
+    std::vector<int2> tiles;
+    std::vector<int4> tasks;
+    for (int I = 0; I < tp; ++I) {
+        if (row_owner(I, tp, dims.world) != dims.rank) continue;
+        for (int J = I; J < tp; ++J) {
+            int lt = (int)tiles.size();
+            tiles.push_back(make_int2(I, J));
+            for (int half = 0; half < 2; ++half) {
+                int cj = 2 * J + half;
+                if (cj * kTaskN >= m) continue;
+                int flags = (I == J ? kTaskDiagonal : 0);
+                if (I * kTile + kTile > m || cj * kTaskN + kTaskN > m) flags |= kTaskRagged;
+                tasks.push_back(make_int4(I, cj, lt, flags));
+            }
+            if (J > I) {
+                for (int half = 0; half < 2; ++half) {
+                    int cj = 2 * I + half;
+                    int flags = kTaskTransposed;
+                    if (J * kTile + kTile > m) flags |= kTaskRagged;
+                    tasks.push_back(make_int4(J, cj, lt, flags));
+                }
+            }
+        }
+    }
+    std::sort(tasks.begin(), tasks.end(), [](const int4 &a, const int4 &b) {
+        return a.x != b.x ? a.x < b.x : a.y < b.y;
+    });
+    std::vector<int2> strips;
+    size_t i = 0;
+    while (i < tasks.size()) {
+        size_t j = i;
+        while (j < tasks.size() && tasks[j].x == tasks[i].x && (int)(j - i) < strip_len) ++j;
+        strips.push_back(make_int2((int)i, (int)j));
+        i = j;
+    }
+    *n_stored = (int)tiles.size();
+    *n_tasks = (int)tasks.size();
+    *n_strips = (int)strips.size();
+    if (out) {
+        out->tiles.swap(tiles);
+        out->tasks.swap(tasks);
+        out->strips.swap(strips);
+    }
+}
+
+// per-thread memo of the last layout: the entry points are called several times per step with the same
+// dims and enumerating the plan costs ~1 ms at 2N = 16384 (thread-local, so the library stays re-entrant)
+struct LayoutMemo {
+    bool valid = false;
+    smh_dims_t dims;
+    smh_layout_t lay;
+};
+static thread_local LayoutMemo g_memo;
+
+static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *plan)
+{
+    if (!plan && g_memo.valid && memcmp(&g_memo.dims, &dims, sizeof(dims)) == 0) {
+        *lay = g_memo.lay;
+        return 0;
+    }
+    memset(lay, 0, sizeof(*lay));
+    const int m = 2 * dims.n;
+    const int tp = (m + kTile - 1) / kTile;
+    const int64_t mp = (int64_t)tp * kTile;
+    lay->m = m;
+    lay->tiles_per_side = tp;
+    lay->strip_len = dims.strip_len > 0 ? dims.strip_len : 16;
+    enumerate_plan(dims, lay->strip_len, plan, &lay->n_stored_tiles, &lay->n_tasks, &lay->n_strips);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        int64_t o = off;
+        off = align_up(off + bytes, 1024);
+        return o;
+    };
+    lay->off_stats = take(sizeof(Stats));
+    lay->off_neg = take(mp * 4);
+    lay->off_rn = take(mp * 4);
+    lay->off_rowloss = take(mp * 4);
+    lay->off_dzacc = take(mp * kD * 4);
+    lay->off_posd = take((int64_t)dims.n * 4);
+    lay->off_zt = take(mp * kD * 4);
+    lay->off_jp = take(mp * kJP * 4);
+    lay->off_dist = take((int64_t)lay->n_stored_tiles * kTileFloats * 4);
+    lay->ws_bytes = off;
+    lay->plan_bytes = align_up((int64_t)sizeof(PlanHeader), 16) + align_up((int64_t)lay->n_stored_tiles * 8, 16) +
+                      (int64_t)lay->n_tasks * 16 + align_up((int64_t)lay->n_strips * 8, 16);
+    g_memo.dims = dims;
+    g_memo.lay = *lay;
+    g_memo.valid = true;
+    return 0;
+}
+
+static WsView carve(void *ws, const smh_layout_t &lay)
+{
+    char *b = (char *)ws;
+    WsView v;
+    v.stats = b + lay.off_stats;
+    v.zt = (float *)(b + lay.off_zt);
+    v.jp = (float *)(b + lay.off_jp);
+    v.posd = (float *)(b + lay.off_posd);
+    v.neg = (float *)(b + lay.off_neg);
+    v.rn = (float *)(b + lay.off_rn);
+    v.rowloss = (float *)(b + lay.off_rowloss);
+    v.dzacc = (float *)(b + lay.off_dzacc);
+    v.dist = (float *)(b + lay.off_dist);
+    return v;
+}
+
+static PlanView carve_plan(const void *plan, const smh_layout_t &lay)
+{
+    const char *b = (const char *)plan;
+    int64_t o = align_up((int64_t)sizeof(PlanHeader), 16);
+    PlanView v;
+    v.tiles = (const int2 *)(b + o);
+    o += align_up((int64_t)lay.n_stored_tiles * 8, 16);
+    v.tasks = (const int4 *)(b + o);
+    o += (int64_t)lay.n_tasks * 16;
+    v.strips = (const int2 *)(b + o);
+    return v;
+}
+
+static int check_ptr(const void *p, const char *name, int align)
+{
+    if (!p) return set_error(SMH_E_ARG, "%s is null", name);
+    if (((uintptr_t)p) % align) return set_error(SMH_E_ALIGN, "%s must be %d-byte aligned", name, align);
+    return 0;
+}
+
+static int check_inputs(const smh_dims_t &dims, const smh_inputs_t *in)
+{
+    if (!in) return set_error(SMH_E_ARG, "inputs is null");
+    int rc;
+    if ((rc = check_ptr(in->z1_dev, "z1", 4))) return rc;
+    if ((rc = check_ptr(in->z2_dev, "z2", 4))) return rc;
+    if ((rc = check_ptr(in->j1_dev, "joints1", 4))) return rc;
+    if ((rc = check_ptr(in->j2_dev, "joints2", 4))) return rc;
+    if (in->z_row_stride < dims.d) return set_error(SMH_E_ARG, "z_row_stride < d");
+    if (in->n_local <= 0 || dims.n % in->n_local != 0)
+        return set_error(SMH_E_DIM, "n_local (%d) must divide n (%d)", in->n_local, dims.n);
+    return 0;
+}
+
+}  // namespace smh
+
+using namespace smh;
+
+extern "C" {
+
+int smh_version(void) { return SMH_VERSION; }
+
+const char *smh_last_error(void) { return g_err; }
+
+int smh_layout(const smh_dims_t *dims, smh_layout_t *out)
+{
+    int rc = validate_dims(dims);
+    if (rc) return rc;
+    if (!out) return set_error(SMH_E_ARG, "layout out is null");
+    return compute_layout(*dims, out, nullptr);
+}
+
+int smh_plan_build(const smh_dims_t *dims, void *plan_host, int64_t plan_bytes)
+{
+    int rc = validate_dims(dims);
+    if (rc) return rc;
+    if (!plan_host) return set_error(SMH_E_ARG, "plan_host is null");
+    smh_layout_t lay;
+    HostPlan hp;
+    compute_layout(*dims, &lay, &hp);
+    if (plan_bytes < lay.plan_bytes)
+        return set_error(SMH_E_SIZE, "plan buffer too small: %lld < %lld", (long long)plan_bytes,
+                         (long long)lay.plan_bytes);
+    char *b = (char *)plan_host;
+    memset(b, 0, (size_t)lay.plan_bytes);
+    PlanHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = kPlanMagic;
+    h.m = (uint32_t)lay.m;
+    h.world = (uint32_t)dims->world;
+    h.rank = (uint32_t)dims->rank;
+    h.tiles_per_side = (uint32_t)lay.tiles_per_side;
+    h.n_stored = (uint32_t)lay.n_stored_tiles;
+    h.n_tasks = (uint32_t)lay.n_tasks;
+    h.n_strips = (uint32_t)lay.n_strips;
+    h.strip_len = (uint32_t)lay.strip_len;
+    int64_t o = align_up((int64_t)sizeof(PlanHeader), 16);
+    h.off_tiles = (uint32_t)o;
+    if (!hp.tiles.empty()) memcpy(b + o, hp.tiles.data(), hp.tiles.size() * 8);
+    o += align_up((int64_t)lay.n_stored_tiles * 8, 16);
+    h.off_tasks = (uint32_t)o;
+    if (!hp.tasks.empty()) memcpy(b + o, hp.tasks.data(), hp.tasks.size() * 16);
+    o += (int64_t)lay.n_tasks * 16;
+    h.off_strips = (uint32_t)o;
+    if (!hp.strips.empty()) memcpy(b + o, hp.strips.data(), hp.strips.size() * 8);
+    memcpy(b, &h, sizeof(h));
+    return 0;
+}
+
+#define SMH_COMMON_PROLOGUE(need_plan)                                                      \
+    int rc = validate_dims(dims);                                                           \
+    if (rc) return rc;                                                                      \
+    if ((rc = check_ptr(ws_dev, "workspace", 1024))) return rc;                             \
+    if (need_plan && (rc = check_ptr(plan_dev, "plan", 16))) return rc;                     \
+    smh_layout_t lay;                                                                       \
+    compute_layout(*dims, &lay, nullptr);                                                   \
+    WsView ws = carve(ws_dev, lay);                                                         \
+    cudaStream_t st = (cudaStream_t)stream;
+
+int smh_prep(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, int engine, void *stream)
+{
+    const void *plan_dev = nullptr;
+    SMH_COMMON_PROLOGUE(false)
+    (void)plan_dev;
+    if ((rc = check_inputs(*dims, in))) return rc;
+    if (engine != SMH_ENGINE_TC_TF32 && engine != SMH_ENGINE_FP32) return set_error(SMH_E_MODE, "unknown engine %d", engine);
+    return launch_prep(*dims, lay, *in, ws, engine == SMH_ENGINE_TC_TF32, st);
+}
+
+int smh_mpjpe(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, void *stream)
+{
+    SMH_COMMON_PROLOGUE(true)
+    return launch_mpjpe(*dims, lay, carve_plan(plan_dev, lay), ws, st);
+}
+
+int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature, int engine,
+                void *stream)
+{
+    SMH_COMMON_PROLOGUE(true)
+    if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
+    PlanView pv = carve_plan(plan_dev, lay);
+    if (engine == SMH_ENGINE_TC_TF32) return launch_sweep_tc(false, *dims, lay, pv, ws, temperature, st);
+    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, *dims, lay, pv, ws, temperature, st);
+    return set_error(SMH_E_MODE, "unknown engine %d", engine);
+}
+
+int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature, int engine,
+                 void *stream)
+{
+    SMH_COMMON_PROLOGUE(true)
+    if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
+    PlanView pv = carve_plan(plan_dev, lay);
+    if ((rc = launch_rn(lay, ws, st))) return rc;
+    if (engine == SMH_ENGINE_TC_TF32) return launch_sweep_tc(true, *dims, lay, pv, ws, temperature, st);
+    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, *dims, lay, pv, ws, temperature, st);
+    return set_error(SMH_E_MODE, "unknown engine %d", engine);
+}
+
+int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, const float *dzacc_src_dev,
+                 float temperature, float grad_scale, float *loss_dev, float *dz1_dev, float *dz2_dev,
+                 int64_t dz_row_stride, void *stream)
+{
+    const void *plan_dev = nullptr;
+    SMH_COMMON_PROLOGUE(false)
+    (void)plan_dev;
+    if ((rc = check_inputs(*dims, in))) return rc;
+    if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
+    if ((dz1_dev == nullptr) != (dz2_dev == nullptr)) return set_error(SMH_E_ARG, "dz1/dz2 must both be set or null");
+    if (dz1_dev && dz_row_stride < dims->d) return set_error(SMH_E_ARG, "dz_row_stride < d");
+    if (dz1_dev && !dzacc_src_dev) dzacc_src_dev = ws.dzacc;
+    return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, temperature, grad_scale, loss_dev, dz1_dev,
+                           dz2_dev, dz_row_stride, st);
+}
+
+int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float *pos_w_dev,
+                      float *neg_w_dev, void *stream)
+{
+    SMH_COMMON_PROLOGUE(true)
+    if (dims->world != 1) return set_error(SMH_E_DIM, "smh_weights_dense needs world == 1");
+    if (!pos_w_dev && !neg_w_dev) return set_error(SMH_E_ARG, "no output requested");
+    return launch_weights_dense(*dims, lay, carve_plan(plan_dev, lay), ws, pos_w_dev, neg_w_dev, st);
+}
+
+int smh_l2norm_fwd(const float *x_dev, float *y_dev, float *norm_dev, int64_t rows, int32_t d, float eps,
+                   void *stream)
+{
+    if (!x_dev || !y_dev) return set_error(SMH_E_ARG, "x/y is null");
+    if (rows <= 0 || d <= 0) return set_error(SMH_E_ARG, "rows and d must be positive");
+    return launch_l2norm_fwd(x_dev, y_dev, norm_dev, rows, d, eps, (cudaStream_t)stream);
+}
+
+int smh_l2norm_bwd(const float *y_dev, const float *norm_dev, const float *dy_dev, float *dx_dev, int64_t rows,
+                   int32_t d, float eps, void *stream)
+{
+    if (!y_dev || !norm_dev || !dy_dev || !dx_dev) return set_error(SMH_E_ARG, "null pointer");
+    if (rows <= 0 || d <= 0) return set_error(SMH_E_ARG, "rows and d must be positive");
+    return launch_l2norm_bwd(y_dev, norm_dev, dy_dev, dx_dev, rows, d, eps, (cudaStream_t)stream);
+}
+
+int smh_selftest(int which, uint64_t *out_dev, int64_t out_words, void *stream)
+{
+    if (!out_dev || out_words < 8) return set_error(SMH_E_ARG, "out buffer needs >= 8 words");
+    return launch_selftest(which, out_dev, out_words, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+// simhand_b200: the small kernels around the sweeps.
+//   rn_kernel            1 / neg_i                                        (feeds the backward sweep)
+//   finalize_kernel      positive-pair weights (src/models/utils.py:233-235), positive logits (:420-423),
+//                        loss = mean_i [log neg_i - S_ip Wp / tau] (:425-426), and the final gradient
+//                        dz_i = dzacc_i / (M tau) - 2 Wp z_p(i) / (M tau).  The positive
+//                        term is evaluated in fp32 from the caller's unrounded z in every mode.
+//   weights_dense_kernel materialised pos_w [N] / neg_w [M, M] with the reference's shapes (:235, :259)
+//   l2norm_*             K3: F.normalize forward/backward (simhand_w_model.py:56-58, 91-93)
+#include <math_constants.h>
+
+#include "smh_common.cuh"
+#include "smh_internal.h"
+
+namespace smh {
+
+__global__ void rn_kernel(const float *__restrict__ neg, float *__restrict__ rn, int m, int mp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < mp) rn[i] = (i < m) ? __frcp_rn(neg[i]) : 0.f;
+}
+
+int launch_rn(const smh_layout_t &lay, const WsView &ws, cudaStream_t stream)
+{
+    const int mp = lay.tiles_per_side * kTile;
+    rn_kernel<<<(mp + 255) / 256, 256, 0, stream>>>(ws.neg, ws.rn, lay.m, mp);
+    return check_launch("rn_kernel");
+}
+
+__device__ __forceinline__ const float *sample_ptr_f(const float *base, int k, int n_local, int64_t rank_stride,
+                                                     int64_t row_stride)
+{
+    return base + (int64_t)(k / n_local) * rank_stride + (int64_t)(k % n_local) * row_stride;
+}
+
+__global__ void __launch_bounds__(256)
+finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict__ neg,
+                const float *__restrict__ posd, float *__restrict__ rowloss, Stats *__restrict__ stats,
+                const float *__restrict__ dzacc_src, int64_t src_row_offset, float inv_tau, float grad_scale,
+                float *__restrict__ loss_out, float *__restrict__ dz1, float *__restrict__ dz2,
+                int64_t dz_row_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int m = 2 * n;
+    const float pmax = __uint_as_float(stats->pmax_bits);
+    const float pmin = __uint_as_float(0x7fffffffu - stats->pmin_inv);
+    const float pden = __fsub_rn(pmax, pmin);
+    const int n_local = in.n_local;
+    const int k_lo = rank * n_local, k_hi = k_lo + n_local;
+    const float gs = grad_scale * inv_tau / (float)m;
+
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < m; row += gridDim.x * warps_per_block) {
+        const int v = row >= n ? 1 : 0;
+        const int k = row - v * n;
+        const float *zi = sample_ptr_f(v ? in.z2_dev : in.z1_dev, k, n_local, in.z_rank_stride, in.z_row_stride);
+        const float *zp = sample_ptr_f(v ? in.z1_dev : in.z2_dev, k, n_local, in.z_rank_stride, in.z_row_stride);
+        float dot = 0.f;
+        for (int c = lane; c < d; c += 32) dot = fmaf(zi[c], zp[c], dot);
+        dot = warp_sum(dot);
+        const float wp = __fdiv_rn(__fsub_rn(pmax, posd[k]), pden);            // utils.py:235
+        if (lane == 0) rowloss[row] = logf(neg[row]) - dot * wp * inv_tau;      // utils.py:420-426
+        if (dz1 != nullptr && k >= k_lo && k < k_hi) {
+            const float *src = dzacc_src + (dz_out_row(row, n, n_local) - src_row_offset) * kD;
+            float *dst = (v ? dz2 : dz1) + (int64_t)(k - k_lo) * dz_row_stride;
+            const float two_wp = 2.f * wp;
+            for (int c = lane; c < d; c += 32) dst[c] = gs * (src[c] - two_wp * zp[c]);
+        }
+    }
+
+    // last block reduces the per-row terms in a fixed order (deterministic loss)
+    __shared__ bool is_last;
+    __shared__ float part[256];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned ticket = atomicAdd(&stats->counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < m; i += 256) acc += __ldcg(rowloss + i);
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2) part[threadIdx.x] += part[threadIdx.x + s2];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float loss = part[0] / (float)m;
+        if ((stats->flags & SMH_FLAG_NONFINITE) || stats->fail_site != 0u) loss = CUDART_NAN_F;
+        stats->loss = loss;
+        stats->counter = 0u;
+        if (loss_out) *loss_out = loss;
+    }
+}
+
+int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
+                    const float *dzacc_src, float temperature, float grad_scale, float *loss, float *dz1,
+                    float *dz2, int64_t dz_row_stride, cudaStream_t stream)
+{
+    const int blocks = (lay.m + 7) / 8 < 1184 ? (lay.m + 7) / 8 : 1184;
+    const int n_local = dims.n / dims.world;
+    // the reduce-scattered block starts at this rank's first row; the full accumulator at row 0
+    const int64_t src_off = (dzacc_src == ws.dzacc) ? 0 : (int64_t)dims.rank * 2 * n_local;
+    smh_inputs_t inp = in;
+    inp.n_local = in.n_local;
+    finalize_kernel<<<blocks, 256, 0, stream>>>(inp, dims.n, dims.d, dims.rank, ws.neg, ws.posd, ws.rowloss,
+                                                (Stats *)ws.stats, dzacc_src, src_off, 1.0f / temperature,
+                                                grad_scale, loss, dz1, dz2, dz_row_stride);
+    return check_launch("finalize_kernel");
+}
+
+// ----------------------------------------------------------------------------------------------
+// materialised weights
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+weights_dense_kernel(const int2 *__restrict__ tiles, const float *__restrict__ dist, const Stats *__restrict__ stats,
+                     float *__restrict__ neg_w, int m)
+{
+    const int2 ij = tiles[blockIdx.x];
+    const float *tile = dist + (int64_t)blockIdx.x * kTileFloats;
+    const float dmax = __uint_as_float(stats->dmax_bits);
+    const bool slow = stats->flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE);
+    const DivConst divw = make_div(dmax);
+    for (int idx = threadIdx.x; idx < kTileFloats; idx += 256) {
+        // direct orientation: consecutive threads walk a row of the output
+        int r = idx >> 7, c = idx & 127;
+        int gi = ij.x * kTile + r, gj = ij.y * kTile + c;
+        if (gi < m && gj < m) {
+            float dv = tile[dist_index(r, c)];
+            float num = __fsub_rn(dmax, dv);
+            neg_w[(int64_t)gi * m + gj] = slow ? __fdiv_rn(num, dmax) : div_fast(num, divw);
+        }
+        if (ij.x != ij.y) {
+            // mirrored orientation: element (c', r') of the stored tile lands at row J*128 + c', col I*128 + r'
+            int cc = idx >> 7, rr = idx & 127;
+            int gi2 = ij.y * kTile + cc, gj2 = ij.x * kTile + rr;
+            if (gi2 < m && gj2 < m) {
+                float dv = tile[dist_index(rr, cc)];
+                float num = __fsub_rn(dmax, dv);
+                neg_w[(int64_t)gi2 * m + gj2] = slow ? __fdiv_rn(num, dmax) : div_fast(num, divw);
+            }
+        }
+    }
+}
+
+__global__ void pos_weights_kernel(const float *__restrict__ posd, const Stats *__restrict__ stats,
+                                   float *__restrict__ pos_w, int n)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float pmax = __uint_as_float(stats->pmax_bits);
+    const float pmin = __uint_as_float(0x7fffffffu - stats->pmin_inv);
+    pos_w[k] = __fdiv_rn(__fsub_rn(pmax, posd[k]), __fsub_rn(pmax, pmin));
+}
+
+int launch_weights_dense(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
+                         float *pos_w, float *neg_w, cudaStream_t stream)
+{
+    if (pos_w) {
+        pos_weights_kernel<<<(dims.n + 255) / 256, 256, 0, stream>>>(ws.posd, (const Stats *)ws.stats, pos_w, dims.n);
+        int rc = check_launch("pos_weights_kernel");
+        if (rc) return rc;
+    }
+    if (neg_w && lay.n_stored_tiles > 0) {
+        weights_dense_kernel<<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.dist, (const Stats *)ws.stats,
+                                                                    neg_w, lay.m);
+        return check_launch("weights_dense_kernel");
+    }
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// K3: row-wise L2 normalisation
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+l2norm_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restrict__ norm, int64_t rows, int d,
+                  float eps)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wpb = blockDim.x >> 5;
+    const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+        const float *xr = x + row * d;
+        float *yr = y + row * d;
+        float ss = 0.f;
+        if (vec) {
+            for (int c = lane * 4; c < d; c += 128) {
+                float4 v = *reinterpret_cast<const float4 *>(xr + c);
+                ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+            }
+        } else {
+            for (int c = lane; c < d; c += 32) ss = fmaf(xr[c], xr[c], ss);
+        }
+        ss = warp_sum(ss);
+        const float nrm = sqrtf(ss);
+        const float inv = 1.0f / fmaxf(nrm, eps);
+        if (vec) {
+            for (int c = lane * 4; c < d; c += 128) {
+                float4 v = *reinterpret_cast<const float4 *>(xr + c);
+                *reinterpret_cast<float4 *>(yr + c) = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+            }
+        } else {
+            for (int c = lane; c < d; c += 32) yr[c] = xr[c] * inv;
+        }
+        if (norm && lane == 0) norm[row] = nrm;
+    }
+}
+
+// dx = (dy - y (y . dy)) / max(||x||, eps)   (for ||x|| >= eps; below eps F.normalize is a plain scale)
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float *__restrict__ y, const float *__restrict__ norm, const float *__restrict__ dy,
+                  float *__restrict__ dx, int64_t rows, int d, float eps)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wpb = blockDim.x >> 5;
+    for (int64_t row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+        const float *yr = y + row * d, *gr = dy + row * d;
+        float *xr = dx + row * d;
+        float dot = 0.f;
+        for (int c = lane; c < d; c += 32) dot = fmaf(yr[c], gr[c], dot);
+        dot = warp_sum(dot);
+        const float nrm = norm[row];
+        const float inv = 1.0f / fmaxf(nrm, eps);
+        if (nrm < eps) dot = 0.f;
+        for (int c = lane; c < d; c += 32) xr[c] = (gr[c] - yr[c] * dot) * inv;
+    }
+}
+
+int launch_l2norm_fwd(const float *x, float *y, float *norm, int64_t rows, int d, float eps, cudaStream_t stream)
+{
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    l2norm_fwd_kernel<<<(int)blocks, 256, 0, stream>>>(x, y, norm, rows, d, eps);
+    return check_launch("l2norm_fwd_kernel");
+}
+
+int launch_l2norm_bwd(const float *y, const float *norm, const float *dy, float *dx, int64_t rows, int d, float eps,
+                      cudaStream_t stream)
+{
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    l2norm_bwd_kernel<<<(int)blocks, 256, 0, stream>>>(y, norm, dy, dx, rows, d, eps);
+    return check_launch("l2norm_bwd_kernel");
+}
+
+}  // namespace smh

@@ -1,0 +1,52 @@
+// simhand_b200: declarations shared by the translation units of libsimhand_b200.so (host side).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/simhand_b200.h"
+
+namespace smh {
+
+struct WsView {                 // device pointers carved out of the caller's workspace blob
+    void *stats;                // Stats
+    float *zt;
+    float *jp;
+    float *posd;
+    float *neg;
+    float *rn;
+    float *rowloss;
+    float *dzacc;
+    float *dist;
+};
+
+struct PlanView {               // device pointers into the caller's plan blob
+    const int2 *tiles;          // (I, J) of each stored tile of this rank
+    const int4 *tasks;          // (row block, 64-col tile, stored tile, flags)
+    const int2 *strips;         // (first task, one-past-last task)
+};
+
+int set_error(int code, const char *fmt, ...);
+int check_launch(const char *what);
+
+// kernel launchers (one per translation unit)
+int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
+                bool round_tf32, cudaStream_t stream);
+int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
+                 cudaStream_t stream);
+int launch_sweep_fp32(bool backward, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
+                      const WsView &ws, float temperature, cudaStream_t stream);
+int launch_sweep_tc(bool backward, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
+                    const WsView &ws, float temperature, cudaStream_t stream);
+int launch_rn(const smh_layout_t &lay, const WsView &ws, cudaStream_t stream);
+int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
+                    const float *dzacc_src, float temperature, float grad_scale, float *loss, float *dz1,
+                    float *dz2, int64_t dz_row_stride, cudaStream_t stream);
+int launch_weights_dense(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
+                         float *pos_w, float *neg_w, cudaStream_t stream);
+int launch_l2norm_fwd(const float *x, float *y, float *norm, int64_t rows, int d, float eps, cudaStream_t stream);
+int launch_l2norm_bwd(const float *y, const float *norm, const float *dy, float *dx, int64_t rows, int d,
+                      float eps, cudaStream_t stream);
+int launch_selftest(int which, uint64_t *out, int64_t out_words, cudaStream_t stream);
+
+}  // namespace smh

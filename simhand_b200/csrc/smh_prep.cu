@@ -1,0 +1,137 @@
+// simhand_b200 K3a: input staging.
+//
+// One warp per sample row.  Replaces the torch.cat calls of src/models/utils.py:237-239 and :407 and the
+// positive-pair MPJPE of :229-231 (the weight normalisation of :233-235 happens in smh_finalize once the
+// global max/min are known).  Writes
+//   zt  : z rounded to tf32 (round-to-nearest) in the pre-swizzled 64-row block layout the sweeps stage
+//         with one linear bulk copy (smh_common.cuh: zt_index)
+//   jp  : joints packed as 10 x (x_k, x_k+1, y_k, y_k+1) + (x_20, y_20, 0, 0) per sample
+//   posd: D_{k,k+N}, with the exact operation order of the all-pairs kernel, so posd[k] is bitwise
+//         D[k, k+N]
+// and folds the fast-domain check of the exact sqrt into stats.flags.
+#include "smh_common.cuh"
+#include "smh_internal.h"
+
+namespace smh {
+
+__device__ __forceinline__ const float *sample_ptr(const float *base, int k, int n_local, int64_t rank_stride,
+                                                   int64_t row_stride)
+{
+    return base + (int64_t)(k / n_local) * rank_stride + (int64_t)(k % n_local) * row_stride;
+}
+
+__global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d, int mp, bool round_tf32,
+                                                   float *__restrict__ zt,
+                                                   float *__restrict__ jp, float *__restrict__ posd,
+                                                   Stats *__restrict__ stats)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int m = 2 * n;
+    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < mp; row += gridDim.x * warps_per_block) {
+        float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+        float jx = 0.f, jy = 0.f;
+        const bool live = row < m;
+        const int v = row >= n ? 1 : 0;
+        const int k = row - v * n;
+        if (live) {
+            const float *zp = sample_ptr(v ? in.z2_dev : in.z1_dev, k, in.n_local, in.z_rank_stride, in.z_row_stride);
+            const int c = 4 * lane;
+            if (c + 3 < d && ((reinterpret_cast<uintptr_t>(zp + c) & 15) == 0)) {
+                zv = *reinterpret_cast<const float4 *>(zp + c);
+            } else {
+                if (c + 0 < d) zv.x = zp[c + 0];
+                if (c + 1 < d) zv.y = zp[c + 1];
+                if (c + 2 < d) zv.z = zp[c + 2];
+                if (c + 3 < d) zv.w = zp[c + 3];
+            }
+            if (round_tf32) {
+                zv.x = to_tf32(zv.x);
+                zv.y = to_tf32(zv.y);
+                zv.z = to_tf32(zv.z);
+                zv.w = to_tf32(zv.w);
+            }
+            if (lane < kJ) {
+                const float *jb = sample_ptr(v ? in.j2_dev : in.j1_dev, k, in.n_local, in.j_rank_stride,
+                                             in.j_sample_stride) +
+                                  (int64_t)lane * in.j_joint_stride;
+                jx = jb[0];
+                jy = jb[in.j_coord_stride];
+            }
+        }
+        *reinterpret_cast<float4 *>(zt + zt_index(row, 4 * lane)) = zv;
+
+        // packed joints
+        float *jrow = jp + (int64_t)row * kJP;
+        if (lane < 20) {
+            int p = lane >> 1, u = lane & 1;
+            jrow[4 * p + u] = jx;
+            jrow[4 * p + 2 + u] = jy;
+        } else if (lane == 20) {
+            jrow[40] = jx;
+            jrow[41] = jy;
+        } else if (lane == 21) {
+            jrow[42] = 0.f;
+            jrow[43] = 0.f;
+        }
+
+        // domain of the branch-free exact sqrt: every coordinate is 0 or 2^-24 <= |c| <= 2^60, finite
+        uint32_t bad = 0;
+        if (live && lane < kJ) {
+            float ax = fabsf(jx), ay = fabsf(jy);
+            bool fin = (ax <= 3.0e38f) && (ay <= 3.0e38f);   // false for NaN/Inf
+            bool okx = (ax == 0.f) || (ax >= 5.9604645e-8f && ax <= 1.1529215e18f);
+            bool oky = (ay == 0.f) || (ay >= 5.9604645e-8f && ay <= 1.1529215e18f);
+            bad = (fin ? 0u : SMH_FLAG_NONFINITE) | ((okx && oky) ? 0u : SMH_FLAG_SLOW_DOMAIN);
+        }
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 16);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 8);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 4);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 2);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, 1);
+        if (bad && lane == 0) atomicOr(&stats->flags, bad);
+
+        // positive pair (k, k + N): utils.py:229-231, IEEE sqrt/div (any domain), ATen summation order
+        if (row < n) {
+            float nk = 0.f;
+            if (lane < kJ) {
+                const float *pb = sample_ptr(in.j2_dev, k, in.n_local, in.j_rank_stride, in.j_sample_stride) +
+                                  (int64_t)lane * in.j_joint_stride;
+                float dx = __fsub_rn(jx, pb[0]);
+                float dy = __fsub_rn(jy, pb[in.j_coord_stride]);
+                nk = __fsqrt_rn(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            }
+            float s = __shfl_sync(0xffffffffu, nk, 16);
+#pragma unroll
+            for (int q = 17; q <= 20; ++q) s = __fadd_rn(s, __shfl_sync(0xffffffffu, nk, q));
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                s = __fadd_rn(s, __fadd_rn(__shfl_sync(0xffffffffu, nk, q), __shfl_sync(0xffffffffu, nk, q + 8)));
+            if (lane == 0) {
+                float dk = __fdiv_rn(s, 21.0f);
+                posd[k] = dk;
+                uint32_t b = __float_as_uint(dk);
+                if (b <= 0x7f800000u) {     // non-negative, not NaN
+                    atomicMax(&stats->pmax_bits, b);
+                    atomicMax(&stats->pmin_inv, 0x7fffffffu - b);
+                } else {
+                    atomicOr(&stats->flags, SMH_FLAG_NONFINITE);
+                }
+            }
+        }
+    }
+}
+
+int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
+                bool round_tf32, cudaStream_t stream)
+{
+    // accumulators and stats are contiguous at the head of the workspace
+    cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)(lay.off_posd - lay.off_stats), stream);
+    if (e != cudaSuccess) return set_error((int)e, "prep memset: %s", cudaGetErrorString(e));
+    const int mp = lay.tiles_per_side * kTile;
+    const int blocks = (mp + 7) / 8;
+    prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, ws.zt, ws.jp, ws.posd, (Stats *)ws.stats);
+    return check_launch("prep_kernel");
+}
+
+}  // namespace smh

@@ -1,0 +1,103 @@
+"""Sharded weighted NT-Xent over the GPUs of one box (BASELINE.json configs[2]).
+
+One process per GPU (`torch.distributed`, NCCL over NVLink).  Every rank holds `n_local` samples of each
+view; the loss is the reference's loss on the concatenation of all local batches (global 2N samples).
+
+Per step and rank:
+  1. all-gather of one packed buffer [z1 | z2 | joints1 | joints2] (the autograd transpose of step 5)
+  2. smh_prep on the gathered batch, smh_mpjpe on this rank's share of the upper-triangular tiles
+  3. all-reduce(MAX) of three integers (Dmax, Pmax, -Pmin images)                 utils.py:233-234, :255
+  4. forward sweep over this rank's tasks -> partial row sums; all-reduce(SUM) of neg [2N]
+  5. backward sweep -> partial dz for all rows; reduce-scatter(SUM) -> dz of the local samples
+  6. smh_finalize: loss (identical on every rank) and the local gradients
+The MPJPE work is split by unordered tile pairs (each rank evaluates 1/P of the upper triangle), which is
+why the row sums and the gradient contributions of a rank touch all rows and the exchange steps 4 and 5 are
+real collectives rather than bookkeeping.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check
+from .ops import _as_f32, _stream_ptr, get_context, make_inputs
+
+
+def pack_local(z1, z2, joints1, joints2) -> torch.Tensor:
+    """[z1 | z2 | joints1 | joints2] of this rank as one flat fp32 buffer (joints as contiguous [n,21,2])."""
+    return torch.cat([_as_f32(z1).reshape(-1), _as_f32(z2).reshape(-1),
+                      _as_f32(joints1).contiguous().reshape(-1), _as_f32(joints2).contiguous().reshape(-1)])
+
+
+def gathered_views(gathered: torch.Tensor, world: int, n_local: int, d: int):
+    """Strided views of the all-gathered buffer with the reference's shapes: z1, z2 [N, d] and joints
+    [N, 21, 2] are not contiguous across ranks, so they are described by (rank_stride, row_stride);
+    returns the four base offsets (elements) and the chunk length."""
+    chunk = 2 * n_local * d + 2 * n_local * 42
+    assert gathered.numel() == world * chunk
+    off_z1, off_z2 = 0, n_local * d
+    off_j1, off_j2 = 2 * n_local * d, 2 * n_local * d + n_local * 42
+    return (off_z1, off_z2, off_j1, off_j2), chunk
+
+
+def sample_offset(k: int, n_local: int, rank_stride: int, row_stride: int) -> int:
+    """Element offset of global sample k inside a gathered segment (mirrors smh_inputs_t)."""
+    return (k // n_local) * rank_stride + (k % n_local) * row_stride
+
+
+def dz_out_row(i: int, n: int, n_local: int) -> int:
+    """Row of global sample row i (= v*N + k) in the rank-major gradient accumulator (smh_common.cuh)."""
+    v = 1 if i >= n else 0
+    k = i - v * n
+    return (k // n_local) * 2 * n_local + v * n_local + k % n_local
+
+
+def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, want_grad: bool,
+                     group: Optional[dist.ProcessGroup], grad_scale: float = 1.0, strip_len: int = 0):
+    lib = _lib.load()
+    eng = _lib.ENGINES[engine]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = z1.device
+    n_local, d = z1.shape
+    n = n_local * world
+    with torch.cuda.device(dev):
+        ctx = get_context(n, d, world, rank, dev, strip_len)
+        lay, dims = ctx.layout, ctx.dims
+        local = pack_local(z1, z2, joints1, joints2)
+        gathered = torch.empty(world * local.numel(), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gathered, local, group=group)
+        (o1, o2, oj1, oj2), chunk = gathered_views(gathered, world, n_local, d)
+        base = gathered.data_ptr()
+        inp = _lib.Inputs(base + 4 * o1, base + 4 * o2, d, base + 4 * oj1, base + 4 * oj2, 42, 2, 1,
+                          n_local, chunk, chunk)
+        ws = torch.empty(int(lay.ws_bytes), dtype=torch.uint8, device=dev)
+        st = _stream_ptr(dev)
+        pd, pi = ctypes.byref(dims), ctypes.byref(inp)
+        plan = ctx.plan_dev.data_ptr()
+        check(lib.smh_prep(pd, pi, ws.data_ptr(), eng, st), "smh_prep")
+        check(lib.smh_mpjpe(pd, plan, ws.data_ptr(), st), "smh_mpjpe")
+        stats3 = ctx.view(ws, lay.off_stats, 3, torch.int32)
+        dist.all_reduce(stats3, op=dist.ReduceOp.MAX, group=group)
+        check(lib.smh_forward(pd, plan, ws.data_ptr(), temperature, eng, st), "smh_forward")
+        neg = ctx.view(ws, lay.off_neg, lay.m)
+        dist.all_reduce(neg, op=dist.ReduceOp.SUM, group=group)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dz1 = dz2 = None
+        dz_local = None
+        if want_grad:
+            check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng, st), "smh_backward")
+            dzacc = ctx.view(ws, lay.off_dzacc, lay.m * 128)
+            dz_local = torch.empty(2 * n_local * 128, dtype=torch.float32, device=dev)
+            dist.reduce_scatter_tensor(dz_local, dzacc, op=dist.ReduceOp.SUM, group=group)
+            dz1 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
+            dz2 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
+        check(lib.smh_finalize(pd, pi, ws.data_ptr(), dz_local.data_ptr() if want_grad else None, temperature,
+                               grad_scale, loss.data_ptr(), dz1.data_ptr() if want_grad else None,
+                               dz2.data_ptr() if want_grad else None, d, st), "smh_finalize")
+        # keep the gathered inputs alive until the stream has consumed them
+        gathered.record_stream(torch.cuda.current_stream(dev))
+    return loss, dz1, dz2

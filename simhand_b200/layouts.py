@@ -1,0 +1,83 @@
+"""Host-side (numpy) mirrors of the HBM layouts and the task plan of libsimhand_b200.so.
+
+Used by the CPU tests to check the plan (every ordered pair of samples is covered exactly once, ranks are
+balanced) and the index arithmetic shared by the kernels (`smh_common.cuh`), and handy when inspecting a
+workspace dumped from the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+TILE = 128
+TASK_N = 64
+TILE_FLOATS = TILE * TILE
+BLOCK_ROWS = 64
+BLOCK_FLOATS = BLOCK_ROWS * 128
+JP = 44
+PIECE_PITCH = 1040 // 4          # floats: one staged piece (64 rows x 4 floats) + 16 B pad
+
+TASK_TRANSPOSED, TASK_DIAGONAL, TASK_RAGGED = 1, 2, 4
+
+
+def zt_index(row, col):
+    """float index of z[row, col] in the pre-swizzled 64-row block image (SWIZZLE_128B, K-major)."""
+    row, col = np.asarray(row), np.asarray(col)
+    blk, r = row // BLOCK_ROWS, row % BLOCK_ROWS
+    kb, cc = col >> 5, col & 31
+    chunk = (cc >> 2) ^ (r & 7)
+    return blk * BLOCK_FLOATS + kb * (BLOCK_ROWS * 32) + r * 32 + chunk * 4 + (cc & 3)
+
+
+def dist_index(row, col):
+    """float index of D[row, col] inside a stored 128x128 tile: [row/64][col/4][row%64][col%4]."""
+    row, col = np.asarray(row), np.asarray(col)
+    return ((((row >> 6) * 32 + (col >> 2)) * 64) + (row & 63)) * 4 + (col & 3)
+
+
+def jp_index(joint, coord):
+    """float index of (joint, coord) in a packed 44-float joint row."""
+    if joint == 20:
+        return 40 + coord
+    return 4 * (joint // 2) + 2 * coord + (joint % 2)
+
+
+def parse_plan(plan_bytes: np.ndarray):
+    """Decodes a plan blob built by smh_plan_build into (header dict, tiles[n,2], tasks[n,4], strips[n,2])."""
+    hdr = np.frombuffer(plan_bytes[:64].tobytes(), dtype=np.uint32)
+    names = ("magic", "m", "world", "rank", "tiles_per_side", "n_stored", "n_tasks", "n_strips", "strip_len",
+             "off_tiles", "off_tasks", "off_strips")
+    h = {k: int(v) for k, v in zip(names, hdr)}
+    raw = plan_bytes.tobytes()
+    tiles = np.frombuffer(raw, np.int32, h["n_stored"] * 2, h["off_tiles"]).reshape(-1, 2)
+    tasks = np.frombuffer(raw, np.int32, h["n_tasks"] * 4, h["off_tasks"]).reshape(-1, 4)
+    strips = np.frombuffer(raw, np.int32, h["n_strips"] * 2, h["off_strips"]).reshape(-1, 2)
+    return h, tiles, tasks, strips
+
+
+def build_plan(n: int, d: int = 128, world: int = 1, rank: int = 0, strip_len: int = 0):
+    from . import _lib
+    lib = _lib.load()
+    dims = _lib.Dims(n, d, world, rank, strip_len)
+    lay = _lib.Layout()
+    _lib.check(lib.smh_layout(ctypes.byref(dims), ctypes.byref(lay)), "smh_layout")
+    buf = np.zeros(int(lay.plan_bytes), np.uint8)
+    _lib.check(lib.smh_plan_build(ctypes.byref(dims), buf.ctypes.data, buf.size), "smh_plan_build")
+    return lay, parse_plan(buf)
+
+
+def staged_piece_source(task, lane: int) -> int:
+    """Which 1 KiB piece of the stored tile the producer copies into staged slot `lane` (smh_sweep_tc.cu)."""
+    half = task[1] & 1
+    if task[3] & TASK_TRANSPOSED:
+        return half * 32 + lane
+    return (lane >> 4) * 32 + half * 16 + (lane & 15)
+
+
+def staged_read(stage: np.ndarray, task, r: int, jl: int) -> float:
+    """The value the epilogue thread of row r reads for task column jl from the staged pieces
+    (`stage` is [32, PIECE_PITCH] floats)."""
+    if task[3] & TASK_TRANSPOSED:
+        return stage[r >> 2, jl * 4 + (r & 3)]
+    return stage[(r >> 6) * 16 + (jl >> 2), (r & 63) * 4 + (jl & 3)]

@@ -1,0 +1,306 @@
+"""Host mirror of the reference's loss operator (`src/models/utils.py`), backed by libsimhand_b200.so.
+
+Drop-in names, argument meaning and reduction follow the reference:
+
+    get_weights_linear(joints1, joints2, diff_type)                       utils.py:218-261
+    vanila_weights_contrastive_loss(z1, z2, pos_w, neg_w, temperature)    utils.py:391-427
+
+`get_weights_linear` returns two lazy handles (they only remember the joints); handing them to
+`vanila_weights_contrastive_loss` runs the fused CUDA path, in which the [2N, 2N] weight and logit
+matrices are never materialised.  `handle.materialize()` gives the real tensors with the reference's
+shapes (pos_w [N], neg_w [2N, 2N]) computed by the same kernels.  `weighted_ntxent` is the one-call
+fused form used by the benchmark and by the sharded path (simhand_b200/dist.py).
+
+There is no CPU or eager-PyTorch fallback: inputs must live on a CUDA (sm_100) device.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Dims, Inputs, Layout, check
+
+_DEFAULT_ENGINE = "tf32"
+_ctx_lock = threading.Lock()
+_ctx_cache = {}
+
+
+class _Context:
+    """Layout + device copy of the task plan for one (n, d, world, rank, strip_len, device)."""
+
+    def __init__(self, n: int, d: int, world: int, rank: int, strip_len: int, device: torch.device):
+        lib = _lib.load()
+        self.dims = Dims(n, d, world, rank, strip_len)
+        self.layout = Layout()
+        check(lib.smh_layout(ctypes.byref(self.dims), ctypes.byref(self.layout)), "smh_layout")
+        host = torch.empty(int(self.layout.plan_bytes), dtype=torch.uint8).pin_memory() \
+            if device.type == "cuda" else torch.empty(int(self.layout.plan_bytes), dtype=torch.uint8)
+        check(lib.smh_plan_build(ctypes.byref(self.dims), host.data_ptr(), host.numel()), "smh_plan_build")
+        self.plan_host = host
+        self.plan_dev = host.to(device) if device.type == "cuda" else None
+        self.device = device
+
+    def view(self, ws: torch.Tensor, off: int, count: int, dtype=torch.float32) -> torch.Tensor:
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        return ws[off:off + nbytes].view(dtype)
+
+
+def get_context(n: int, d: int, world: int, rank: int, device, strip_len: int = 0) -> _Context:
+    device = torch.device(device)
+    key = (n, d, world, rank, strip_len, device.type, device.index)
+    with _ctx_lock:
+        ctx = _ctx_cache.get(key)
+        if ctx is None:
+            ctx = _Context(n, d, world, rank, strip_len, device)
+            _ctx_cache[key] = ctx
+    return ctx
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"simhand_b200: `{name}` is on {t.device}; the op runs only on a CUDA sm_100 device "
+            "(there is no CPU fallback)")
+
+
+def _as_f32(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def make_inputs(z1, z2, joints1, joints2, n_local: Optional[int] = None, z_rank_stride: int = 0,
+                j_rank_stride: int = 0) -> Tuple[Inputs, tuple]:
+    """Describes the caller's tensors to the library without copying them: z rows may be strided,
+    joints may be any strided `[N, 21, 2]` view (the reference passes `joints[:, :, :2]`)."""
+    z1, z2 = _as_f32(z1), _as_f32(z2)
+    joints1, joints2 = _as_f32(joints1), _as_f32(joints2)
+    if z1.dim() != 2 or z1.shape != z2.shape:
+        raise ValueError(f"z1/z2 must be [N, d] with equal shapes, got {tuple(z1.shape)} / {tuple(z2.shape)}")
+    if joints1.shape != joints2.shape or joints1.dim() != 3 or joints1.shape[1:] != (21, 2):
+        raise ValueError(f"joints must be [N, 21, 2], got {tuple(joints1.shape)} / {tuple(joints2.shape)}")
+    if z1.stride(1) != 1 or z2.stride(1) != 1 or z1.stride(0) != z2.stride(0):
+        z1, z2 = z1.contiguous(), z2.contiguous()
+    if joints1.stride() != joints2.stride():
+        joints1, joints2 = joints1.contiguous(), joints2.contiguous()
+    n = z1.shape[0]
+    inp = Inputs(z1.data_ptr(), z2.data_ptr(), z1.stride(0) if n > 1 else z1.shape[1],
+                 joints1.data_ptr(), joints2.data_ptr(),
+                 joints1.stride(0), joints1.stride(1), joints1.stride(2),
+                 n if n_local is None else n_local, z_rank_stride, j_rank_stride)
+    return inp, (z1, z2, joints1, joints2)       # keep the (possibly new) tensors alive
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _DEFAULT_ENGINE,
+             want_grad: bool = True, grad_scale: float = 1.0, strip_len: int = 0, return_aux: bool = False):
+    """One fused fwd(+bwd) step on a single GPU.  Returns (loss[()], dz1, dz2[, aux])."""
+    for t, nm in ((z1, "z1"), (z2, "z2"), (joints1, "joints1"), (joints2, "joints2")):
+        _require_cuda(t, nm)
+    lib = _lib.load()
+    eng = _lib.ENGINES[engine]
+    dev = z1.device
+    n, d = z1.shape
+    with torch.cuda.device(dev):
+        ctx = get_context(n, d, 1, 0, dev, strip_len)
+        lay, dims = ctx.layout, ctx.dims
+        inp, keep = make_inputs(z1, z2, joints1, joints2)
+        ws = torch.empty(int(lay.ws_bytes), dtype=torch.uint8, device=dev)
+        st = _stream_ptr(dev)
+        pd, pi = ctypes.byref(dims), ctypes.byref(inp)
+        check(lib.smh_prep(pd, pi, ws.data_ptr(), eng, st), "smh_prep")
+        check(lib.smh_mpjpe(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), st), "smh_mpjpe")
+        check(lib.smh_forward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, eng, st), "smh_forward")
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dz1 = dz2 = None
+        if want_grad:
+            check(lib.smh_backward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, eng, st), "smh_backward")
+            dz1 = torch.empty((n, d), dtype=torch.float32, device=dev)
+            dz2 = torch.empty((n, d), dtype=torch.float32, device=dev)
+        check(lib.smh_finalize(pd, pi, ws.data_ptr(), None, temperature, grad_scale, loss.data_ptr(),
+                               dz1.data_ptr() if want_grad else None, dz2.data_ptr() if want_grad else None,
+                               d, st), "smh_finalize")
+        del keep
+        if return_aux:
+            aux = dict(ws=ws, ctx=ctx, neg=ctx.view(ws, lay.off_neg, lay.m),
+                       stats=ctx.view(ws, lay.off_stats, 8, torch.int32),
+                       posd=ctx.view(ws, lay.off_posd, n))
+            return loss, dz1, dz2, aux
+    return loss, dz1, dz2
+
+
+class _WeightedNTXentFn(torch.autograd.Function):
+    """loss = weighted NT-Xent(z1, z2 | joints1, joints2); the backward sweep runs inside forward (the
+    gradient w.r.t. z is what a training step needs), backward() only scales the saved gradients."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, z1, z2, joints1, joints2, temperature, engine, group):
+        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        if group is None:
+            loss, dz1, dz2 = run_step(z1, z2, joints1, joints2, temperature, engine, want)
+        else:
+            from .dist import run_step_sharded
+            loss, dz1, dz2 = run_step_sharded(z1, z2, joints1, joints2, temperature, engine, want, group)
+        if want:
+            ctx.save_for_backward(dz1, dz2)
+        return loss
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        dz1, dz2 = ctx.saved_tensors
+        g1 = grad_out * dz1 if ctx.needs_input_grad[0] else None
+        g2 = grad_out * dz2 if ctx.needs_input_grad[1] else None
+        return g1, g2, None, None, None, None, None
+
+
+def weighted_ntxent(z1: torch.Tensor, z2: torch.Tensor, joints1: torch.Tensor, joints2: torch.Tensor,
+                    temperature: float = 0.5, group=None, engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
+    """Fused similarity-weighted NT-Xent (weight_type linear, diff_type mpjpe, pos_neg): equals
+    `vanila_weights_contrastive_loss(z1, z2, *get_weights_linear(joints1, joints2, 'mpjpe'), temperature)`
+    of the reference.  With `group` (a torch.distributed process group) the batch is the concatenation of
+    every rank's local batch and the work is sharded over the ranks."""
+    return _WeightedNTXentFn.apply(z1, z2, joints1, joints2, float(temperature), engine, group)
+
+
+# ----------------------------------------------------------------------------------------------------
+# the reference's two-call API
+# ----------------------------------------------------------------------------------------------------
+class _WeightSource:
+    def __init__(self, joints1, joints2):
+        self.joints1, self.joints2 = joints1, joints2
+        self._dense = None
+
+    def dense(self):
+        if self._dense is None:
+            self._dense = mpjpe_weights(self.joints1, self.joints2)
+        return self._dense
+
+
+class LazyWeights:
+    """Stand-in for one of the two tensors `get_weights_linear` returns.  Behaves like the tensor on
+    demand (`materialize()`, attribute access), but the fused loss never needs the values."""
+
+    def __init__(self, source: _WeightSource, kind: str):
+        self._source, self.kind = source, kind
+
+    def materialize(self) -> torch.Tensor:
+        pos_w, neg_w = self._source.dense()
+        return pos_w if self.kind == "pos" else neg_w
+
+    @property
+    def shape(self):
+        n = self._source.joints1.shape[0]
+        return torch.Size([n]) if self.kind == "pos" else torch.Size([2 * n, 2 * n])
+
+    def __getattr__(self, name):            # anything else: act on the real tensor
+        return getattr(self.materialize(), name)
+
+    def __repr__(self):
+        return f"LazyWeights(kind={self.kind!r}, shape={tuple(self.shape)})"
+
+
+def mpjpe_weights(joints1: torch.Tensor, joints2: torch.Tensor, strip_len: int = 0):
+    """Materialised (pos_w [N], neg_w [2N, 2N]) exactly as `get_weights_linear(j1, j2, 'mpjpe')` returns
+    them, from the CUDA kernels (prep -> MPJPE tiles -> dense expansion)."""
+    _require_cuda(joints1, "joints1")
+    _require_cuda(joints2, "joints2")
+    lib = _lib.load()
+    dev = joints1.device
+    n = joints1.shape[0]
+    with torch.cuda.device(dev):
+        ctx = get_context(n, 1, 1, 0, dev, strip_len)
+        zero = torch.zeros((n, 1), dtype=torch.float32, device=dev)
+        inp, keep = make_inputs(zero, zero, joints1, joints2)
+        ws = torch.empty(int(ctx.layout.ws_bytes), dtype=torch.uint8, device=dev)
+        st = _stream_ptr(dev)
+        pd = ctypes.byref(ctx.dims)
+        check(lib.smh_prep(pd, ctypes.byref(inp), ws.data_ptr(), _lib.ENGINE_FP32, st), "smh_prep")
+        check(lib.smh_mpjpe(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), st), "smh_mpjpe")
+        pos_w = torch.empty(n, dtype=torch.float32, device=dev)
+        neg_w = torch.empty((2 * n, 2 * n), dtype=torch.float32, device=dev)
+        check(lib.smh_weights_dense(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), pos_w.data_ptr(),
+                                    neg_w.data_ptr(), st), "smh_weights_dense")
+        del keep
+    return pos_w, neg_w
+
+
+def get_weights_linear(joints1: torch.Tensor, joints2: torch.Tensor, diff_type: str):
+    """Drop-in for `src/models/utils.py:218` (`diff_type == 'mpjpe'`, the configuration of the hot path).
+    Returns `(pos_weights, neg_weights)` as lazy handles."""
+    if diff_type != "mpjpe":
+        raise NotImplementedError(
+            f"simhand_b200.get_weights_linear: diff_type {diff_type!r} is outside the accelerated path "
+            "(only 'mpjpe'); keep the reference function for it")
+    src = _WeightSource(joints1, joints2)
+    return LazyWeights(src, "pos"), LazyWeights(src, "neg")
+
+
+def vanila_weights_contrastive_loss(z1: torch.Tensor, z2: torch.Tensor, pos_weights, neg_weights,
+                                    temperature: float = 0.5, engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
+    """Drop-in for `src/models/utils.py:391`: mean-reduced weighted NT-Xent, differentiable in z1, z2."""
+    if isinstance(pos_weights, LazyWeights) and isinstance(neg_weights, LazyWeights):
+        if pos_weights._source is not neg_weights._source or pos_weights.kind != "pos" or neg_weights.kind != "neg":
+            raise ValueError("pos_weights / neg_weights must come from the same get_weights_linear call")
+        src = pos_weights._source
+        if src.joints1.shape[0] != z1.shape[0]:
+            raise ValueError(f"weights were built for batch {src.joints1.shape[0]}, z1 has {z1.shape[0]}")
+        return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine)
+    raise NotImplementedError(
+        "simhand_b200.vanila_weights_contrastive_loss: dense weight tensors are not accepted yet; pass the "
+        "handles returned by simhand_b200.get_weights_linear (fused path)")
+
+
+def install(*modules) -> None:
+    """Rebinds `get_weights_linear` / `vanila_weights_contrastive_loss` in the given modules (the reference's
+    `src.models.utils` and the model modules that imported the names: simhand_w_model, peclr_w_model,
+    simclr_w_model).  See INTEGRATION.md."""
+    for mod in modules:
+        for name, fn in (("get_weights_linear", get_weights_linear),
+                         ("vanila_weights_contrastive_loss", vanila_weights_contrastive_loss)):
+            if hasattr(mod, name):
+                setattr(mod, name, fn)
+
+
+# ----------------------------------------------------------------------------------------------------
+# K3: L2 normalisation
+# ----------------------------------------------------------------------------------------------------
+class _L2NormFn(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, eps):
+        _require_cuda(x, "x")
+        lib = _lib.load()
+        x = x.contiguous()
+        rows, d = x.shape
+        y = torch.empty_like(x)
+        norm = torch.empty(rows, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.smh_l2norm_fwd(x.data_ptr(), y.data_ptr(), norm.data_ptr(), rows, d, eps,
+                                     _stream_ptr(x.device)), "smh_l2norm_fwd")
+        ctx.save_for_backward(y, norm)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        y, norm = ctx.saved_tensors
+        lib = _lib.load()
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            check(lib.smh_l2norm_bwd(y.data_ptr(), norm.data_ptr(), dy.data_ptr(), dx.data_ptr(), y.shape[0],
+                                     y.shape[1], ctx.eps, _stream_ptr(y.device)), "smh_l2norm_bwd")
+        return dx, None
+
+
+def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """`torch.nn.functional.normalize(x, dim=1)` for `[B, d]` fp32 (simhand_w_model.py:56-58, 91-93)."""
+    return _L2NormFn.apply(x, float(eps))

@@ -1,0 +1,117 @@
+"""CPU tests of the host side of the C ABI: library loads, exports every declared symbol, argument
+validation, and the task plan / layout arithmetic (no kernel launches)."""
+import ctypes
+import re
+import os
+
+import numpy as np
+import pytest
+
+from simhand_b200 import _lib, layouts as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "simhand_b200.h")).read()
+    declared = set(re.findall(r"\b(smh_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.smh_version() == 100
+
+
+def test_struct_sizes_match_header():
+    assert ctypes.sizeof(_lib.Dims) == 20
+    assert ctypes.sizeof(_lib.Stats) == 32
+    assert ctypes.sizeof(_lib.Layout) == 11 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.Inputs) == 88
+
+
+@pytest.mark.parametrize("args,code", [((0, 128, 1, 0), -1), ((8, 129, 1, 0), -2), ((8, 0, 1, 0), -2),
+                                       ((8, 128, 2, 2), -2), ((9, 128, 2, 0), -2)])
+def test_layout_rejects_bad_dims(args, code):
+    lib = _lib.load()
+    dims, lay = _lib.Dims(*args, 0), _lib.Layout()
+    assert lib.smh_layout(ctypes.byref(dims), ctypes.byref(lay)) == code
+    assert lib.smh_last_error()
+
+
+def test_compute_calls_reject_null_workspace_without_gpu():
+    lib = _lib.load()
+    dims = _lib.Dims(8, 128, 1, 0, 0)
+    assert lib.smh_mpjpe(ctypes.byref(dims), None, None, None) == -1
+    assert lib.smh_forward(ctypes.byref(dims), None, None, 0.5, 0, None) == -1
+    assert lib.smh_l2norm_fwd(None, None, None, 4, 4, 1e-12, None) == -1
+
+
+@pytest.mark.parametrize("n,world", [(3, 1), (64, 1), (96, 1), (200, 1), (256, 1), (256, 2), (1024, 8),
+                                     (330, 2), (8192, 8)])
+def test_plan_covers_every_ordered_pair_once(n, world):
+    m = 2 * n
+    tp = (m + 127) // 128
+    cover = np.zeros((tp, 2 * tp), np.int32)          # (row block, 64-col tile)
+    stored = np.zeros((tp, tp), np.int32)
+    per_rank = []
+    for rank in range(world):
+        lay, (h, tiles, tasks, strips) = L.build_plan(n, 128, world, rank)
+        assert h["magic"] == 0x534D4831 and h["m"] == m
+        per_rank.append(len(tiles))
+        for I, J in tiles:
+            assert I <= J
+            stored[I, J] += 1
+        for row, cj, lt, flags in tasks:
+            I, J = tiles[lt]
+            if flags & L.TASK_TRANSPOSED:
+                assert row == J and cj // 2 == I and I != J
+            else:
+                assert row == I and cj // 2 == J
+                assert bool(flags & L.TASK_DIAGONAL) == (I == J)
+            ragged = (row * 128 + 128 > m) or (cj * 64 + 64 > m)
+            assert bool(flags & L.TASK_RAGGED) == ragged
+            cover[row, cj] += 1
+        # strips partition the task list and never mix row blocks
+        assert strips[0, 0] == 0 and strips[-1, 1] == len(tasks)
+        assert (strips[1:, 0] == strips[:-1, 1]).all()
+        for a, b in strips:
+            assert 0 < b - a <= lay.strip_len
+            assert len(set(tasks[a:b, 0])) == 1
+    assert (stored[np.triu_indices(tp)] == 1).all() and stored.sum() == tp * (tp + 1) // 2
+    live = np.array([[cj * 64 < m for cj in range(2 * tp)]] * tp)
+    assert (cover[live] == 1).all() and (cover[~live] == 0).all()
+    if tp >= 2 * world:
+        assert max(per_rank) - min(per_rank) <= tp + 1      # balanced over ranks
+
+
+def test_layout_indices_are_bijections():
+    r, c = np.meshgrid(np.arange(128), np.arange(128), indexing="ij")
+    assert sorted(L.dist_index(r, c).ravel()) == list(range(128 * 128))
+    r, c = np.meshgrid(np.arange(192), np.arange(128), indexing="ij")
+    assert sorted(L.zt_index(r, c).ravel()) == list(range(192 * 128))
+    # a 16-byte chunk stays together and lands in the XOR-swizzled slot of its 128-byte row
+    assert L.zt_index(5, 8) == 5 * 32 + ((2 ^ 5) * 4)
+    assert sorted(L.jp_index(j, c) for j in range(21) for c in range(2)) == list(range(40)) + [40, 41]
+
+
+def test_staged_tile_reads_match_matrix():
+    """Producer piece mapping + epilogue reads (smh_sweep_tc.cu) reproduce D[gi, gj] for every task."""
+    n = 200
+    m = 2 * n
+    rng = np.random.default_rng(0)
+    dfull = rng.random((512, 512)).astype(np.float32)
+    dfull = np.triu(dfull) + np.triu(dfull, 1).T             # symmetric like the MPJPE matrix
+    lay, (h, tiles, tasks, strips) = L.build_plan(n)
+    r, c = np.meshgrid(np.arange(128), np.arange(128), indexing="ij")
+    store = np.zeros((len(tiles), L.TILE_FLOATS), np.float32)
+    for lt, (I, J) in enumerate(tiles):
+        store[lt, L.dist_index(r, c)] = dfull[I * 128:(I + 1) * 128, J * 128:(J + 1) * 128]
+    for task in tasks:
+        row, cj, lt, flags = task
+        stage = np.full((32, L.PIECE_PITCH), np.nan, np.float32)
+        for lane in range(32):
+            p = L.staged_piece_source(task, lane)
+            stage[lane, :256] = store[lt, p * 256:(p + 1) * 256]
+        for rr in (0, 1, 5, 63, 64, 77, 127):
+            for jl in (0, 3, 4, 31, 32, 63):
+                assert L.staged_read(stage, task, rr, jl) == dfull[row * 128 + rr, cj * 64 + jl]
