@@ -299,7 +299,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--engine", default="tf32", choices=["tf32", "fp32", "auto"])
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 30)

@@ -65,6 +65,7 @@ typedef struct smh_layout {
     int64_t plan_bytes;          /* size of the task plan (host build, device copy by the caller) */
     int64_t off_stats;           /* smh_stats_t */
     int64_t off_zt;              /* [Tp*128][128] fp32, tf32-rounded z, pre-swizzled 64-row blocks */
+    int64_t off_zb;              /* [Tp*128][128] bf16 copy of z, pre-swizzled 64-row blocks (backward value operand) */
     int64_t off_jp;              /* [Tp*128][44] fp32 packed joints */
     int64_t off_posd;            /* [N] fp32 positive-pair MPJPE */
     int64_t off_neg;             /* [Tp*128] fp32 off-diagonal row sums (partial until all-reduced) */
@@ -162,10 +163,11 @@ int smh_l2norm_bwd(const float *y_dev, const float *norm_dev, const float *dy_de
  * checks).  out_dev receives test-specific counters. */
 int smh_selftest(int which, uint64_t *out_dev, int64_t out_words, void *stream);
 
-/* diagnostic: one tcgen05 tile S = A B^T and dZ = tf32(S) Z_B on staged z blocks with caller-supplied
- * descriptor fields (see smh_selftest.cu); tests/ pins the encodings hard-coded in the sweeps with it. */
-int smh_tc_probe(const float *zt_dev, int blk_a, int blk_b, const uint32_t *params16_host, float *s_out_dev,
-                 float *dz_out_dev, uint32_t *fail_dev, void *stream);
+/* diagnostic: one tcgen05 tile S = A B^T (tf32) and dZ = bf16(S) Z_B (bf16 value operand, MN-major) on staged
+ * z blocks with caller-supplied descriptor fields (see smh_selftest.cu); tests/ pins the encodings hard-coded
+ * in the sweeps with it. */
+int smh_tc_probe(const float *zt_dev, const void *zb_dev, int blk_a, int blk_b, const uint32_t *params16_host,
+                 float *s_out_dev, uint32_t *g_out_dev, float *dz_out_dev, uint32_t *fail_dev, void *stream);
 void smh_tc_default_params(uint32_t *params16_host);
 
 #ifdef __cplusplus

@@ -25,7 +25,7 @@ class Dims(ctypes.Structure):
 
 class Layout(ctypes.Structure):
     _fields_ = [("ws_bytes", ctypes.c_int64), ("plan_bytes", ctypes.c_int64), ("off_stats", ctypes.c_int64),
-                ("off_zt", ctypes.c_int64), ("off_jp", ctypes.c_int64), ("off_posd", ctypes.c_int64),
+                ("off_zt", ctypes.c_int64), ("off_zb", ctypes.c_int64), ("off_jp", ctypes.c_int64), ("off_posd", ctypes.c_int64),
                 ("off_neg", ctypes.c_int64), ("off_rn", ctypes.c_int64), ("off_rowloss", ctypes.c_int64),
                 ("off_dzacc", ctypes.c_int64), ("off_dist", ctypes.c_int64),
                 ("m", ctypes.c_int32), ("tiles_per_side", ctypes.c_int32), ("n_stored_tiles", ctypes.c_int32),
@@ -78,7 +78,7 @@ def load() -> ctypes.CDLL:
     lib.smh_l2norm_fwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     lib.smh_l2norm_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]
     lib.smh_selftest.argtypes = [ctypes.c_int, vp, i64, vp]
-    lib.smh_tc_probe.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), vp, vp, vp, vp]
+    lib.smh_tc_probe.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), vp, vp, vp, vp, vp]
     lib.smh_tc_default_params.argtypes = [ctypes.POINTER(ctypes.c_uint32)]
     lib.smh_tc_default_params.restype = None
     for name in EXPORTS:

@@ -142,6 +142,7 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     lay->off_dzacc = take(mp * kD * 4);
     lay->off_posd = take((int64_t)dims.n * 4);
     lay->off_zt = take(mp * kD * 4);
+    lay->off_zb = take(mp * kD * 2);
     lay->off_jp = take(mp * kJP * 4);
     lay->off_dist = take((int64_t)lay->n_stored_tiles * kTileFloats * 4);
     lay->ws_bytes = off;
@@ -159,6 +160,7 @@ static WsView carve(void *ws, const smh_layout_t &lay)
     WsView v;
     v.stats = b + lay.off_stats;
     v.zt = (float *)(b + lay.off_zt);
+    v.zb = (uint16_t *)(b + lay.off_zb);
     v.jp = (float *)(b + lay.off_jp);
     v.posd = (float *)(b + lay.off_posd);
     v.neg = (float *)(b + lay.off_neg);
@@ -261,7 +263,7 @@ int smh_plan_build(const smh_dims_t *dims, void *plan_host, int64_t plan_bytes)
 #define SMH_COMMON_PROLOGUE(need_plan)                                                      \
     int rc = validate_dims(dims);                                                           \
     if (rc) return rc;                                                                      \
-    if ((rc = check_ptr(ws_dev, "workspace", 1024))) return rc;                             \
+    if ((rc = check_ptr(ws_dev, "workspace", 256))) return rc;                             \
     if (need_plan && (rc = check_ptr(plan_dev, "plan", 16))) return rc;                     \
     smh_layout_t lay;                                                                       \
     compute_layout(*dims, &lay, nullptr);                                                   \

@@ -11,6 +11,7 @@ namespace smh {
 struct WsView {                 // device pointers carved out of the caller's workspace blob
     void *stats;                // Stats
     float *zt;
+    uint16_t *zb;
     float *jp;
     float *posd;
     float *neg;

@@ -5,6 +5,7 @@
 // global max/min are known).  Writes
 //   zt  : z rounded to tf32 (round-to-nearest) in the pre-swizzled 64-row block layout the sweeps stage
 //         with one linear bulk copy (smh_common.cuh: zt_index)
+//   zb  : bf16 copy of z in the pre-swizzled block layout the backward sweep reads MN-major (zb_index)
 //   jp  : joints packed as 10 x (x_k, x_k+1, y_k, y_k+1) + (x_20, y_20, 0, 0) per sample
 //   posd: D_{k,k+N}, with the exact operation order of the all-pairs kernel, so posd[k] is bitwise
 //         D[k, k+N]
@@ -21,7 +22,7 @@ __device__ __forceinline__ const float *sample_ptr(const float *base, int k, int
 }
 
 __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d, int mp, bool round_tf32,
-                                                   float *__restrict__ zt,
+                                                   float *__restrict__ zt, uint16_t *__restrict__ zb,
                                                    float *__restrict__ jp, float *__restrict__ posd,
                                                    Stats *__restrict__ stats)
 {
@@ -60,6 +61,8 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
             }
         }
         *reinterpret_cast<float4 *>(zt + zt_index(row, 4 * lane)) = zv;
+        // bf16 copy (value operand of dz += G z): 4 consecutive columns = 8 bytes inside one 16-byte chunk
+        *reinterpret_cast<uint2 *>(zb + zb_index(row, 4 * lane)) = make_uint2(pack_bf16x2(zv.x, zv.y), pack_bf16x2(zv.z, zv.w));
 
         // packed joints
         float *jrow = jp + (int64_t)row * kJP;
@@ -130,7 +133,7 @@ int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_input
     if (e != cudaSuccess) return set_error((int)e, "prep memset: %s", cudaGetErrorString(e));
     const int mp = lay.tiles_per_side * kTile;
     const int blocks = (mp + 7) / 8;
-    prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, ws.zt, ws.jp, ws.posd, (Stats *)ws.stats);
+    prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, ws.zt, ws.zb, ws.jp, ws.posd, (Stats *)ws.stats);
     return check_launch("prep_kernel");
 }
 

@@ -145,11 +145,11 @@ int launch_selftest(int which, uint64_t *out, int64_t out_words, cudaStream_t st
 
 // ----------------------------------------------------------------------------------------------
 // tcgen05 probe: one CTA computes S = A B^T (kind::tf32, both operands K-major SWIZZLE_128B from the staged
-// z blocks) and then dZ = tf32(S) Z_B (A operand from TMEM, B operand the same staged block read MN-major),
-// with every descriptor field supplied by the caller.  tests/ uses it to pin the descriptor encodings the
-// sweep kernels hard-code (smh_sweep_tc.cu) against a host matmul.
+// tf32 z blocks) and then dZ = bf16(S) Z_B (kind::f16: A operand = packed bf16 in TMEM, B operand = the staged
+// bf16 block read MN-major), with every descriptor field supplied by the caller.  tests/ uses it to pin the
+// descriptor encodings the sweep kernels hard-code (smh_sweep_tc.cu) against a host matmul.
 // params: [0] idesc1 [1] a_lbo [2] a_sbo [3] b_lbo [4] b_sbo [5] kstep_bytes [6] box_stride_a [7] box_stride_b
-//         [8] idesc2 [9] b2_lbo [10] b2_sbo [11] b2_kstep_bytes [12] a2_col_step
+//         [8] idesc2 [9] b2_lbo [10] b2_sbo [11] b2_kstep_bytes [12] a2 TMEM columns per K step
 // ----------------------------------------------------------------------------------------------
 namespace smh {
 
@@ -158,13 +158,14 @@ struct ProbeParams {
 };
 
 __global__ void __launch_bounds__(128, 1)
-tc_probe_kernel(const float *__restrict__ zt, int blk_a, int blk_b, ProbeParams p, float *__restrict__ s_out,
-                float *__restrict__ dz_out, uint32_t *__restrict__ fail)
+tc_probe_kernel(const float *__restrict__ zt, const uint16_t *__restrict__ zb, int blk_a, int blk_b, ProbeParams p,
+                float *__restrict__ s_out, uint32_t *__restrict__ g_out, float *__restrict__ dz_out,
+                uint32_t *__restrict__ fail)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *sA = sm, *sB = sm + 65536;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + 65536 + 32768);
+    unsigned char *sA = sm, *sB = sm + 65536, *sBb = sm + 65536 + 32768;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + 65536 + 32768 + 16384);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -182,12 +183,13 @@ tc_probe_kernel(const float *__restrict__ zt, int blk_a, int blk_b, ProbeParams 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) {
-        mbar_arrive_expect_tx(&bars[0], 65536 + 32768);
+        mbar_arrive_expect_tx(&bars[0], 65536 + 32768 + 16384);
         for (int kb = 0; kb < 4; ++kb) {
             bulk_g2s(sA + kb * 16384, zt + (int64_t)blk_a * kBlockFloats + kb * 2048, 8192, &bars[0]);
             bulk_g2s(sA + kb * 16384 + 8192, zt + (int64_t)(blk_a + 1) * kBlockFloats + kb * 2048, 8192, &bars[0]);
         }
         bulk_g2s(sB, zt + (int64_t)blk_b * kBlockFloats, 32768, &bars[0]);
+        bulk_g2s(sBb, zb + (int64_t)blk_b * kBlockFloats, 16384, &bars[0]);
         mbar_wait(&bars[0], 0, fail, 101);
         tc_fence_after();
         const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
@@ -204,25 +206,31 @@ tc_probe_kernel(const float *__restrict__ zt, int blk_a, int blk_b, ProbeParams 
     const int r = warp * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int chunk = 0; chunk < 2; ++chunk) {
-        uint32_t v[32];
+        uint32_t v[32], pk[16];
         tc_ld32(lane_addr + chunk * 32, v);
         tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            s_out[r * 64 + chunk * 32 + c] = __uint_as_float(v[c]);
-            v[c] = __float_as_uint(to_tf32(__uint_as_float(v[c])));
-        }
-        tc_st32(lane_addr + chunk * 32, v);
+        for (int c = 0; c < 32; ++c) s_out[r * 64 + chunk * 32 + c] = __uint_as_float(v[c]);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) pk[c] = pack_bf16x2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+        tc_st16(lane_addr + chunk * 16, pk);
     }
     tc_wait_st();
+    {   // read G back (checks that tcgen05.st landed where the MMA will look)
+        uint32_t v[32];
+        tc_ld32(lane_addr, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) g_out[r * 32 + c] = v[c];
+    }
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
         tc_fence_after();
-        const uint32_t sB_u = smem_u32(sB);
-        for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t bd = umma_desc_sw128(sB_u + ks * p.v[11], p.v[9], p.v[10]);
-            tc_mma_ts_tf32(tmem_base + 128, tmem_base + ks * p.v[12], bd, p.v[8], ks ? 1u : 0u);
+        const uint32_t sBb_u = smem_u32(sBb);
+        for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bd = umma_desc_sw128(sBb_u + ks * p.v[11], p.v[9], p.v[10]);
+            tc_mma_ts_f16(tmem_base + 128, tmem_base + ks * p.v[12], bd, p.v[8], ks ? 1u : 0u);
         }
         tc_commit(&bars[2]);
     }
@@ -242,17 +250,19 @@ tc_probe_kernel(const float *__restrict__ zt, int blk_a, int blk_b, ProbeParams 
 
 }  // namespace smh
 
-extern "C" int smh_tc_probe(const float *zt_dev, int blk_a, int blk_b, const uint32_t *params16_host, float *s_out_dev,
-                            float *dz_out_dev, uint32_t *fail_dev, void *stream)
+extern "C" int smh_tc_probe(const float *zt_dev, const void *zb_dev, int blk_a, int blk_b, const uint32_t *params16_host,
+                            float *s_out_dev, uint32_t *g_out_dev, float *dz_out_dev, uint32_t *fail_dev, void *stream)
 {
     using namespace smh;
-    if (!zt_dev || !params16_host || !s_out_dev || !dz_out_dev || !fail_dev) return set_error(SMH_E_ARG, "null pointer");
+    if (!zt_dev || !zb_dev || !params16_host || !s_out_dev || !g_out_dev || !dz_out_dev || !fail_dev)
+        return set_error(SMH_E_ARG, "null pointer");
     ProbeParams p;
     for (int i = 0; i < 16; ++i) p.v[i] = params16_host[i];
-    const int smem = 1024 + 65536 + 32768 + 64;
+    const int smem = 1024 + 65536 + 32768 + 16384 + 64;
     cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "probe smem attr: %s", cudaGetErrorString(e));
-    tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(zt_dev, blk_a, blk_b, p, s_out_dev, dz_out_dev, fail_dev);
+    tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(zt_dev, (const uint16_t *)zb_dev, blk_a, blk_b, p, s_out_dev,
+                                                          g_out_dev, dz_out_dev, fail_dev);
     return check_launch("tc_probe_kernel");
 }
 
@@ -268,9 +278,9 @@ extern "C" void smh_tc_default_params(uint32_t *params16_host)
     params16_host[5] = 32;      // 8 tf32 = 32 B per K step inside the 128 B swizzle row
     params16_host[6] = 16384;   // A: next 32-column box (128 rows x 128 B)
     params16_host[7] = 8192;    // B: next 32-column box (64 rows x 128 B)
-    params16_host[8] = umma_idesc_tf32(kTile, kD, 0, 1);
-    params16_host[9] = 8192;    // MN-major B: stride between 32-element MN atoms (boxes)
+    params16_host[8] = umma_idesc_bf16(kTile, kD, 0, 1);
+    params16_host[9] = 8192;    // MN-major bf16 B: stride between 64-element (128 B) MN atoms
     params16_host[10] = 1024;   // stride between 8-row K groups
-    params16_host[11] = 1024;   // K step of 8 rows
-    params16_host[12] = 8;      // A (TMEM) column step per K step: 8 tf32
+    params16_host[11] = 2048;   // K step of 16 sample rows
+    params16_host[12] = 8;      // A (TMEM) columns per K step: 16 packed bf16
 }

@@ -5,9 +5,10 @@
 //            tile (W = (Dmax - D) / Dmax, correctly rounded), masks the diagonal and accumulates the row sums.
 //            The 2N x 2N logit matrix never leaves the SM.
 //   backward (autograd of :411-426): the same S tile and weights; the epilogue writes
-//            G = W E (1/neg_i + 1/neg_j) back into the TMEM columns S came from (tf32, round-to-nearest) and a
-//            second tcgen05.mma (A = G from TMEM, B = the staged z block read MN-major) accumulates
-//            dzacc_I += G z_J in TMEM across the whole strip; the softmax is never materialised.
+//            G = W E (1/neg_i + 1/neg_j) back into the TMEM columns S came from (packed bf16) and a second
+//            tcgen05.mma (kind::f16: A = G from TMEM, B = the staged bf16 z block read MN-major; tf32 operands
+//            cannot be read MN-major from a SWIZZLE_128B image) accumulates dzacc_I += G z_J in fp32 in TMEM
+//            across the whole strip; the softmax is never materialised.
 //
 // Persistent CTAs (one per SM) walk strips of 128x64 tasks that share a 128-row block.  Warp roles:
 //   warp 0      producer: cp.async.bulk of the z blocks (pre-swizzled SWIZZLE_128B images, smh_prep.cu) and of
@@ -24,12 +25,15 @@ namespace smh {
 constexpr int kTcThreads = 192;
 constexpr int kStages = 2;
 constexpr int kABytes = kTile * kD * 4;                 // 65536
-constexpr int kBBytes = kTaskN * kD * 4;                // 32768
+constexpr int kBBytes = kTaskN * kD * 4;                // 32768  tf32 block (logit operand)
+constexpr int kBbBytes = kTaskN * kD * 2;               // 16384  bf16 block (value operand, backward only)
 constexpr int kPieceBytes = 1024;                       // 64 rows x 16 B of a stored tile
 constexpr int kPiecePitch = 1040;                       // +16 B: conflict-free transposed reads
 constexpr int kDBytes = 32 * kPiecePitch;               // 33280
 constexpr int kNumBars = 24;
-constexpr int kTcSmem = 1024 /*align slack*/ + kABytes + kStages * kBBytes + kStages * kDBytes + kNumBars * 8 + 16;
+constexpr int kTcSmemFwd = 1024 /*align slack*/ + kABytes + kStages * kBBytes + kStages * kDBytes + kNumBars * 8 + 16;
+constexpr int kTcSmemBwd = kTcSmemFwd + kStages * kBbBytes;
+static_assert(kTcSmemBwd <= 232448, "backward sweep exceeds the 227 KB shared-memory limit");
 
 struct TcBars {
     uint64_t full_b[kStages], empty_b[kStages], full_d[kStages], empty_d[kStages];
@@ -76,7 +80,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned
             if (!BWD) {
                 rowsum += e;
             } else {
-                v[c] = __float_as_uint(to_tf32(w * e * (rni + rnjv[u])));
+                v[c] = __float_as_uint(w * e * (rni + rnjv[u]));
             }
         }
     }
@@ -85,7 +89,8 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned
 template <bool BWD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, int n_strips,
-                const float *__restrict__ zt, const float *__restrict__ dist, const float *__restrict__ rn,
+                const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
+                const float *__restrict__ rn,
                 float *__restrict__ neg, float *__restrict__ dzacc, Stats *__restrict__ stats, int m, int n,
                 int n_local, float k2)
 {
@@ -94,7 +99,8 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     unsigned char *sA = sm;
     unsigned char *sB = sA + kABytes;
     unsigned char *sD = sB + kStages * kBBytes;
-    TcBars *bars = reinterpret_cast<TcBars *>(sD + kStages * kDBytes);
+    unsigned char *sBb = sD + kStages * kDBytes;                 // backward only
+    TcBars *bars = reinterpret_cast<TcBars *>(sBb + (BWD ? kStages * kBbBytes : 0));
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(bars) + kNumBars * 8);
 
     const int warp = threadIdx.x >> 5;
@@ -152,8 +158,11 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 const int4 task = tasks[ti];
                 if (lane == 0) {
                     mbar_wait(&bars->empty_b[stage], ph ^ 1u, fail, 2);
-                    mbar_arrive_expect_tx(&bars->full_b[stage], kBBytes);
+                    mbar_arrive_expect_tx(&bars->full_b[stage], kBBytes + (BWD ? kBbBytes : 0));
                     bulk_g2s(sB + stage * kBBytes, zt + (int64_t)task.y * kBlockFloats, kBBytes, &bars->full_b[stage]);
+                    if (BWD)
+                        bulk_g2s(sBb + stage * kBbBytes, zb + (int64_t)task.y * kBlockFloats, kBbBytes,
+                                 &bars->full_b[stage]);
                     mbar_wait(&bars->empty_d[stage], ph ^ 1u, fail, 3);
                     mbar_arrive_expect_tx(&bars->full_d[stage], 32 * kPieceBytes);
                 }
@@ -174,8 +183,8 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
             constexpr uint32_t idesc1 = umma_idesc_tf32(kTile, kTaskN, 0, 0);
-            constexpr uint32_t idesc2 = umma_idesc_tf32(kTile, kD, 0, 1);
-            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            constexpr uint32_t idesc2 = umma_idesc_bf16(kTile, kD, 0, 1);
+            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), sBb_u = smem_u32(sBb);
             int stage = 0, sb = 0;
             uint32_t ph = 0, sph = 0, a_ph = 0, dz_ph = 0;
             bool pending = false, p_first = false;
@@ -189,10 +198,12 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 }
                 tc_fence_after();
 #pragma unroll
-                for (int ks = 0; ks < kTaskN / 8; ++ks) {
-                    const uint64_t bdesc = umma_desc_sw128(sB_u + p_stage * kBBytes + ks * 1024, 8192, 1024);
-                    tc_mma_ts_tf32(tmem_base + kDzCol, tmem_base + p_sb * kTaskN + ks * 8, bdesc, idesc2,
-                                   (p_first && ks == 0) ? 0u : 1u);
+                for (int ks = 0; ks < kTaskN / 16; ++ks) {
+                    // MN-major bf16 B: 64-element (128 B) atoms along d at LBO = 8 KiB, 8-row K groups at SBO = 1 KiB,
+                    // 16 sample rows (2 KiB) per K step; A = 16 packed-bf16 K values = 8 TMEM columns per step
+                    const uint64_t bdesc = umma_desc_sw128(sBb_u + p_stage * kBbBytes + ks * 2048, 8192, 1024);
+                    tc_mma_ts_f16(tmem_base + kDzCol, tmem_base + p_sb * kTaskN + ks * 8, bdesc, idesc2,
+                                  (p_first && ks == 0) ? 0u : 1u);
                 }
                 tc_commit(&bars->sg_empty[p_sb]);
                 tc_commit(&bars->empty_b[p_stage]);
@@ -280,7 +291,14 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                         else
                             epilogue_chunk<BWD, false, false>(v, dstage, r, chunk, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
                     }
-                    if (BWD) tc_st32(taddr, v);
+                    if (BWD) {
+                        // G as packed bf16x2 into the first 32 columns of the buffer S came from
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            pk[c] = pack_bf16x2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                        tc_st16(lane_addr + sb * kTaskN + chunk * 16, pk);
+                    }
                 }
                 if (BWD) tc_wait_st();
                 tc_fence_before();
@@ -337,16 +355,16 @@ int launch_sweep_tc(bool backward, const smh_dims_t &dims, const smh_layout_t &l
     const int n_local = dims.n / dims.world;
     cudaError_t e;
     if (backward) {
-        e = cudaFuncSetAttribute(sweep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+        e = cudaFuncSetAttribute(sweep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBwd);
         if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-        sweep_tc_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
-                                                                    ws.dist, ws.rn, ws.neg, ws.dzacc,
+        sweep_tc_kernel<true><<<grid, kTcThreads, kTcSmemBwd, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
+                                                                       ws.zb, ws.dist, ws.rn, ws.neg, ws.dzacc,
                                                                     (Stats *)ws.stats, lay.m, dims.n, n_local, k2);
     } else {
-        e = cudaFuncSetAttribute(sweep_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+        e = cudaFuncSetAttribute(sweep_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemFwd);
         if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-        sweep_tc_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
-                                                                     ws.dist, ws.rn, ws.neg, ws.dzacc,
+        sweep_tc_kernel<false><<<grid, kTcThreads, kTcSmemFwd, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
+                                                                        ws.zb, ws.dist, ws.rn, ws.neg, ws.dzacc,
                                                                      (Stats *)ws.stats, lay.m, dims.n, n_local, k2);
     }
     return check_launch("sweep_tc_kernel");

@@ -24,7 +24,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check
-from .ops import _as_f32, _stream_ptr, get_context, make_inputs
+from .ops import _as_f32, _stream_ptr, get_context, make_inputs, resolve_engine
 
 
 def pack_local(z1, z2, joints1, joints2) -> torch.Tensor:
@@ -59,11 +59,11 @@ def dz_out_row(i: int, n: int, n_local: int) -> int:
 def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, want_grad: bool,
                      group: Optional[dist.ProcessGroup], grad_scale: float = 1.0, strip_len: int = 0):
     lib = _lib.load()
-    eng = _lib.ENGINES[engine]
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = z1.device
     n_local, d = z1.shape
     n = n_local * world
+    eng = _lib.ENGINES[resolve_engine(engine, n)]
     with torch.cuda.device(dev):
         ctx = get_context(n, d, world, rank, dev, strip_len)
         lay, dims = ctx.layout, ctx.dims

@@ -24,7 +24,18 @@ import torch
 from . import _lib
 from ._lib import Dims, Inputs, Layout, check
 
-_DEFAULT_ENGINE = "tf32"
+_DEFAULT_ENGINE = "auto"
+_AUTO_FP32_MAX_M = 256     # below this many samples the exact-fp32 engine is used: tf32 rounding of the logits
+                           # does not average out over so few negatives, and the sweep is launch-bound anyway
+
+
+def resolve_engine(engine: str, n: int) -> str:
+    """'auto' -> 'fp32' for tiny batches (2N <= 256), else 'tf32' (tcgen05)."""
+    if engine == "auto":
+        return "fp32" if 2 * n <= _AUTO_FP32_MAX_M else "tf32"
+    if engine not in _lib.ENGINES:
+        raise ValueError(f"unknown engine {engine!r}; choose from auto, tf32, fp32")
+    return engine
 _ctx_lock = threading.Lock()
 _ctx_cache = {}
 
@@ -103,9 +114,9 @@ def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _
     for t, nm in ((z1, "z1"), (z2, "z2"), (joints1, "joints1"), (joints2, "joints2")):
         _require_cuda(t, nm)
     lib = _lib.load()
-    eng = _lib.ENGINES[engine]
     dev = z1.device
     n, d = z1.shape
+    eng = _lib.ENGINES[resolve_engine(engine, n)]
     with torch.cuda.device(dev):
         ctx = get_context(n, d, 1, 0, dev, strip_len)
         lay, dims = ctx.layout, ctx.dims

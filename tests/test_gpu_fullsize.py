@@ -52,10 +52,15 @@ def test_sampled_rows_against_oracle(batch, result):
     assert seen_max <= dmax
 
 
-def test_dmax_is_exact(batch, result):
+@pytest.fixture(scope="module")
+def host_minmax(batch):
     z1, z2, j1, j2 = batch["cpu"]
     bj = R.pack_joints(j1[:, :, :2], j2[:, :, :2])
-    dmax, dmin = R.c_minmax(bj)            # full 2.7e8-pair sweep on the host cores (OpenMP)
+    return R.c_minmax(bj)                  # full 2.7e8-pair sweep on the host cores (OpenMP)
+
+
+def test_dmax_is_exact(batch, result, host_minmax):
+    dmax, dmin = host_minmax
     stats = result[3]["stats"].cpu().numpy().view(np.float32)
     assert stats[0] == dmax and dmin == 0.0
 
@@ -63,7 +68,6 @@ def test_dmax_is_exact(batch, result):
 def test_loss_consistent_with_row_sums(batch, result):
     z1, z2, j1, j2 = batch["cpu"]
     loss, dz1, dz2, aux = result
-    res_pw = R.c_lib()          # noqa: F841  (build check)
     bj = R.pack_joints(j1[:, :, :2], j2[:, :, :2])
     pw = np.empty(N, np.float32)
     import ctypes
@@ -101,17 +105,15 @@ def test_engines_agree(batch, result):
     assert torch.isfinite(dz1).all() and float(dz1.abs().max()) > 0
 
 
-def test_weight_tile_checksum_against_oracle(batch):
+def test_weight_tile_checksum_against_oracle(batch, host_minmax):
     """Materialised weights at full size: 16 sampled rows bit-exact against the C oracle."""
     z1, z2, j1, j2 = batch["cpu"]
     dj1, dj2 = batch["dev"][2], batch["dev"][3]
     pos_w, neg_w = ops.mpjpe_weights(dj1[:, :, :2], dj2[:, :, :2])
     bj = R.pack_joints(j1[:, :, :2], j2[:, :, :2])
-    dmax = float(neg_w.new_tensor(0))  # placeholder to keep names local
     rows = np.random.default_rng(1).choice(2 * N, 16, replace=False)
     got = neg_w[torch.from_numpy(rows).to(neg_w.device)].cpu().numpy()
-    gmax, gmin = R.c_minmax(bj)
+    gmax, gmin = host_minmax
     for k, i in enumerate(rows):
         want = R.c_neg_weights_rows(bj, int(i), int(i) + 1, gmax, gmin)[0]
         assert R.ulp_distance(got[k], want).max() == 0
-    del dmax

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.Dims) == 20
     assert ctypes.sizeof(_lib.Stats) == 32
-    assert ctypes.sizeof(_lib.Layout) == 11 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.Layout) == 12 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.Inputs) == 88
 
 

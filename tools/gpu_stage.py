@@ -85,6 +85,13 @@ def stage_engine(engine):
         _report_step(f"{engine} {name}", loss, dz1, dz2, aux, g)
 
 
+def bf16_rne(x):
+    import numpy as np
+    b = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    b = ((b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    return b.view(np.float32)
+
+
 def stage_probe():
     import numpy as np
     import torch
@@ -99,49 +106,57 @@ def stage_probe():
     st = torch.cuda.current_stream().cuda_stream
     _lib.check(lib.smh_prep(ctypes.byref(ctx.dims), ctypes.byref(inp), ws.data_ptr(), 0, st))
     zt_ptr = ws.data_ptr() + ctx.layout.off_zt
-    zfull = tf32_rna(torch.cat([z1, z2]).numpy()).astype(np.float64)
+    zb_ptr = ws.data_ptr() + ctx.layout.off_zb
+    zt32 = tf32_rna(torch.cat([z1, z2]).numpy())
+    zfull = zt32.astype(np.float64)
+    zb16 = bf16_rne(zt32).astype(np.float64)
     blk_a, blk_b = 0, 3
     A = zfull[blk_a * 64: blk_a * 64 + 128]
     B = zfull[blk_b * 64: blk_b * 64 + 64]
+    Bb = zb16[blk_b * 64: blk_b * 64 + 64]
     s_ref = A @ B.T
 
-    def run(params):
+    def run(params, tag=None):
         arr = (ctypes.c_uint32 * 16)(*params)
         s_out = torch.full((128, 64), float("nan"), device=dev)
+        g_out = torch.zeros((128, 32), dtype=torch.int32, device=dev)
         dz_out = torch.full((128, 128), float("nan"), device=dev)
         fail = torch.zeros(1, dtype=torch.int32, device=dev)
-        _lib.check(lib.smh_tc_probe(zt_ptr, blk_a, blk_b, arr, s_out.data_ptr(), dz_out.data_ptr(), fail.data_ptr(), st))
+        _lib.check(lib.smh_tc_probe(zt_ptr, zb_ptr, blk_a, blk_b, arr, s_out.data_ptr(), g_out.data_ptr(),
+                                    dz_out.data_ptr(), fail.data_ptr(), st))
         torch.cuda.synchronize()
         s = s_out.cpu().numpy().astype(np.float64)
-        dz_ref = tf32_rna(s.astype(np.float32)).astype(np.float64) @ B
+        g = g_out.cpu().numpy().view(np.uint32)
+        glo = ((g & 0xFFFF) << 16).astype(np.uint32).view(np.float32)
+        ghi = (g & 0xFFFF0000).astype(np.uint32).view(np.float32)
+        gq = bf16_rne(s.astype(np.float32)).astype(np.float64)
+        gread = np.empty((128, 64))
+        gread[:, 0::2], gread[:, 1::2] = glo, ghi
+        dz = dz_out.cpu().numpy().astype(np.float64)
+        dz_ref = gq @ Bb
         e1 = np.abs(s - s_ref).max()
-        e2 = np.abs(dz_out.cpu().numpy() - dz_ref).max()
-        return e1, e2, int(fail.item())
+        eg = np.abs(gread - gq).max()
+        e2 = np.abs(dz - dz_ref).max()
+        if tag:
+            np.savez(os.path.join(OUT, f"probe_{tag}.npz"), s=s, g=gread, dz=dz, s_ref=s_ref, dz_ref=dz_ref, B=Bb)
+            print(f"[{tag}] dz min {np.nanmin(dz):.4f} max {np.nanmax(dz):.4f} nan {int(np.isnan(dz).sum())} | ref min "
+                  f"{dz_ref.min():.4f} max {dz_ref.max():.4f} | dz[0,:4] {dz[0,:4]} ref {dz_ref[0,:4]}")
+        return e1, eg, e2, int(fail.item())
 
     d = (ctypes.c_uint32 * 16)()
     lib.smh_tc_default_params(d)
     base = list(d)
     print("default params", base)
-    e1, e2, f = run(base)
-    print(f"default: max|S - ref| {e1:.3e}   max|dZ - ref| {e2:.3e}   fail {f}")
-    if not (e1 < 1e-4):
-        for a_lbo in (0, 16, 1024):
-            for sbo in (1024, 128, 8192):
-                for kstep in (32, 16, 64):
-                    p = list(base)
-                    p[1] = p[3] = a_lbo
-                    p[2] = p[4] = sbo
-                    p[5] = kstep
-                    e1, _, f = run(p)
-                    print(f"  MMA1 lbo {a_lbo} sbo {sbo} kstep {kstep}: err {e1:.3e} fail {f}")
+    e1, eg, e2, f = run(base, "default")
+    print(f"default: max|S - ref| {e1:.3e}  max|G readback - bf16(S)| {eg:.3e}  max|dZ - ref| {e2:.3e}  fail {f}")
     if not (e2 < 1e-4):
-        for lbo, sbo in ((8192, 1024), (1024, 8192), (8192, 128), (128, 8192), (16, 1024), (1024, 16)):
-            for kstep in (1024, 256, 128):
-                for colstep in (8, 4, 16):
+        for lbo, sbo in ((8192, 1024), (1024, 8192), (8192, 128), (128, 8192), (16, 1024), (8192, 16), (4096, 1024)):
+            for kstep in (2048, 1024, 256, 32):
+                for colstep in (8, 16):
                     p = list(base)
                     p[9], p[10], p[11], p[12] = lbo, sbo, kstep, colstep
-                    _, e2, f = run(p)
-                    print(f"  MMA2 lbo {lbo} sbo {sbo} kstep {kstep} colstep {colstep}: err {e2:.3e} fail {f}")
+                    _, _, e2, f = run(p)
+                    print(f"  MN-major bf16 lbo {lbo} sbo {sbo} kstep {kstep} colstep {colstep}: err {e2:.3e} fail {f}")
 
 
 def stage_big():
