@@ -222,7 +222,7 @@ def run_ours(args):
     m = 2 * N_PER_VIEW
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
-                dtype="tf32" if engine == "tf32" else "f32", data="synthetic",
+                dtype={"tf32": "tf32", "bf16": "bf16"}.get(engine, "f32"), data="synthetic",
                 config=dict(workload="handclr_w loss fwd+bwd, global batch 8192 (2N=16384), d=128, 21 joints, "
                                      "mpjpe/linear/pos_neg, tau 0.5", global_batch=N_PER_VIEW, proj_dim=DIM,
                             engine=engine, parallelism=f"row/tile-sharded x{world}" if world > 1 else "single GPU",
@@ -299,7 +299,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="tf32", choices=["tf32", "fp32", "auto"])
+    ap.add_argument("--engine", default="tf32", choices=["tf32", "fp32", "auto", "bf16"])
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 30)

@@ -47,8 +47,9 @@ extern "C" {
 #define SMH_E_MODE (-6)          /* unknown engine / mode */
 
 /* engine of the forward/backward sweeps (the dense contraction S = z z^T and dz = G z) */
-#define SMH_ENGINE_TC_TF32 0     /* tcgen05.mma kind::tf32, TMEM accumulators, bulk-async staged tiles */
+#define SMH_ENGINE_TC_TF32 0     /* tcgen05: tf32 logits in the forward sweep, bf16 operands in the backward sweep */
 #define SMH_ENGINE_FP32 1        /* CUDA-core FFMA, fp32 accumulate (exact-fp32 mode) */
+#define SMH_ENGINE_TC_BF16 2     /* tcgen05: bf16 operands in both sweeps (bf16 mode) */
 
 /* problem description shared by all calls */
 typedef struct smh_dims {

@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsimhand_b200.so")
 
 ENGINE_TC_TF32 = 0
 ENGINE_FP32 = 1
-ENGINES = {"tf32": ENGINE_TC_TF32, "tc": ENGINE_TC_TF32, "fp32": ENGINE_FP32}
+ENGINE_TC_BF16 = 2
+ENGINES = {"tf32": ENGINE_TC_TF32, "tc": ENGINE_TC_TF32, "fp32": ENGINE_FP32, "bf16": ENGINE_TC_BF16}
 
 FLAG_SLOW_DOMAIN = 1
 FLAG_NONFINITE = 2

@@ -94,7 +94,22 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
         size_t j = i;
         while (j < tasks.size() && tasks[j].x == tasks[i].x && (int)(j - i) < strip_len) ++j;
         strips.push_back(make_int2((int)i, (int)j));
+        tasks[i].w |= kTaskFirst;
+        tasks[j - 1].w |= kTaskLast;
         i = j;
+    }
+    // Execution order of the strips (CTAs take them round-robin, so neighbours in this list run at the same
+    // time): strips of super-tile (A, B) are followed by those of (B, A), which read the same stored MPJPE
+    // tiles transposed -- the second read then hits the 126 MB L2 instead of HBM.
+    {
+        const int sbk = 16;                                   // row blocks per super block (2048 samples)
+        auto key = [&](const int2 &st) {
+            const int4 &t0 = tasks[st.x];
+            long long a = t0.x / sbk, b = (t0.y / 2) / sbk;
+            long long lo = a < b ? a : b, hi = a < b ? b : a;
+            return (((lo * 4096 + hi) * 2 + (a > b ? 1 : 0)) * 4096 + t0.x) * 8192 + t0.y;
+        };
+        std::stable_sort(strips.begin(), strips.end(), [&](const int2 &x, const int2 &y) { return key(x) < key(y); });
     }
     *n_stored = (int)tiles.size();
     *n_tasks = (int)tasks.size();
@@ -276,7 +291,8 @@ int smh_prep(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, int e
     SMH_COMMON_PROLOGUE(false)
     (void)plan_dev;
     if ((rc = check_inputs(*dims, in))) return rc;
-    if (engine != SMH_ENGINE_TC_TF32 && engine != SMH_ENGINE_FP32) return set_error(SMH_E_MODE, "unknown engine %d", engine);
+    if (engine != SMH_ENGINE_TC_TF32 && engine != SMH_ENGINE_FP32 && engine != SMH_ENGINE_TC_BF16)
+        return set_error(SMH_E_MODE, "unknown engine %d", engine);
     return launch_prep(*dims, lay, *in, ws, engine == SMH_ENGINE_TC_TF32, st);
 }
 
@@ -292,7 +308,8 @@ int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, floa
     SMH_COMMON_PROLOGUE(true)
     if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
     PlanView pv = carve_plan(plan_dev, lay);
-    if (engine == SMH_ENGINE_TC_TF32) return launch_sweep_tc(false, *dims, lay, pv, ws, temperature, st);
+    if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
+        return launch_sweep_tc(false, engine == SMH_ENGINE_TC_BF16, *dims, lay, pv, ws, temperature, st);
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, *dims, lay, pv, ws, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
@@ -304,7 +321,8 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
     if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
     PlanView pv = carve_plan(plan_dev, lay);
     if ((rc = launch_rn(lay, ws, st))) return rc;
-    if (engine == SMH_ENGINE_TC_TF32) return launch_sweep_tc(true, *dims, lay, pv, ws, temperature, st);
+    if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
+        return launch_sweep_tc(true, true, *dims, lay, pv, ws, temperature, st);
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, *dims, lay, pv, ws, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }

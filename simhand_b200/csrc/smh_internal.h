@@ -37,8 +37,8 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
                  cudaStream_t stream);
 int launch_sweep_fp32(bool backward, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
                       const WsView &ws, float temperature, cudaStream_t stream);
-int launch_sweep_tc(bool backward, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
-                    const WsView &ws, float temperature, cudaStream_t stream);
+int launch_sweep_tc(bool backward, bool logits_bf16, const smh_dims_t &dims, const smh_layout_t &lay,
+                    const PlanView &plan, const WsView &ws, float temperature, cudaStream_t stream);
 int launch_rn(const smh_layout_t &lay, const WsView &ws, cudaStream_t stream);
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
                     const float *dzacc_src, float temperature, float grad_scale, float *loss, float *dz1,

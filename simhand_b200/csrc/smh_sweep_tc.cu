@@ -1,6 +1,7 @@
-// simhand_b200 K1/K2, tensor-core engine (SMH_ENGINE_TC_TF32): the fused forward / backward sweeps.
+// simhand_b200 K1/K2, tensor-core engines (SMH_ENGINE_TC_TF32 / SMH_ENGINE_TC_BF16): the fused forward / backward sweeps.
 //
-//   forward  (src/models/utils.py:411-417): S = z z^T on tcgen05 (kind::tf32, fp32 accumulate in TMEM); the
+//   forward  (src/models/utils.py:411-417): S = z z^T on tcgen05 (kind::tf32 from the tf32 image of z, or kind::f16
+//            from its bf16 image in the bf16 engine; fp32 accumulate in TMEM); the
 //            epilogue turns each S tile into E = exp(S * W / tau) with W built on the fly from the stored MPJPE
 //            tile (W = (Dmax - D) / Dmax, correctly rounded), masks the diagonal and accumulates the row sums.
 //            The 2N x 2N logit matrix never leaves the SM.
@@ -8,60 +9,74 @@
 //            G = W E (1/neg_i + 1/neg_j) back into the TMEM columns S came from (packed bf16) and a second
 //            tcgen05.mma (kind::f16: A = G from TMEM, B = the staged bf16 z block read MN-major; tf32 operands
 //            cannot be read MN-major from a SWIZZLE_128B image) accumulates dzacc_I += G z_J in fp32 in TMEM
-//            across the whole strip; the softmax is never materialised.
+//            across the whole strip; the softmax is never materialised.  The backward recomputes S from the bf16
+//            image in both engines (its effect on the gradient is ~1e-5 max|g|, below the bf16 rounding of G), which
+//            lets one staged bf16 block serve both contractions (K-major for S, MN-major for dz) and frees the
+//            shared memory for a deeper prefetch of the MPJPE tiles.
 //
 // Persistent CTAs (one per SM) walk strips of 128x64 tasks that share a 128-row block.  Warp roles:
-//   warp 0      producer: cp.async.bulk of the z blocks (pre-swizzled SWIZZLE_128B images, smh_prep.cu) and of
-//               the MPJPE tile pieces, completing on mbarriers
+//   warp 0      tile producer: cp.async.bulk of the MPJPE tile halves (HBM), up to 3-4 tasks ahead, on mbarriers
+//   warp 18     operand producer: cp.async.bulk of the z blocks (pre-swizzled SWIZZLE_128B images, smh_prep.cu)
 //   warp 1      one elected thread issues tcgen05.mma and tcgen05.commit
-//   warps 2..5  epilogue, one row per thread (TMEM lane == row): tcgen05.ld -> weights -> ex2 -> row sums
-//               (forward) or tcgen05.st of G (backward); strip flush of dzacc with red.global.add.v4.f32
+//   warps 2..17 epilogue, two groups of 8 warps taking alternate tasks; one row per thread (TMEM lane == row); two
+//               warps of a group share a TMEM lane quadrant and split the 64 columns of a task: tcgen05.ld -> weights -> ex2 -> row sums (forward) or tcgen05.st of G
+//               (backward); strip flush of dzacc with red.global.add.v4.f32
 // Every pipeline wait is bounded (smh_common.cuh: mbar_wait) so a protocol bug cannot hang the device.
 #include "smh_common.cuh"
 #include "smh_internal.h"
 
 namespace smh {
 
-constexpr int kTcThreads = 192;
-constexpr int kStages = 2;
-constexpr int kABytes = kTile * kD * 4;                 // 65536
-constexpr int kBBytes = kTaskN * kD * 4;                // 32768  tf32 block (logit operand)
-constexpr int kBbBytes = kTaskN * kD * 2;               // 16384  bf16 block (value operand, backward only)
-constexpr int kPieceBytes = 1024;                       // 64 rows x 16 B of a stored tile
-constexpr int kPiecePitch = 1040;                       // +16 B: conflict-free transposed reads
-constexpr int kDBytes = 32 * kPiecePitch;               // 33280
-constexpr int kNumBars = 24;
-constexpr int kTcSmemFwd = 1024 /*align slack*/ + kABytes + kStages * kBBytes + kStages * kDBytes + kNumBars * 8 + 16;
-constexpr int kTcSmemBwd = kTcSmemFwd + kStages * kBbBytes;
-static_assert(kTcSmemBwd <= 232448, "backward sweep exceeds the 227 KB shared-memory limit");
+constexpr int kEpiGroups = 2;                            // epilogue groups take alternate tasks
+constexpr int kGroupWarps = 8;                           // 4 TMEM lane quadrants x 2 column halves
+constexpr int kEpiWarps = kEpiGroups * kGroupWarps;      // 16
+constexpr int kTcThreads = 64 + 32 * kEpiWarps + 32;     // 608: tile producer, MMA, 16 epilogue, operand producer
+constexpr int kSBufs = 4;                                // S / G buffers in TMEM (64 columns each)
+constexpr int kMaxBStages = 4;                           // z blocks come from L2
+constexpr int kMaxDStages = 4;                           // MPJPE tile pieces come from HBM: deeper prefetch
+constexpr int kDBytes = 32768;                           // the half of a stored tile a task needs
+constexpr int kNumBars = 40;
+constexpr int kCtlBytes = kNumBars * 8 + kMaxDStages * 16 + 16;   // barriers, staged task records, TMEM base
+
+template <bool SBF16>
+struct TcCfg {
+    static constexpr int kABytes = SBF16 ? kTile * kD * 2 : kTile * kD * 4;        // row block of z
+    static constexpr int kBBytes = SBF16 ? kTaskN * kD * 2 : kTaskN * kD * 4;      // column block of z
+    static constexpr int kBStages = SBF16 ? 4 : 2;
+    static constexpr int kDStages = SBF16 ? 4 : 3;
+    static constexpr int kSmem = 1024 /*align slack*/ + kABytes + kBStages * kBBytes + kDStages * kDBytes + kCtlBytes;
+    static_assert(kSmem <= 232448, "sweep exceeds the 227 KB shared-memory limit");
+};
 
 struct TcBars {
-    uint64_t full_b[kStages], empty_b[kStages], full_d[kStages], empty_d[kStages];
+    uint64_t full_b[kMaxBStages], empty_b[kMaxBStages], full_d[kMaxDStages], empty_d[kMaxDStages];
     uint64_t a_full, a_empty;
-    uint64_t sg_full[2], sg_empty[2], g_ready[2];
+    uint64_t sg_full[kSBufs], sg_empty[kSBufs], g_ready[kSBufs];
     uint64_t dz_full, dz_empty;
 };
 static_assert(sizeof(TcBars) <= kNumBars * 8, "barrier block too small");
 
-// one 32-column chunk of the epilogue.  v[] holds S on entry and (backward) G bits on exit.
+// the 32 columns [half * 32, half * 32 + 32) of one task for one row.  v[] holds S on entry and (backward) G on exit.
 template <bool BWD, bool TRANSPOSED, bool MASKED>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned char *dstage, int r, int chunk,
                                                int gi, int gj0, int m, bool diagonal, float dmax,
                                                const DivConst &divw, float k2, float rni,
-                                               const float *__restrict__ rn, float &rowsum)
+                                               const float *__restrict__ rn, float (&rowsum)[4])
 {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int jl = chunk * 32 + q * 4;                       // first of 4 columns inside the task
         float dv[4];
         if (!TRANSPOSED) {
-            const float4 t4 = *reinterpret_cast<const float4 *>(dstage + ((r >> 6) * 16 + (jl >> 2)) * kPiecePitch +
-                                                                (r & 63) * 16);
+            const int c4l = jl >> 2;                              // == (global c4) mod 16; its low 3 bits drive the XOR
+            const float4 t4 = *reinterpret_cast<const float4 *>(dstage + ((r >> 6) * 16 + c4l) * 1024 +
+                                                                ((r & 63) ^ (c4l & 7)) * 16);
             dv[0] = t4.x; dv[1] = t4.y; dv[2] = t4.z; dv[3] = t4.w;
         } else {
-            const unsigned char *base = dstage + (r >> 2) * kPiecePitch + (r & 3) * 4;
+            const int c4 = r >> 2;
+            const unsigned char *base = dstage + c4 * 1024 + (r & 3) * 4;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dv[u] = *reinterpret_cast<const float *>(base + (jl + u) * 16);
+            for (int u = 0; u < 4; ++u) dv[u] = *reinterpret_cast<const float *>(base + ((jl + u) ^ (c4 & 7)) * 16);
         }
         float4 rnj = make_float4(0.f, 0.f, 0.f, 0.f);
         if (BWD) rnj = __ldg(reinterpret_cast<const float4 *>(rn + gj0 + jl));
@@ -78,7 +93,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned
                 e = valid ? e : 0.f;
             }
             if (!BWD) {
-                rowsum += e;
+                rowsum[u] += e;
             } else {
                 v[c] = __float_as_uint(w * e * (rni + rnjv[u]));
             }
@@ -86,45 +101,51 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned
     }
 }
 
-template <bool BWD>
+// BWD: backward sweep (always reads the bf16 image).  SBF16: logits from the bf16 image (else tf32 image).
+template <bool BWD, bool SBF16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, int n_strips,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
-                const float *__restrict__ rn,
-                float *__restrict__ neg, float *__restrict__ dzacc, Stats *__restrict__ stats, int m, int n,
-                int n_local, float k2)
+                const float *__restrict__ rn, float *__restrict__ neg, float *__restrict__ dzacc,
+                Stats *__restrict__ stats, int m, int n, int n_local, float k2)
 {
+    static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
+    using Cfg = TcCfg<SBF16>;
+    constexpr int kABytes = Cfg::kABytes, kBBytes = Cfg::kBBytes, kDStages = Cfg::kDStages, kBStages = Cfg::kBStages;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sA = sm;
     unsigned char *sB = sA + kABytes;
-    unsigned char *sD = sB + kStages * kBBytes;
-    unsigned char *sBb = sD + kStages * kDBytes;                 // backward only
-    TcBars *bars = reinterpret_cast<TcBars *>(sBb + (BWD ? kStages * kBbBytes : 0));
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(bars) + kNumBars * 8);
+    unsigned char *sD = sB + kBStages * kBBytes;
+    unsigned char *ctl = sD + kDStages * kDBytes;
+    TcBars *bars = reinterpret_cast<TcBars *>(ctl);
+    int4 *task_slot = reinterpret_cast<int4 *>(ctl + kNumBars * 8);          // task record travelling with a D stage
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ctl + kNumBars * 8 + kMaxDStages * 16);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     uint32_t *fail = &stats->fail_site;
-    constexpr uint32_t kTmemCols = BWD ? 256u : 128u;
-    constexpr uint32_t kDzCol = 128u;
+    constexpr uint32_t kTmemCols = BWD ? 512u : 256u;
+    constexpr uint32_t kDzCol = kSBufs * kTaskN;                 // 256: gradient accumulator behind the S buffers
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < kBStages; ++i) {
             mbar_init(&bars->full_b[i], 1);
             mbar_init(&bars->empty_b[i], 1);
+        }
+        for (int i = 0; i < kDStages; ++i) {
             mbar_init(&bars->full_d[i], 1);
-            mbar_init(&bars->empty_d[i], 4);
+            mbar_init(&bars->empty_d[i], kGroupWarps);
         }
         mbar_init(&bars->a_full, 1);
         mbar_init(&bars->a_empty, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kSBufs; ++i) {
             mbar_init(&bars->sg_full[i], 1);
-            mbar_init(&bars->sg_empty[i], BWD ? 1 : 4);
-            mbar_init(&bars->g_ready[i], 4);
+            mbar_init(&bars->sg_empty[i], BWD ? 1 : kGroupWarps);
+            mbar_init(&bars->g_ready[i], kGroupWarps);
         }
         mbar_init(&bars->dz_full, 1);
-        mbar_init(&bars->dz_empty, 4);
+        mbar_init(&bars->dz_empty, kEpiWarps);
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -137,62 +158,90 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ producer
-        int stage = 0;
-        uint32_t ph = 0, a_ph = 0;
+        // ------------------------------------------------------------------ tile producer (MPJPE pieces, HBM)
+        int dst = 0;
+        uint32_t dph = 0;
         for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
             const int2 strip = strips[s];
-            const int I = tasks[strip.x].x;
-            if (lane == 0) {
+            int4 task = tasks[strip.x];
+            for (int ti = strip.x; ti < strip.y; ++ti) {
+                const int4 next = (ti + 1 < strip.y) ? tasks[ti + 1] : task;      // prefetch the next record
+                if (lane == 0) {
+                    mbar_wait(&bars->empty_d[dst], dph ^ 1u, fail, 3);
+                    task_slot[dst] = task;
+                    mbar_arrive_expect_tx(&bars->full_d[dst], kDBytes);
+                    const float *tile = dist + (int64_t)task.z * kTileFloats;
+                    const int half = task.y & 1;
+                    if (task.w & kTaskTransposed) {
+                        // stored rows half*64 .. +63, all 128 stored columns: one contiguous 32 KiB slab
+                        bulk_g2s(sD + dst * kDBytes, tile + half * 8192, 32768, &bars->full_d[dst]);
+                    } else {
+                        // stored columns half*64 .. +63: one 16 KiB slab per 64-row half
+                        bulk_g2s(sD + dst * kDBytes, tile + (half * 16) * 256, 16384, &bars->full_d[dst]);
+                        bulk_g2s(sD + dst * kDBytes + 16384, tile + (32 + half * 16) * 256, 16384, &bars->full_d[dst]);
+                    }
+                }
+                task = next;
+                if (++dst == kDStages) { dst = 0; dph ^= 1u; }
+            }
+        }
+    } else if (warp == 2 + kEpiWarps) {
+        // ------------------------------------------------------------------ operand producer (z blocks, L2)
+        if (lane == 0) {
+            int bst = 0;
+            uint32_t bph = 0, a_ph = 0;
+            for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
+                const int2 strip = strips[s];
+                int4 task = tasks[strip.x];
+                const int I = task.x;
                 mbar_wait(&bars->a_empty, a_ph ^ 1u, fail, 1);
                 mbar_arrive_expect_tx(&bars->a_full, kABytes);
+                if (SBF16) {
+                    // two 64-row bf16 blocks -> two 64-column boxes of [128 rows][128 B]
 #pragma unroll
-                for (int kb = 0; kb < 4; ++kb) {
-                    bulk_g2s(sA + kb * 16384, zt + (int64_t)(2 * I) * kBlockFloats + kb * 2048, 8192, &bars->a_full);
-                    bulk_g2s(sA + kb * 16384 + 8192, zt + (int64_t)(2 * I + 1) * kBlockFloats + kb * 2048, 8192,
-                             &bars->a_full);
+                    for (int db = 0; db < 2; ++db) {
+                        bulk_g2s(sA + db * 16384, zb + (int64_t)(2 * I) * kBlockFloats + db * 4096, 8192, &bars->a_full);
+                        bulk_g2s(sA + db * 16384 + 8192, zb + (int64_t)(2 * I + 1) * kBlockFloats + db * 4096, 8192,
+                                 &bars->a_full);
+                    }
+                } else {
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        bulk_g2s(sA + kb * 16384, zt + (int64_t)(2 * I) * kBlockFloats + kb * 2048, 8192, &bars->a_full);
+                        bulk_g2s(sA + kb * 16384 + 8192, zt + (int64_t)(2 * I + 1) * kBlockFloats + kb * 2048, 8192,
+                                 &bars->a_full);
+                    }
                 }
-            }
-            a_ph ^= 1u;
-            for (int ti = strip.x; ti < strip.y; ++ti) {
-                const int4 task = tasks[ti];
-                if (lane == 0) {
-                    mbar_wait(&bars->empty_b[stage], ph ^ 1u, fail, 2);
-                    mbar_arrive_expect_tx(&bars->full_b[stage], kBBytes + (BWD ? kBbBytes : 0));
-                    bulk_g2s(sB + stage * kBBytes, zt + (int64_t)task.y * kBlockFloats, kBBytes, &bars->full_b[stage]);
-                    if (BWD)
-                        bulk_g2s(sBb + stage * kBbBytes, zb + (int64_t)task.y * kBlockFloats, kBbBytes,
-                                 &bars->full_b[stage]);
-                    mbar_wait(&bars->empty_d[stage], ph ^ 1u, fail, 3);
-                    mbar_arrive_expect_tx(&bars->full_d[stage], 32 * kPieceBytes);
+                a_ph ^= 1u;
+                for (int ti = strip.x; ti < strip.y; ++ti) {
+                    const int4 next = (ti + 1 < strip.y) ? tasks[ti + 1] : task;
+                    mbar_wait(&bars->empty_b[bst], bph ^ 1u, fail, 2);
+                    mbar_arrive_expect_tx(&bars->full_b[bst], kBBytes);
+                    if (SBF16)
+                        bulk_g2s(sB + bst * kBBytes, zb + (int64_t)task.y * kBlockFloats, kBBytes, &bars->full_b[bst]);
+                    else
+                        bulk_g2s(sB + bst * kBBytes, zt + (int64_t)task.y * kBlockFloats, kBBytes, &bars->full_b[bst]);
+                    task = next;
+                    if (++bst == kBStages) { bst = 0; bph ^= 1u; }
                 }
-                __syncwarp();
-                {
-                    // piece `lane`: direct -> (rh = lane / 16, c4 = half * 16 + lane % 16); transposed -> (rh = half, c4 = lane)
-                    const int half = task.y & 1;
-                    const int src_piece = (task.w & kTaskTransposed) ? (half * 32 + lane)
-                                                                    : ((lane >> 4) * 32 + half * 16 + (lane & 15));
-                    bulk_g2s(sD + stage * kDBytes + lane * kPiecePitch,
-                             dist + (int64_t)task.z * kTileFloats + src_piece * 256, kPieceBytes, &bars->full_d[stage]);
-                }
-                stage ^= 1;
-                if (stage == 0) ph ^= 1u;
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            constexpr uint32_t idesc1 = umma_idesc_tf32(kTile, kTaskN, 0, 0);
+            constexpr uint32_t idesc1 = SBF16 ? umma_idesc_bf16(kTile, kTaskN, 0, 0) : umma_idesc_tf32(kTile, kTaskN, 0, 0);
             constexpr uint32_t idesc2 = umma_idesc_bf16(kTile, kD, 0, 1);
-            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB), sBb_u = smem_u32(sBb);
-            int stage = 0, sb = 0;
-            uint32_t ph = 0, sph = 0, a_ph = 0, dz_ph = 0;
-            bool pending = false, p_first = false;
-            int p_stage = 0, p_sb = 0;
-            uint32_t p_sph = 0;
-            auto mma2 = [&]() {
-                mbar_wait(&bars->g_ready[p_sb], p_sph, fail, 4);
-                if (p_first) {
+            const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            uint32_t a_ph = 0, dz_ph = 0;
+            uint32_t seq = 0;                       // tasks issued so far by this CTA
+            uint32_t done2 = 0;                     // value MMAs issued so far (backward)
+            uint32_t first_mask = 0, last_mask = 0; // per pending task (bit = seq % 32): first / last of its strip
+            // value contraction of task q (the q-th task of this CTA): dz (+)= G_q z_J
+            auto mma2 = [&](uint32_t q) {
+                const uint32_t sbq = q % kSBufs, bstq = q % kBStages;
+                const bool first = (first_mask >> (q & 31)) & 1u, last = (last_mask >> (q & 31)) & 1u;
+                mbar_wait(&bars->g_ready[sbq], (q / kSBufs) & 1u, fail, 4);
+                if (first) {
                     mbar_wait(&bars->dz_empty, dz_ph ^ 1u, fail, 5);
                     dz_ph ^= 1u;
                 }
@@ -200,136 +249,151 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
 #pragma unroll
                 for (int ks = 0; ks < kTaskN / 16; ++ks) {
                     // MN-major bf16 B: 64-element (128 B) atoms along d at LBO = 8 KiB, 8-row K groups at SBO = 1 KiB,
-                    // 16 sample rows (2 KiB) per K step; A = 16 packed-bf16 K values = 8 TMEM columns per step
-                    const uint64_t bdesc = umma_desc_sw128(sBb_u + p_stage * kBbBytes + ks * 2048, 8192, 1024);
-                    tc_mma_ts_f16(tmem_base + kDzCol, tmem_base + p_sb * kTaskN + ks * 8, bdesc, idesc2,
-                                  (p_first && ks == 0) ? 0u : 1u);
+                    // 16 sample rows (2 KiB) per K step.  A = packed bf16 G: columns [0,16) hold task columns 0..31,
+                    // columns [32,48) hold task columns 32..63 (each epilogue half overwrites its own S columns).
+                    const uint64_t bdesc = umma_desc_sw128(sB_u + bstq * kBBytes + ks * 2048, 8192, 1024);
+                    const uint32_t a_col = (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u;
+                    tc_mma_ts_f16(tmem_base + kDzCol, tmem_base + sbq * kTaskN + a_col, bdesc, idesc2,
+                                  (first && ks == 0) ? 0u : 1u);
                 }
-                tc_commit(&bars->sg_empty[p_sb]);
-                tc_commit(&bars->empty_b[p_stage]);
-                pending = false;
+                tc_commit(&bars->sg_empty[sbq]);
+                tc_commit(&bars->empty_b[bstq]);
+                if (last) tc_commit(&bars->dz_full);
             };
             for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
                 const int2 strip = strips[s];
                 mbar_wait(&bars->a_full, a_ph, fail, 6);
                 a_ph ^= 1u;
-                for (int ti = strip.x; ti < strip.y; ++ti) {
-                    mbar_wait(&bars->full_b[stage], ph, fail, 7);
-                    mbar_wait(&bars->sg_empty[sb], sph ^ 1u, fail, 8);
+                for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
+                    const uint32_t sb = seq % kSBufs, bst = seq % kBStages;
+                    mbar_wait(&bars->full_b[bst], (seq / kBStages) & 1u, fail, 7);
+                    mbar_wait(&bars->sg_empty[sb], ((seq / kSBufs) & 1u) ^ 1u, fail, 8);
                     tc_fence_after();
+                    if (SBF16) {
+                        // K-major bf16: 64 columns (128 B) per box, 16 columns (32 B) per K step
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) {
+                        for (int db = 0; db < 2; ++db) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t adesc = umma_desc_sw128(sA_u + kb * 16384 + ks * 32, 16, 1024);
-                            const uint64_t bdesc = umma_desc_sw128(sB_u + stage * kBBytes + kb * 8192 + ks * 32, 16, 1024);
-                            tc_mma_ss_tf32(tmem_base + sb * kTaskN, adesc, bdesc, idesc1, (kb | ks) ? 1u : 0u);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t adesc = umma_desc_sw128(sA_u + db * 16384 + ks * 32, 16, 1024);
+                                const uint64_t bdesc = umma_desc_sw128(sB_u + bst * kBBytes + db * 8192 + ks * 32, 16, 1024);
+                                tc_mma_ss_f16(tmem_base + sb * kTaskN, adesc, bdesc, idesc1, (db | ks) ? 1u : 0u);
+                            }
+                        }
+                    } else {
+                        // K-major tf32: 32 columns (128 B) per box, 8 columns (32 B) per K step
+#pragma unroll
+                        for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t adesc = umma_desc_sw128(sA_u + kb * 16384 + ks * 32, 16, 1024);
+                                const uint64_t bdesc = umma_desc_sw128(sB_u + bst * kBBytes + kb * 8192 + ks * 32, 16, 1024);
+                                tc_mma_ss_tf32(tmem_base + sb * kTaskN, adesc, bdesc, idesc1, (kb | ks) ? 1u : 0u);
+                            }
                         }
                     }
                     tc_commit(&bars->sg_full[sb]);
-                    if (!BWD) tc_commit(&bars->empty_b[stage]);
+                    if (!BWD) tc_commit(&bars->empty_b[bst]);
+                    if (ti + 1 == strip.y) tc_commit(&bars->a_empty);     // every MMA1 of the strip has read sA
                     if (BWD) {
-                        if (pending) mma2();
-                        pending = true;
-                        p_stage = stage;
-                        p_sb = sb;
-                        p_sph = sph;
-                        p_first = (ti == strip.x);
+                        const uint32_t bit = 1u << (seq & 31);
+                        first_mask = (ti == strip.x) ? (first_mask | bit) : (first_mask & ~bit);
+                        last_mask = (ti + 1 == strip.y) ? (last_mask | bit) : (last_mask & ~bit);
+                        // keep the logit MMAs two tasks ahead of the value MMAs: both epilogue groups stay fed
+                        if (seq >= 2) mma2(done2++);
                     }
-                    stage ^= 1;
-                    if (stage == 0) ph ^= 1u;
-                    sb ^= 1;
-                    if (sb == 0) sph ^= 1u;
-                }
-                tc_commit(&bars->a_empty);            // every MMA1 of the strip has read sA
-                if (BWD) {
-                    if (pending) mma2();
-                    tc_commit(&bars->dz_full);
                 }
             }
+            if (BWD)
+                while (done2 < seq) mma2(done2++);
         }
-    } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+    } else if (warp >= 2 && warp < 2 + kEpiWarps) {
+        // ------------------------------------------------------------------ epilogue (warps 2..17)
+        const int e = warp - 2;
+        const int group = e >> 3;                      // takes the tasks with (sequence number % 2) == group
+        const int half = (e >> 2) & 1;                 // which 32 of the task's 64 columns
         const int w4 = warp & 3;                       // TMEM lane quadrant this warp may touch
         const int r = w4 * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16);
         const float dmax = __uint_as_float(stats->dmax_bits);
         const DivConst divw = make_div(dmax);          // Dmax - Dmin, Dmin = +0
-        int stage = 0, sb = 0;
-        uint32_t ph = 0, sph = 0, dz_ph = 0;
+        uint32_t seq = 0, dz_ph = 0;
+        float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
         for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
             const int2 strip = strips[s];
-            const int I = tasks[strip.x].x;
-            const int gi = I * kTile + r;
-            const bool row_ok = gi < m;
-            const float rni = (BWD && row_ok) ? rn[gi] : 0.f;
-            float rowsum = 0.f;
-            for (int ti = strip.x; ti < strip.y; ++ti) {
-                const int4 task = tasks[ti];
+            int row_block = -1;
+            float rni = 0.f;
+            for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
+                if ((int)(seq & 1u) != group) continue;
+                const uint32_t dst = seq % kDStages, sb = seq % kSBufs;
+                mbar_wait(&bars->full_d[dst], (seq / kDStages) & 1u, fail, 10);
+                const int4 task = task_slot[dst];
+                const int gi = task.x * kTile + r;
+                const bool row_ok = gi < m;
                 const int gj0 = task.y * kTaskN;
                 const bool transposed = task.w & kTaskTransposed;
                 const bool masked = task.w & (kTaskDiagonal | kTaskRagged);
                 const bool diagonal = task.w & kTaskDiagonal;
-                mbar_wait(&bars->sg_full[sb], sph, fail, 9);
-                mbar_wait(&bars->full_d[stage], ph, fail, 10);
-                tc_fence_after();
-                const unsigned char *dstage = sD + stage * kDBytes;
-#pragma unroll 1
-                for (int chunk = 0; chunk < 2; ++chunk) {
-                    uint32_t v[32];
-                    const uint32_t taddr = lane_addr + sb * kTaskN + chunk * 32;
-                    tc_ld32(taddr, v);
-                    tc_wait_ld();
-                    if (masked) {
-                        if (transposed)
-                            epilogue_chunk<BWD, true, true>(v, dstage, r, chunk, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
-                        else
-                            epilogue_chunk<BWD, false, true>(v, dstage, r, chunk, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
-                    } else {
-                        if (transposed)
-                            epilogue_chunk<BWD, true, false>(v, dstage, r, chunk, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
-                        else
-                            epilogue_chunk<BWD, false, false>(v, dstage, r, chunk, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
-                    }
-                    if (BWD) {
-                        // G as packed bf16x2 into the first 32 columns of the buffer S came from
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int c = 0; c < 16; ++c)
-                            pk[c] = pack_bf16x2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
-                        tc_st16(lane_addr + sb * kTaskN + chunk * 16, pk);
-                    }
+                if (row_block < 0) {
+                    row_block = task.x;
+                    if (BWD) rni = row_ok ? rn[gi] : 0.f;
                 }
-                if (BWD) tc_wait_st();
+                mbar_wait(&bars->sg_full[sb], (seq / kSBufs) & 1u, fail, 9);
+                tc_fence_after();
+                const unsigned char *dstage = sD + dst * kDBytes;
+                uint32_t v[32];
+                tc_ld32(lane_addr + sb * kTaskN + half * 32, v);
+                tc_wait_ld();
+                if (masked) {
+                    if (transposed)
+                        epilogue_chunk<BWD, true, true>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
+                    else
+                        epilogue_chunk<BWD, false, true>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
+                } else {
+                    if (transposed)
+                        epilogue_chunk<BWD, true, false>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
+                    else
+                        epilogue_chunk<BWD, false, false>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
+                }
+                if (BWD) {
+                    // G as packed bf16x2 over the first half of this warp's own S columns
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        pk[c] = pack_bf16x2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                    tc_st16(lane_addr + sb * kTaskN + half * 32, pk);
+                    tc_wait_st();
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(BWD ? &bars->g_ready[sb] : &bars->sg_empty[sb]);
-                    mbar_arrive(&bars->empty_d[stage]);
+                    mbar_arrive(&bars->empty_d[dst]);
                 }
-                stage ^= 1;
-                if (stage == 0) ph ^= 1u;
-                sb ^= 1;
-                if (sb == 0) sph ^= 1u;
             }
+            // strip flush: both groups hold partial results for the strip's row block
+            const int gi = (row_block < 0 ? 0 : row_block) * kTile + r;
+            const bool row_ok = row_block >= 0 && gi < m;
             if (!BWD) {
-                if (row_ok) atomicAdd(neg + gi, rowsum);
+                if (row_ok) atomicAdd(neg + gi, (rowsum[0] + rowsum[1]) + (rowsum[2] + rowsum[3]));
+                rowsum[0] = rowsum[1] = rowsum[2] = rowsum[3] = 0.f;
             } else {
+                // every epilogue warp drains 32 of the 128 gradient columns of its lane quadrant
                 mbar_wait(&bars->dz_full, dz_ph, fail, 11);
                 dz_ph ^= 1u;
                 tc_fence_after();
-                float *orow = dzacc + (row_ok ? dz_out_row(gi, n, n_local) : 0) * kD;
-#pragma unroll 1
-                for (int chunk = 0; chunk < 4; ++chunk) {
-                    uint32_t v[32];
-                    tc_ld32(lane_addr + kDzCol + chunk * 32, v);
-                    tc_wait_ld();
-                    if (row_ok) {
+                const int gi2 = tasks[strip.x].x * kTile + r;
+                const bool ok2 = gi2 < m;
+                float *orow = dzacc + (ok2 ? dz_out_row(gi2, n, n_local) : 0) * kD;
+                const int chunk = group * 2 + half;
+                uint32_t dv[32];
+                tc_ld32(lane_addr + kDzCol + chunk * 32, dv);
+                tc_wait_ld();
+                if (ok2) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            red_add_v4(orow + chunk * 32 + q * 4, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                    }
+                    for (int q = 0; q < 8; ++q)
+                        red_add_v4(orow + chunk * 32 + q * 4, __uint_as_float(dv[4 * q]), __uint_as_float(dv[4 * q + 1]),
+                                   __uint_as_float(dv[4 * q + 2]), __uint_as_float(dv[4 * q + 3]));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -343,31 +407,32 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     if (warp == 2) tc_dealloc(tmem_base, kTmemCols);
 }
 
-int launch_sweep_tc(bool backward, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
-                    const WsView &ws, float temperature, cudaStream_t stream)
+template <bool BWD, bool SBF16>
+static int launch_one(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
+                      float temperature, cudaStream_t stream)
 {
-    if (lay.n_strips == 0) return 0;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = lay.n_strips < sms ? lay.n_strips : sms;
     const float k2 = 1.4426950408889634f / temperature;
     const int n_local = dims.n / dims.world;
-    cudaError_t e;
-    if (backward) {
-        e = cudaFuncSetAttribute(sweep_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBwd);
-        if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-        sweep_tc_kernel<true><<<grid, kTcThreads, kTcSmemBwd, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
-                                                                       ws.zb, ws.dist, ws.rn, ws.neg, ws.dzacc,
-                                                                    (Stats *)ws.stats, lay.m, dims.n, n_local, k2);
-    } else {
-        e = cudaFuncSetAttribute(sweep_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemFwd);
-        if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-        sweep_tc_kernel<false><<<grid, kTcThreads, kTcSmemFwd, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
-                                                                        ws.zb, ws.dist, ws.rn, ws.neg, ws.dzacc,
-                                                                     (Stats *)ws.stats, lay.m, dims.n, n_local, k2);
-    }
+    constexpr int smem = TcCfg<SBF16>::kSmem;
+    cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
+    sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt, ws.zb,
+                                                                   ws.dist, ws.rn, ws.neg, ws.dzacc, (Stats *)ws.stats,
+                                                                   lay.m, dims.n, n_local, k2);
     return check_launch("sweep_tc_kernel");
+}
+
+int launch_sweep_tc(bool backward, bool logits_bf16, const smh_dims_t &dims, const smh_layout_t &lay,
+                    const PlanView &plan, const WsView &ws, float temperature, cudaStream_t stream)
+{
+    if (lay.n_strips == 0) return 0;
+    if (backward) return launch_one<true, true>(dims, lay, plan, ws, temperature, stream);
+    if (logits_bf16) return launch_one<false, true>(dims, lay, plan, ws, temperature, stream);
+    return launch_one<false, false>(dims, lay, plan, ws, temperature, stream);
 }
 
 }  // namespace smh

@@ -16,9 +16,9 @@ TILE_FLOATS = TILE * TILE
 BLOCK_ROWS = 64
 BLOCK_FLOATS = BLOCK_ROWS * 128
 JP = 44
-PIECE_PITCH = 1040 // 4          # floats: one staged piece (64 rows x 4 floats) + 16 B pad
+STAGE_FLOATS = 8192              # floats of a stored tile staged per task (32 KiB, no padding)
 
-TASK_TRANSPOSED, TASK_DIAGONAL, TASK_RAGGED = 1, 2, 4
+TASK_TRANSPOSED, TASK_DIAGONAL, TASK_RAGGED, TASK_FIRST, TASK_LAST = 1, 2, 4, 8, 16
 
 
 def zt_index(row, col):
@@ -31,9 +31,10 @@ def zt_index(row, col):
 
 
 def dist_index(row, col):
-    """float index of D[row, col] inside a stored 128x128 tile: [row/64][col/4][row%64][col%4]."""
+    """float index of D[row, col] inside a stored 128x128 tile: [row/64][col/4][(row%64) ^ (col/4 % 8)][col%4]."""
     row, col = np.asarray(row), np.asarray(col)
-    return ((((row >> 6) * 32 + (col >> 2)) * 64) + (row & 63)) * 4 + (col & 3)
+    c4 = col >> 2
+    return ((((row >> 6) * 32 + c4) * 64) + ((row & 63) ^ (c4 & 7))) * 4 + (col & 3)
 
 
 def jp_index(joint, coord):
@@ -67,17 +68,21 @@ def build_plan(n: int, d: int = 128, world: int = 1, rank: int = 0, strip_len: i
     return lay, parse_plan(buf)
 
 
-def staged_piece_source(task, lane: int) -> int:
-    """Which 1 KiB piece of the stored tile the producer copies into staged slot `lane` (smh_sweep_tc.cu)."""
+def stage_task(tile: np.ndarray, task) -> np.ndarray:
+    """The 32 KiB the tile producer stages for a task (smh_sweep_tc.cu): direct -> the two 16 KiB column-half
+    slabs (rows 0..63, rows 64..127); transposed -> the 32 KiB row-half slab."""
     half = task[1] & 1
     if task[3] & TASK_TRANSPOSED:
-        return half * 32 + lane
-    return (lane >> 4) * 32 + half * 16 + (lane & 15)
+        return tile[half * 8192:(half + 1) * 8192].copy()
+    lo = tile[(half * 16) * 256:(half * 16 + 16) * 256]
+    hi = tile[(32 + half * 16) * 256:(32 + half * 16 + 16) * 256]
+    return np.concatenate([lo, hi])
 
 
 def staged_read(stage: np.ndarray, task, r: int, jl: int) -> float:
-    """The value the epilogue thread of row r reads for task column jl from the staged pieces
-    (`stage` is [32, PIECE_PITCH] floats)."""
+    """The value the epilogue thread of row r reads for task column jl from the staged 8192 floats."""
     if task[3] & TASK_TRANSPOSED:
-        return stage[r >> 2, jl * 4 + (r & 3)]
-    return stage[(r >> 6) * 16 + (jl >> 2), (r & 63) * 4 + (jl & 3)]
+        c4 = r >> 2
+        return stage[(c4 * 64 + (jl ^ (c4 & 7))) * 4 + (r & 3)]
+    c4l = jl >> 2
+    return stage[(((r >> 6) * 16 + c4l) * 64 + ((r & 63) ^ (c4l & 7))) * 4 + (jl & 3)]

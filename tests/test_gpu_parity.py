@@ -52,16 +52,17 @@ def test_weights_match_reference_bitwise(golden):
     assert R.ulp_distance(neg_w.cpu().numpy(), golden["neg_w"]).max() == 0
 
 
-@pytest.mark.parametrize("engine", ["fp32", "tf32", "auto"])
+@pytest.mark.parametrize("engine", ["fp32", "tf32", "auto", "bf16"])
 def test_step_matches_reference(golden, engine):
     z1, z2, a, b = _to_dev(golden)
     if engine == "tf32" and z1.shape[0] < 8:
         pytest.skip("tf32 logits over < 16 samples do not average to 1e-5; 'auto' picks the fp32 engine there")
+    loss_rtol = 1e-3 if engine == "bf16" else LOSS_RTOL          # BASELINE.json: bf16 mode within 1e-3
     loss, dz1, dz2, aux = ops.run_step(z1, z2, a, b, 0.5, engine, True, return_aux=True)
     stats = aux["stats"].cpu().numpy()
     assert stats[6] == 0, f"pipeline wait timed out at site {stats[6]}"
     ref = float(golden["loss_f64"])
-    assert abs(float(loss) - ref) <= LOSS_RTOL * abs(ref), (float(loss), ref)
+    assert abs(float(loss) - ref) <= loss_rtol * abs(ref), (float(loss), ref)
     for got, key in ((dz1, "dz1_f64"), (dz2, "dz2_f64")):
         cos, mx = R.grad_metrics(got.cpu().numpy(), golden[key])
         assert cos >= GRAD_COS and mx <= GRAD_MAXABS, (engine, key, cos, mx)
@@ -71,7 +72,7 @@ def test_step_matches_reference(golden, engine):
     _, _, _, neg = R.closed_form_fp64(torch.from_numpy(golden["z1"]), torch.from_numpy(golden["z2"]),
                                       torch.from_numpy(golden["pos_w"]), torch.from_numpy(golden["neg_w"]))
     rel = (aux["neg"].cpu().double() - neg).abs() / neg
-    assert rel.max() < (2e-6 if ops.resolve_engine(engine, z1.shape[0]) == "fp32" else 2e-4)
+    assert rel.max() < {"fp32": 2e-6, "tf32": 2e-4, "bf16": 4e-3}[ops.resolve_engine(engine, z1.shape[0])]
 
 
 def test_drop_in_api_and_autograd(golden):
@@ -101,17 +102,17 @@ def test_step_matches_c_oracle_mid_size(n, jset):
     a, b = j1[:, :, :2], j2[:, :, :2]
     ref = R.c_step(z1, z2, a, b)
     dev = _dev()
-    for engine in ("tf32", "fp32"):
+    for engine in ("tf32", "fp32", "bf16"):
         loss, dz1, dz2, aux = ops.run_step(z1.to(dev), z2.to(dev), j1.to(dev)[:, :, :2], j2.to(dev)[:, :, :2],
                                            0.5, engine, True, return_aux=True)
         assert aux["stats"].cpu().numpy()[6] == 0
-        assert abs(float(loss) - ref["loss"]) <= LOSS_RTOL * abs(ref["loss"])
+        assert abs(float(loss) - ref["loss"]) <= (1e-3 if engine == "bf16" else LOSS_RTOL) * abs(ref["loss"])
         cos, mx = R.grad_metrics(torch.cat([dz1, dz2]).cpu().numpy(), np.concatenate([ref["dz1"], ref["dz2"]]))
         assert cos >= GRAD_COS and mx <= GRAD_MAXABS, (engine, cos, mx)
         stats = aux["stats"].cpu().numpy().view(np.float32)
         assert stats[0] == ref["stats"]["dmax"] and stats[1] == ref["stats"]["pmax"]
         rel = np.abs(aux["neg"].cpu().numpy().astype(np.float64) - ref["neg"]) / ref["neg"]
-        assert rel.max() < 2e-4
+        assert rel.max() < (4e-3 if engine == "bf16" else 2e-4)
 
 
 def test_non_contiguous_and_half_inputs():

@@ -165,7 +165,7 @@ def stage_big():
     dev = torch.device("cuda")
     z1, z2, j1, j2 = synth.make_batch(8192, 128, 5, "hand")
     a, b, c, d = z1.to(dev), z2.to(dev), j1.to(dev), j2.to(dev)
-    for engine in ("tf32", "fp32"):
+    for engine in ("tf32", "bf16", "fp32"):
         for it in range(3):
             torch.cuda.synchronize()
             t0 = time.time()
@@ -192,7 +192,8 @@ def main():
             rc |= p.returncode
         sys.exit(1 if rc else 0)
     fn = {"selftest": stage_selftest, "weights": stage_weights, "fp32": lambda: stage_engine("fp32"),
-          "probe": stage_probe, "tc": lambda: stage_engine("tf32"), "big": stage_big}[what]
+          "probe": stage_probe, "tc": lambda: stage_engine("tf32"), "bf16": lambda: stage_engine("bf16"),
+          "big": stage_big}[what]
     fn()
 
 
