@@ -15,60 +15,60 @@
 
 namespace smh {
 
-template <bool FAST>
+// MODE 0: IEEE intrinsics (any input).  MODE 1: branch-free exact forms with the zero guard.  MODE 2: without the
+// guard (a coincident joint gives NaN; the caller repairs that pair with MODE 1).
+// distances of joints (2p, 2p+1) of one pair of samples
+template <int MODE>
+__device__ __forceinline__ f2 joint_pair(const f2 ax, const f2 ay, const float *__restrict__ col, int p)
+{
+    const float4 b = *reinterpret_cast<const float4 *>(col + 4 * p);   // (bx_2p, bx_2p+1, by_2p, by_2p+1)
+    f2 dx = sub2(ax, pack2(b.x, b.y));
+    f2 dy = sub2(ay, pack2(b.z, b.w));
+    f2 x = fma2(dy, dy, mul2(dx, dx));
+    if (MODE == 2) return sqrt2_rn_fast_nz(x);
+    if (MODE == 1) return sqrt2_rn_fast(x);
+    float x0, x1;
+    unpack2(x, x0, x1);
+    return pack2(__fsqrt_rn(x0), __fsqrt_rn(x1));
+}
+
+// Joints are evaluated in the order the ATen summation consumes them (16..20 first, then k and k+8 together), so only
+// two pair results are live at a time.
+template <int MODE>
 __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10], float ax20, float ay20,
                                            const float *__restrict__ col, const DivConst &div21)
 {
-    f2 nn[10];
-#pragma unroll
-    for (int p = 0; p < 10; ++p) {
-        const float4 b = *reinterpret_cast<const float4 *>(col + 4 * p);   // (bx_2p, bx_2p+1, by_2p, by_2p+1)
-        f2 dx = sub2(ax[p], pack2(b.x, b.y));
-        f2 dy = sub2(ay[p], pack2(b.z, b.w));
-        f2 x = fma2(dy, dy, mul2(dx, dx));
-        if (FAST) {
-            nn[p] = sqrt2_rn_fast(x);
-        } else {
-            float x0, x1;
-            unpack2(x, x0, x1);
-            nn[p] = pack2(__fsqrt_rn(x0), __fsqrt_rn(x1));
-        }
-    }
-    const float2 b20 = *reinterpret_cast<const float2 *>(col + 40);
-    const float dx20 = __fsub_rn(ax20, b20.x), dy20 = __fsub_rn(ay20, b20.y);
-    const float x20 = __fmaf_rn(dy20, dy20, __fmul_rn(dx20, dx20));
-    const float n20 = FAST ? sqrt_rn_fast(x20) : __fsqrt_rn(x20);
-
+    constexpr bool FAST = MODE != 0;
     float a, b;
-    unpack2(nn[8], a, b);                 // (n16, n17)
+    unpack2(joint_pair<MODE>(ax[8], ay[8], col, 8), a, b);          // (n16, n17)
     float s = __fadd_rn(a, b);
-    unpack2(nn[9], a, b);                 // (n18, n19)
+    unpack2(joint_pair<MODE>(ax[9], ay[9], col, 9), a, b);          // (n18, n19)
     s = __fadd_rn(s, a);
     s = __fadd_rn(s, b);
-    s = __fadd_rn(s, n20);
+    {
+        const float2 b20 = *reinterpret_cast<const float2 *>(col + 40);
+        const float dx20 = __fsub_rn(ax20, b20.x), dy20 = __fsub_rn(ay20, b20.y);
+        const float x20 = __fmaf_rn(dy20, dy20, __fmul_rn(dx20, dx20));
+        s = __fadd_rn(s, MODE == 2 ? sqrt_rn_fast_nz(x20) : (MODE == 1 ? sqrt_rn_fast(x20) : __fsqrt_rn(x20)));
+    }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        f2 t = add2(nn[p], nn[p + 4]);    // (n_2p + n_2p+8, n_2p+1 + n_2p+9)
-        unpack2(t, a, b);
+        f2 t = add2(joint_pair<MODE>(ax[p], ay[p], col, p), joint_pair<MODE>(ax[p + 4], ay[p + 4], col, p + 4));
+        unpack2(t, a, b);                 // (n_2p + n_2p+8, n_2p+1 + n_2p+9)
         s = __fadd_rn(s, a);
         s = __fadd_rn(s, b);
     }
     return FAST ? div_fast(s, div21) : __fdiv_rn(s, 21.0f);
 }
 
-template <bool FAST>
+// MODE as in joint_pair.  vmax_bits: running maximum of the integer image of D (D >= 0; NaN is larger than any finite).
+template <int MODE>
 __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, float *__restrict__ tile_out, int I,
-                                                int J, int m, float *cs, float &vmax)
+                                                int J, int m, const float *cs, uint32_t &vmax_bits)
 {
     const int t = threadIdx.x;
     const int r = t & 127;
     const int h = t >> 7;
-    // stage the 128 column samples (contiguous 128 x 44 floats)
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(jp + (int64_t)J * kTile * kJP);
-        float4 *dst = reinterpret_cast<float4 *>(cs);
-        for (int i = t; i < kTile * kJP / 4; i += 256) dst[i] = src[i];
-    }
     // this thread's row sample in registers
     f2 ax[10], ay[10];
     float ax20, ay20;
@@ -84,7 +84,6 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, fl
         ax20 = v.x;
         ay20 = v.y;
     }
-    __syncthreads();
     const DivConst div21 = make_div(21.0f);
     const bool row_ok = (I * kTile + r) < m;
     const int col_limit = m - J * kTile;          // columns >= col_limit are padding
@@ -94,8 +93,8 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, fl
         float dv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            dv[u] = mpjpe_one<FAST>(ax, ay, ax20, ay20, cs + (c0 + u) * kJP, div21);
-            if (row_ok && (c0 + u) < col_limit) vmax = fmaxf(vmax, dv[u]);
+            dv[u] = mpjpe_one<MODE>(ax, ay, ax20, ay20, cs + (c0 + u) * kJP, div21);
+            if (row_ok && (c0 + u) < col_limit) vmax_bits = max(vmax_bits, __float_as_uint(dv[u]));
         }
         *reinterpret_cast<float4 *>(tile_out + dist_index(r, c0)) = make_float4(dv[0], dv[1], dv[2], dv[3]);
     }
@@ -106,23 +105,48 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float
              Stats *__restrict__ stats)
 {
     __shared__ __align__(16) float cs[kTile * kJP];
-    __shared__ float wmax[8];
+    __shared__ uint32_t wmax[8];
     const int2 ij = tiles[blockIdx.x];
     float *tile_out = dist + (int64_t)blockIdx.x * kTileFloats;
-    float vmax = 0.f;
-    const uint32_t flags = stats->flags;
-    if (flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE))
-        mpjpe_tile_body<false>(jp, tile_out, ij.x, ij.y, m, cs, vmax);
-    else
-        mpjpe_tile_body<true>(jp, tile_out, ij.x, ij.y, m, cs, vmax);
-    vmax = warp_max(vmax);
-    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = vmax;
+    // stage the 128 column samples (contiguous 128 x 44 floats)
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(jp + (int64_t)ij.y * kTile * kJP);
+        float4 *dst = reinterpret_cast<float4 *>(cs);
+        for (int i = threadIdx.x; i < kTile * kJP / 4; i += 256) dst[i] = src[i];
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float v = wmax[0];
+    const uint32_t flags = stats->flags;
+    const bool slow = flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE);
+    uint32_t vmax_bits = 0u;
+    if (slow)
+        mpjpe_tile_body<0>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
+    else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
+        mpjpe_tile_body<1>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);     // zero distances: diagonal, zero padding
+    else
+        mpjpe_tile_body<2>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
+    auto block_max = [&](uint32_t v) {
 #pragma unroll
-        for (int w = 1; w < 8; ++w) v = fmaxf(v, wmax[w]);
-        atomicMax(&stats->dmax_bits, __float_as_uint(v));
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = wmax[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) v = max(v, wmax[w]);
+        return v;
+    };
+    uint32_t bmax = block_max(vmax_bits);
+    if (!slow && bmax > 0x7f800000u) {
+        // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo the tile guarded
+        vmax_bits = 0u;
+        mpjpe_tile_body<1>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
+        bmax = block_max(vmax_bits);
+    }
+    if (threadIdx.x == 0) {
+        if (bmax > 0x7f800000u)
+            atomicOr(&stats->flags, SMH_FLAG_NONFINITE);      // non-finite inputs (IEEE path): the loss is NaN
+        else
+            atomicMax(&stats->dmax_bits, bmax);
     }
 }
 

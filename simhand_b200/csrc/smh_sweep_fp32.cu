@@ -103,7 +103,7 @@ sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strip
                         rowsum[p] += e;
                     } else {
                         const float rnj = (gj < m) ? rn[gj] : 0.f;
-                        Gs[jl * kPitch + r] = w * e * (rni[p] + rnj);
+                        Gs[jl * kPitch + r] = valid ? w * e * (rni[p] + rnj) : 0.f;
                     }
                 }
             }

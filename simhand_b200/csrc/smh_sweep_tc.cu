@@ -87,15 +87,17 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned
             const float s = __uint_as_float(v[c]);
             const float w = div_fast(__fsub_rn(dmax, dv[u]), divw);
             float e = ex2_approx(s * (w * k2));
+            float g = BWD ? w * e * (rni + rnjv[u]) : 0.f;
             if (MASKED) {
                 const int gj = gj0 + jl + u;
                 const bool valid = (gi < m) && (gj < m) && !(diagonal && gi == gj);
                 e = valid ? e : 0.f;
+                g = valid ? g : 0.f;
             }
             if (!BWD) {
                 rowsum[u] += e;
             } else {
-                v[c] = __float_as_uint(w * e * (rni + rnjv[u]));
+                v[c] = __float_as_uint(g);
             }
         }
     }

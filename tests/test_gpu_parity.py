@@ -167,6 +167,30 @@ def test_slow_domain_inputs_use_ieee_path():
     assert R.ulp_distance(neg_w.cpu().numpy(), want).max() == 0
 
 
+def test_coincident_joints_take_the_guarded_redo():
+    """The hot MPJPE loop has no zero guard: a joint shared by two different samples (zero distance in an
+    off-diagonal tile) makes it produce NaN, which the kernel notices through the integer max and repairs by
+    redoing the tile with the guarded form.  Result must still be bit-exact."""
+    dev = _dev()
+    z1, z2, j1, j2 = synth.make_batch(200, 128, 31, "uniform")
+    j1[150] = j1[5]                       # duplicate sample: all 21 distances zero, tiles (0, 1)
+    j2[77, 3] = j1[190, 3]                # one shared joint across the two views, tiles (1, 2)
+    a, b = j1[:, :, :2], j2[:, :, :2]
+    pos_w, neg_w = ops.mpjpe_weights(a.to(dev), b.to(dev))
+    bj = R.pack_joints(a, b)
+    dmax, dmin = R.c_minmax(bj)
+    want = R.c_neg_weights_rows(bj, 0, 400, dmax, dmin)
+    got = neg_w.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert R.ulp_distance(got, want).max() == 0
+    assert got[5, 150] == 1.0 and got[150, 5] == 1.0
+    ref = R.c_step(z1, z2, a, b)
+    loss, dz1, dz2 = ops.run_step(z1.to(dev), z2.to(dev), a.to(dev), b.to(dev), 0.5, "tf32", True)
+    assert abs(float(loss) - ref["loss"]) <= LOSS_RTOL * abs(ref["loss"])
+    cos, mx = R.grad_metrics(torch.cat([dz1, dz2]).cpu().numpy(), np.concatenate([ref["dz1"], ref["dz2"]]))
+    assert cos >= GRAD_COS and mx <= GRAD_MAXABS
+
+
 def test_l2_normalize_matches_torch():
     dev = _dev()
     g = torch.Generator().manual_seed(1)
