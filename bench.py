@@ -155,15 +155,41 @@ def run_ours(args):
     dz1_, dz2_, dj1, dj2 = hz1.to(dev), hz2.to(dev), hj1.to(dev), hj2.to(dev)
     engine = args.engine
 
-    def step(a, b, c, e):
-        if world == 1:
-            return ops.run_step(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True)
-        return run_step_sharded(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True, group)
-
     def barrier():
         if world > 1:
             dist.barrier(group)
         torch.cuda.synchronize(dev)
+
+    transport = args.transport
+
+    def eager_step(a, b, c, e):
+        if world == 1:
+            return ops.run_step(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True)
+        return run_step_sharded(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True, group, transport=transport)
+
+    # The step is a fixed sequence of kernel launches on one stream (no host decisions, no NCCL when the peer
+    # exchange is used): capture it once into a CUDA graph and replay it, as a training loop would.
+    use_graph = args.graph and (world == 1 or transport != "nccl")
+    graph = None
+    if use_graph:
+        for _ in range(3):
+            eager_step(dz1_, dz2_, dj1, dj2)
+        barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = eager_step(dz1_, dz2_, dj1, dj2)
+        barrier()
+
+    def step(a, b, c, e):
+        if graph is None:
+            return eager_step(a, b, c, e)
+        if a is not dz1_:
+            dz1_.copy_(a, non_blocking=True)
+            dz2_.copy_(b, non_blocking=True)
+            dj1.copy_(c, non_blocking=True)
+            dj2.copy_(e, non_blocking=True)
+        graph.replay()
+        return static_out
 
     for _ in range(max(args.warmup, 3)):
         loss, g1, g2 = step(dz1_, dz2_, dj1, dj2)
@@ -187,10 +213,13 @@ def run_ours(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        a = hz1.to(dev, non_blocking=True)
-        b = hz2.to(dev, non_blocking=True)
-        c = hj1.to(dev, non_blocking=True)
-        e = hj2.to(dev, non_blocking=True)
+        if graph is None:
+            a = hz1.to(dev, non_blocking=True)
+            b = hz2.to(dev, non_blocking=True)
+            c = hj1.to(dev, non_blocking=True)
+            e = hj2.to(dev, non_blocking=True)
+        else:
+            a, b, c, e = hz1, hz2, hj1, hj2          # copied H2D into the graph's static inputs inside step()
         loss, g1, g2 = step(a, b, c, e)
         host_loss.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the loss every step
@@ -225,13 +254,14 @@ def run_ours(args):
                 dtype={"tf32": "tf32", "bf16": "bf16"}.get(engine, "f32"), data="synthetic",
                 config=dict(workload="handclr_w loss fwd+bwd, global batch 8192 (2N=16384), d=128, 21 joints, "
                                      "mpjpe/linear/pos_neg, tau 0.5", global_batch=N_PER_VIEW, proj_dim=DIM,
-                            engine=engine, parallelism=f"row/tile-sharded x{world}" if world > 1 else "single GPU",
+                            engine=engine, parallelism=f"tile-pair sharded x{world}" if world > 1 else "single GPU",
+                            transport=(transport if world > 1 else None), cuda_graph=bool(graph is not None),
                             l2="per-step working set (MPJPE tile workspace, 0.5 GiB at 1 GPU) exceeds the 126 MB L2; "
                                "no explicit flush"),
                 clocks=clocks,
                 e2e=dict(value=1e3 / (ms_e2e / args.steps), unit=UNIT,
                          h2d_bytes_per_step=int(hz1.numel() * 8 + hj1.numel() * 8), d2h_bytes_per_step=4),
-                gpu_launches=6 * args.steps * 1)
+                gpu_launches=(6 if world == 1 else 13) * args.steps)
     if kernels is not None:
         f_clk = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
         xu_peak = NUM_SMS * MUFU_LANES_PER_SM * f_clk * 1e6 / 1e9          # G special-function ops / s
@@ -272,9 +302,9 @@ def time_kernels(ops, _lib, z1, z2, j1, j2, engine, iters):
     pd, pi, plan = ctypes.byref(ctx.dims), ctypes.byref(inp), ctx.plan_dev.data_ptr()
     calls = [
         ("prep", lambda: lib.smh_prep(pd, pi, ws.data_ptr(), eng, st)),
-        ("mpjpe_kernel", lambda: lib.smh_mpjpe(pd, plan, ws.data_ptr(), st)),
-        ("sweep_fwd", lambda: lib.smh_forward(pd, plan, ws.data_ptr(), TAU, eng, st)),
-        ("sweep_bwd", lambda: lib.smh_backward(pd, plan, ws.data_ptr(), TAU, eng, st)),
+        ("mpjpe_kernel", lambda: lib.smh_mpjpe(pd, plan, ws.data_ptr(), None, st)),
+        ("sweep_fwd", lambda: lib.smh_forward(pd, plan, ws.data_ptr(), TAU, eng, None, st)),
+        ("sweep_bwd", lambda: lib.smh_backward(pd, plan, ws.data_ptr(), TAU, eng, None, st)),
         ("finalize", lambda: lib.smh_finalize(pd, pi, ws.data_ptr(), None, TAU, 1.0, loss.data_ptr(), g1.data_ptr(),
                                               g2.data_ptr(), d, st)),
     ]
@@ -300,6 +330,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="tf32", choices=["tf32", "fp32", "auto", "bf16"])
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU exchange: collectives fused into the kernels over peer memory, or NCCL calls")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the step eagerly")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 30)

@@ -50,6 +50,7 @@ extern "C" {
 #define SMH_ENGINE_TC_TF32 0     /* tcgen05: tf32 logits in the forward sweep, bf16 operands in the backward sweep */
 #define SMH_ENGINE_FP32 1        /* CUDA-core FFMA, fp32 accumulate (exact-fp32 mode) */
 #define SMH_ENGINE_TC_BF16 2     /* tcgen05: bf16 operands in both sweeps (bf16 mode) */
+#define SMH_PREP_NO_ZERO 0x100   /* OR into smh_prep's engine: the accumulators were already zeroed by smh_prep_zero */
 
 /* problem description shared by all calls */
 typedef struct smh_dims {
@@ -92,7 +93,7 @@ typedef struct smh_stats {
     float loss;                  /* final loss (also written to the caller's pointer) */
     uint32_t counter;            /* internal: last-block-done ticket */
     uint32_t fail_site;          /* != 0: a bounded pipeline wait timed out (result invalid) */
-    uint32_t pad;
+    uint32_t ticket2;            /* internal: last-block-done ticket of the MPJPE kernel (peer exchange) */
 } smh_stats_t;
 
 #define SMH_FLAG_SLOW_DOMAIN 1u  /* joints outside the fast exact-sqrt domain: IEEE slow path used */
@@ -112,6 +113,20 @@ typedef struct smh_inputs {
     int64_t z_rank_stride, j_rank_stride;/* elements between rank chunks (ignored when world == 1) */
 } smh_inputs_t;
 
+/* Peer exchange (world > 1, optional): the ranks' workspaces and input staging buffers are symmetric allocations
+ * mapped into every process (torch.distributed._symmetric_memory or CUDA IPC); with it the kernels do the
+ * collectives themselves over NVLink: the MPJPE kernel's last CTA pushes Dmax to every peer (atomicMax), the
+ * forward sweep adds its row sums into every peer's `neg`, the backward sweep adds its gradient rows straight into
+ * the owning rank's accumulator (red.global.add.v4.f32 on peer pointers), and smh_barrier separates the phases.
+ * Without it (exch == NULL) the caller runs all-reduce / reduce-scatter between the calls. */
+#define SMH_MAX_PEERS 8
+typedef struct smh_exchange {
+    int32_t world, rank;
+    void *ws_peer[SMH_MAX_PEERS];        /* workspace blob of every rank (ws_peer[rank] == the local ws_dev) */
+    void *xin_peer[SMH_MAX_PEERS];       /* gathered-input buffer of every rank: world x chunk floats */
+    void *signal_peer[SMH_MAX_PEERS];    /* 64 x uint32 barrier words of every rank (zero-initialised once) */
+} smh_exchange_t;
+
 int smh_version(void);
 const char *smh_last_error(void);
 
@@ -126,23 +141,32 @@ int smh_plan_build(const smh_dims_t *dims, void *plan_host, int64_t plan_bytes);
  * SMH_ENGINE_FP32), positive-pair MPJPE (utils.py:229-231), zeroes the accumulators.  Replaces the
  * torch.cat calls of utils.py:237-239 and :407. */
 int smh_prep(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, int engine, void *stream);
+/* zeroes the accumulators only (peer exchange: must precede the barrier after which peers may add into them) */
+int smh_prep_zero(const smh_dims_t *dims, void *ws_dev, void *stream);
 
 /* K0: all-pairs MPJPE tiles of this rank (upper triangle) + running max (utils.py:251-255). */
-int smh_mpjpe(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, void *stream);
+int smh_mpjpe(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, const smh_exchange_t *exch, void *stream);
 
 /* K1: weighted logits, exp and off-diagonal row sums (utils.py:411-417) -> ws.neg (partial sums of
  * this rank's tasks for all M rows). */
 int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature,
-                int engine, void *stream);
+                int engine, const smh_exchange_t *exch, void *stream);
 
 /* K2: dz accumulation (autograd of utils.py:411-426) -> ws.dzacc (partial sums of
  * this rank's tasks for all M rows, rows in rank-major order).  Needs ws.neg complete. */
 int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature,
-                 int engine, void *stream);
+                 int engine, const smh_exchange_t *exch, void *stream);
+
+/* peer exchange: copy this rank's packed inputs ([z1|z2|joints1|joints2], `floats` fp32) into slot `rank` of every
+ * peer's gathered-input buffer (the all-gather of SURVEY.md 8e, push-based over NVLink) */
+int smh_push_inputs(const smh_exchange_t *exch, const float *local_dev, int64_t floats, void *stream);
+/* peer exchange: device-side barrier over all ranks (monotonic counters in signal_peer; CUDA-graph safe) */
+int smh_barrier(const smh_exchange_t *exch, void *stream);
 
 /* loss (utils.py:420-426) over all M rows and, if dz1_dev != NULL, the gradients of the local
  * samples: dz = dzacc_src / (M tau) - 2 Wp z_partner / (M tau), scaled by grad_scale.
- * dzacc_src_dev is ws.dzacc (world == 1) or the reduce-scattered [2 * n_local][128] block. */
+ * dzacc_src_dev: NULL = all M rows in ws.dzacc (world == 1); otherwise this rank's own [2 * n_local][128] block
+ * (the reduce-scattered buffer, or ws.dzacc itself when the peer exchange accumulated into it). */
 int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev,
                  const float *dzacc_src_dev, float temperature, float grad_scale,
                  float *loss_dev, float *dz1_dev, float *dz2_dev, int64_t dz_row_stride,

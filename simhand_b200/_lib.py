@@ -15,6 +15,7 @@ ENGINE_FP32 = 1
 ENGINE_TC_BF16 = 2
 ENGINES = {"tf32": ENGINE_TC_TF32, "tc": ENGINE_TC_TF32, "fp32": ENGINE_FP32, "bf16": ENGINE_TC_BF16}
 
+PREP_NO_ZERO = 0x100
 FLAG_SLOW_DOMAIN = 1
 FLAG_NONFINITE = 2
 
@@ -41,16 +42,26 @@ class Inputs(ctypes.Structure):
                 ("z_rank_stride", ctypes.c_int64), ("j_rank_stride", ctypes.c_int64)]
 
 
+MAX_PEERS = 8
+
+
+class Exchange(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32),
+                ("ws_peer", ctypes.c_void_p * MAX_PEERS), ("xin_peer", ctypes.c_void_p * MAX_PEERS),
+                ("signal_peer", ctypes.c_void_p * MAX_PEERS)]
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("dmax_bits", ctypes.c_uint32), ("pmax_bits", ctypes.c_uint32), ("pmin_inv", ctypes.c_uint32),
                 ("flags", ctypes.c_uint32), ("loss", ctypes.c_float), ("counter", ctypes.c_uint32),
-                ("fail_site", ctypes.c_uint32), ("pad", ctypes.c_uint32)]
+                ("fail_site", ctypes.c_uint32), ("ticket2", ctypes.c_uint32)]
 
 
 # every symbol include/simhand_b200.h declares (tests check that the library exports all of them)
 EXPORTS = ("smh_version", "smh_last_error", "smh_layout", "smh_plan_build", "smh_prep", "smh_mpjpe",
            "smh_forward", "smh_backward", "smh_finalize", "smh_weights_dense", "smh_l2norm_fwd",
-           "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params")
+           "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params", "smh_push_inputs",
+           "smh_barrier", "smh_prep_zero")
 
 _lib = None
 
@@ -71,9 +82,13 @@ def load() -> ctypes.CDLL:
     lib.smh_layout.argtypes = [pd, pl]
     lib.smh_plan_build.argtypes = [pd, vp, i64]
     lib.smh_prep.argtypes = [pd, pi, vp, ctypes.c_int, vp]
-    lib.smh_mpjpe.argtypes = [pd, vp, vp, vp]
-    lib.smh_forward.argtypes = [pd, vp, vp, f32, ctypes.c_int, vp]
-    lib.smh_backward.argtypes = [pd, vp, vp, f32, ctypes.c_int, vp]
+    px = ctypes.POINTER(Exchange)
+    lib.smh_mpjpe.argtypes = [pd, vp, vp, px, vp]
+    lib.smh_forward.argtypes = [pd, vp, vp, f32, ctypes.c_int, px, vp]
+    lib.smh_backward.argtypes = [pd, vp, vp, f32, ctypes.c_int, px, vp]
+    lib.smh_push_inputs.argtypes = [px, vp, i64, vp]
+    lib.smh_barrier.argtypes = [px, vp]
+    lib.smh_prep_zero.argtypes = [pd, vp, vp]
     lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, vp]
     lib.smh_weights_dense.argtypes = [pd, vp, vp, vp, vp, vp]
     lib.smh_l2norm_fwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]

@@ -199,6 +199,33 @@ static PlanView carve_plan(const void *plan, const smh_layout_t &lay)
     return v;
 }
 
+static int make_peers(const smh_dims_t &dims, const smh_layout_t &lay, void *ws_dev, const smh_exchange_t *exch,
+                      Peers *out)
+{
+    memset(out, 0, sizeof(*out));
+    out->off_stats = lay.off_stats;
+    out->off_neg = lay.off_neg;
+    out->off_dzacc = lay.off_dzacc;
+    if (!exch) {
+        out->world = 1;
+        out->rank = 0;
+        out->ws[0] = (unsigned char *)ws_dev;
+        return 0;
+    }
+    if (exch->world != dims.world || exch->rank != dims.rank || exch->world > SMH_MAX_PEERS)
+        return set_error(SMH_E_DIM, "exchange world/rank %d/%d does not match dims %d/%d (max %d peers)", exch->world,
+                         exch->rank, dims.world, dims.rank, SMH_MAX_PEERS);
+    if (exch->ws_peer[exch->rank] != ws_dev)
+        return set_error(SMH_E_ARG, "exchange ws_peer[rank] must be the local workspace");
+    out->world = exch->world;
+    out->rank = exch->rank;
+    for (int p = 0; p < exch->world; ++p) {
+        if (!exch->ws_peer[p]) return set_error(SMH_E_ARG, "exchange ws_peer[%d] is null", p);
+        out->ws[p] = (unsigned char *)exch->ws_peer[p];
+    }
+    return 0;
+}
+
 static int check_ptr(const void *p, const char *name, int align)
 {
     if (!p) return set_error(SMH_E_ARG, "%s is null", name);
@@ -291,39 +318,61 @@ int smh_prep(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, int e
     SMH_COMMON_PROLOGUE(false)
     (void)plan_dev;
     if ((rc = check_inputs(*dims, in))) return rc;
+    const bool zero = !(engine & SMH_PREP_NO_ZERO);
+    engine &= ~SMH_PREP_NO_ZERO;
     if (engine != SMH_ENGINE_TC_TF32 && engine != SMH_ENGINE_FP32 && engine != SMH_ENGINE_TC_BF16)
         return set_error(SMH_E_MODE, "unknown engine %d", engine);
+    if (zero) {
+        cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)(lay.off_posd - lay.off_stats), st);
+        if (e != cudaSuccess) return set_error((int)e, "prep memset: %s", cudaGetErrorString(e));
+    }
     return launch_prep(*dims, lay, *in, ws, engine == SMH_ENGINE_TC_TF32, st);
 }
 
-int smh_mpjpe(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, void *stream)
+int smh_prep_zero(const smh_dims_t *dims, void *ws_dev, void *stream)
+{
+    const void *plan_dev = nullptr;
+    SMH_COMMON_PROLOGUE(false)
+    (void)plan_dev;
+    cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)(lay.off_posd - lay.off_stats), st);
+    if (e != cudaSuccess) return set_error((int)e, "prep memset: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int smh_mpjpe(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, const smh_exchange_t *exch, void *stream)
 {
     SMH_COMMON_PROLOGUE(true)
-    return launch_mpjpe(*dims, lay, carve_plan(plan_dev, lay), ws, st);
+    Peers peers;
+    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
+    return launch_mpjpe(*dims, lay, carve_plan(plan_dev, lay), ws, peers, st);
 }
 
 int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature, int engine,
-                void *stream)
+                const smh_exchange_t *exch, void *stream)
 {
     SMH_COMMON_PROLOGUE(true)
     if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
     PlanView pv = carve_plan(plan_dev, lay);
+    Peers peers;
+    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
-        return launch_sweep_tc(false, engine == SMH_ENGINE_TC_BF16, *dims, lay, pv, ws, temperature, st);
-    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, *dims, lay, pv, ws, temperature, st);
+        return launch_sweep_tc(false, engine == SMH_ENGINE_TC_BF16, *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
 
 int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature, int engine,
-                 void *stream)
+                 const smh_exchange_t *exch, void *stream)
 {
     SMH_COMMON_PROLOGUE(true)
     if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
     PlanView pv = carve_plan(plan_dev, lay);
+    Peers peers;
+    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
     if ((rc = launch_rn(lay, ws, st))) return rc;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
-        return launch_sweep_tc(true, true, *dims, lay, pv, ws, temperature, st);
-    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, *dims, lay, pv, ws, temperature, st);
+        return launch_sweep_tc(true, true, *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
 
@@ -338,8 +387,10 @@ int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, c
     if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
     if ((dz1_dev == nullptr) != (dz2_dev == nullptr)) return set_error(SMH_E_ARG, "dz1/dz2 must both be set or null");
     if (dz1_dev && dz_row_stride < dims->d) return set_error(SMH_E_ARG, "dz_row_stride < d");
-    if (dz1_dev && !dzacc_src_dev) dzacc_src_dev = ws.dzacc;
-    return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, temperature, grad_scale, loss_dev, dz1_dev,
+    // NULL: all rows in the local accumulator (rank-major); otherwise this rank's own [2 n_local][128] block
+    const bool local_block = dzacc_src_dev != nullptr;
+    if (!dzacc_src_dev) dzacc_src_dev = ws.dzacc;
+    return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, local_block, temperature, grad_scale, loss_dev, dz1_dev,
                            dz2_dev, dz_row_stride, st);
 }
 
@@ -350,6 +401,21 @@ int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev
     if (dims->world != 1) return set_error(SMH_E_DIM, "smh_weights_dense needs world == 1");
     if (!pos_w_dev && !neg_w_dev) return set_error(SMH_E_ARG, "no output requested");
     return launch_weights_dense(*dims, lay, carve_plan(plan_dev, lay), ws, pos_w_dev, neg_w_dev, st);
+}
+
+int smh_push_inputs(const smh_exchange_t *exch, const float *local_dev, int64_t floats, void *stream)
+{
+    if (!exch || !local_dev || floats <= 0) return set_error(SMH_E_ARG, "push_inputs: null exchange/buffer");
+    if (exch->world < 1 || exch->world > SMH_MAX_PEERS) return set_error(SMH_E_DIM, "bad exchange world %d", exch->world);
+    if (floats % 4) return set_error(SMH_E_ALIGN, "push_inputs: length must be a multiple of 4 floats");
+    return launch_push_inputs(*exch, local_dev, floats, (cudaStream_t)stream);
+}
+
+int smh_barrier(const smh_exchange_t *exch, void *stream)
+{
+    if (!exch) return set_error(SMH_E_ARG, "barrier: null exchange");
+    if (exch->world < 1 || exch->world > SMH_MAX_PEERS) return set_error(SMH_E_DIM, "bad exchange world %d", exch->world);
+    return launch_barrier(*exch, (cudaStream_t)stream);
 }
 
 int smh_l2norm_fwd(const float *x_dev, float *y_dev, float *norm_dev, int64_t rows, int32_t d, float eps,

@@ -97,13 +97,13 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
 }
 
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
-                    const float *dzacc_src, float temperature, float grad_scale, float *loss, float *dz1,
+                    const float *dzacc_src, bool local_block, float temperature, float grad_scale, float *loss, float *dz1,
                     float *dz2, int64_t dz_row_stride, cudaStream_t stream)
 {
     const int blocks = (lay.m + 7) / 8 < 1184 ? (lay.m + 7) / 8 : 1184;
     const int n_local = dims.n / dims.world;
-    // the reduce-scattered block starts at this rank's first row; the full accumulator at row 0
-    const int64_t src_off = (dzacc_src == ws.dzacc) ? 0 : (int64_t)dims.rank * 2 * n_local;
+    // a rank-local block (reduce-scattered buffer or peer-exchange accumulator) starts at this rank's first row
+    const int64_t src_off = local_block ? (int64_t)dims.rank * 2 * n_local : 0;
     smh_inputs_t inp = in;
     inp.n_local = in.n_local;
     finalize_kernel<<<blocks, 256, 0, stream>>>(inp, dims.n, dims.d, dims.rank, ws.neg, ws.posd, ws.rowloss,

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "../../include/simhand_b200.h"
+#include "smh_common.cuh"
 
 namespace smh {
 
@@ -34,14 +35,16 @@ int check_launch(const char *what);
 int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
                 bool round_tf32, cudaStream_t stream);
 int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
-                 cudaStream_t stream);
+                 const Peers &peers, cudaStream_t stream);
 int launch_sweep_fp32(bool backward, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
-                      const WsView &ws, float temperature, cudaStream_t stream);
+                      const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
 int launch_sweep_tc(bool backward, bool logits_bf16, const smh_dims_t &dims, const smh_layout_t &lay,
-                    const PlanView &plan, const WsView &ws, float temperature, cudaStream_t stream);
+                    const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
+int launch_push_inputs(const smh_exchange_t &exch, const float *local, int64_t floats, cudaStream_t stream);
+int launch_barrier(const smh_exchange_t &exch, cudaStream_t stream);
 int launch_rn(const smh_layout_t &lay, const WsView &ws, cudaStream_t stream);
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
-                    const float *dzacc_src, float temperature, float grad_scale, float *loss, float *dz1,
+                    const float *dzacc_src, bool local_block, float temperature, float grad_scale, float *loss, float *dz1,
                     float *dz2, int64_t dz_row_stride, cudaStream_t stream);
 int launch_weights_dense(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
                          float *pos_w, float *neg_w, cudaStream_t stream);

@@ -102,7 +102,7 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, fl
 
 __global__ void __launch_bounds__(256, 2)
 mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float *__restrict__ dist, int m,
-             Stats *__restrict__ stats)
+             Stats *__restrict__ stats, Peers peers)
 {
     __shared__ __align__(16) float cs[kTile * kJP];
     __shared__ uint32_t wmax[8];
@@ -147,15 +147,27 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float
             atomicOr(&stats->flags, SMH_FLAG_NONFINITE);      // non-finite inputs (IEEE path): the loss is NaN
         else
             atomicMax(&stats->dmax_bits, bmax);
+        if (peers.world > 1) {
+            // fused all-reduce(MAX): the last CTA of this rank pushes the rank's maximum into every peer's stats
+            __threadfence();
+            const unsigned ticket = atomicAdd(&stats->ticket2, 1u);
+            if (ticket == gridDim.x - 1) {
+                const uint32_t mine = atomicMax(&stats->dmax_bits, 0u);
+                for (int p = 0; p < peers.world; ++p)
+                    if (p != peers.rank) atomicMax(&peers.stats(p)->dmax_bits, mine);
+                stats->ticket2 = 0u;
+                __threadfence_system();
+            }
+        }
     }
 }
 
 int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
-                 cudaStream_t stream)
+                 const Peers &peers, cudaStream_t stream)
 {
     (void)dims;
     if (lay.n_stored_tiles == 0) return 0;
-    mpjpe_kernel<<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, (Stats *)ws.stats);
+    mpjpe_kernel<<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, (Stats *)ws.stats, peers);
     return check_launch("mpjpe_kernel");
 }
 

@@ -128,9 +128,6 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
 int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
                 bool round_tf32, cudaStream_t stream)
 {
-    // accumulators and stats are contiguous at the head of the workspace
-    cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)(lay.off_posd - lay.off_stats), stream);
-    if (e != cudaSuccess) return set_error((int)e, "prep memset: %s", cudaGetErrorString(e));
     const int mp = lay.tiles_per_side * kTile;
     const int blocks = (mp + 7) / 8;
     prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, ws.zt, ws.zb, ws.jp, ws.posd, (Stats *)ws.stats);

@@ -21,8 +21,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(256, 1)
 sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, int n_strips,
                   const float *__restrict__ zt, const float *__restrict__ dist, const float *__restrict__ rn,
-                  float *__restrict__ neg, float *__restrict__ dzacc, const Stats *__restrict__ stats, int m, int n,
-                  int n_local, float k2)
+                  Peers peers, const Stats *__restrict__ stats, int m, int n, int n_local, float k2)
 {
     extern __shared__ __align__(16) float smem[];
     float *As = smem;                         // [128][129]  row block of z
@@ -133,14 +132,15 @@ sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strip
                 v += __shfl_xor_sync(0xffffffffu, v, 2);
                 v += __shfl_xor_sync(0xffffffffu, v, 1);
                 const int gi = I * kTile + ty + 16 * p;
-                if (tx == 0 && gi < m) atomicAdd(neg + gi, v);
+                if (tx == 0 && gi < m)
+                    for (int pp = 0; pp < peers.world; ++pp) atomicAdd(peers.neg(pp) + gi, v);
             }
         } else {
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
                 const int gi = I * kTile + ty + 16 * p;
                 if (gi < m) {
-                    float *orow = dzacc + dz_out_row(gi, n, n_local) * kD;
+                    float *orow = dz_row_ptr(peers, gi, n, n_local);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) atomicAdd(orow + tx + 16 * q, dz[p][q]);
                 }
@@ -150,7 +150,7 @@ sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strip
 }
 
 int launch_sweep_fp32(bool backward, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
-                      const WsView &ws, float temperature, cudaStream_t stream)
+                      const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream)
 {
     if (lay.n_strips == 0) return 0;
     int dev = 0, sms = 0;
@@ -164,13 +164,13 @@ int launch_sweep_fp32(bool backward, const smh_dims_t &dims, const smh_layout_t 
         e = cudaFuncSetAttribute(sweep_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32Smem);
         if (e != cudaSuccess) return set_error((int)e, "fp32 sweep smem attr: %s", cudaGetErrorString(e));
         sweep_fp32_kernel<true><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
-                                                                 ws.dist, ws.rn, ws.neg, ws.dzacc,
+                                                                 ws.dist, ws.rn, peers,
                                                                  (const Stats *)ws.stats, lay.m, dims.n, n_local, k2);
     } else {
         e = cudaFuncSetAttribute(sweep_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32Smem);
         if (e != cudaSuccess) return set_error((int)e, "fp32 sweep smem attr: %s", cudaGetErrorString(e));
         sweep_fp32_kernel<false><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
-                                                                  ws.dist, ws.rn, ws.neg, ws.dzacc,
+                                                                  ws.dist, ws.rn, peers,
                                                                   (const Stats *)ws.stats, lay.m, dims.n, n_local, k2);
     }
     return check_launch("sweep_fp32_kernel");

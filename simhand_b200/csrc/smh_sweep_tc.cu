@@ -108,8 +108,8 @@ template <bool BWD, bool SBF16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, int n_strips,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
-                const float *__restrict__ rn, float *__restrict__ neg, float *__restrict__ dzacc,
-                Stats *__restrict__ stats, int m, int n, int n_local, float k2)
+                const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
+                float k2)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
     using Cfg = TcCfg<SBF16>;
@@ -377,7 +377,11 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             const int gi = (row_block < 0 ? 0 : row_block) * kTile + r;
             const bool row_ok = row_block >= 0 && gi < m;
             if (!BWD) {
-                if (row_ok) atomicAdd(neg + gi, (rowsum[0] + rowsum[1]) + (rowsum[2] + rowsum[3]));
+                // fused all-reduce(SUM): the row sums go into every rank's `neg` (peer pointers over NVLink)
+                if (row_ok) {
+                    const float part = (rowsum[0] + rowsum[1]) + (rowsum[2] + rowsum[3]);
+                    for (int p = 0; p < peers.world; ++p) atomicAdd(peers.neg(p) + gi, part);
+                }
                 rowsum[0] = rowsum[1] = rowsum[2] = rowsum[3] = 0.f;
             } else {
                 // every epilogue warp drains 32 of the 128 gradient columns of its lane quadrant
@@ -386,7 +390,8 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 tc_fence_after();
                 const int gi2 = tasks[strip.x].x * kTile + r;
                 const bool ok2 = gi2 < m;
-                float *orow = dzacc + (ok2 ? dz_out_row(gi2, n, n_local) : 0) * kD;
+                // fused reduce-scatter: the gradient rows are added straight into the owning rank's accumulator
+                float *orow = dz_row_ptr(peers, ok2 ? gi2 : 0, n, n_local);
                 const int chunk = group * 2 + half;
                 uint32_t dv[32];
                 tc_ld32(lane_addr + kDzCol + chunk * 32, dv);
@@ -411,7 +416,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
 
 template <bool BWD, bool SBF16>
 static int launch_one(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
-                      float temperature, cudaStream_t stream)
+                      const Peers &peers, float temperature, cudaStream_t stream)
 {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -423,18 +428,18 @@ static int launch_one(const smh_dims_t &dims, const smh_layout_t &lay, const Pla
     cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
     sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt, ws.zb,
-                                                                   ws.dist, ws.rn, ws.neg, ws.dzacc, (Stats *)ws.stats,
-                                                                   lay.m, dims.n, n_local, k2);
+                                                                   ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
+                                                                   dims.n, n_local, k2);
     return check_launch("sweep_tc_kernel");
 }
 
 int launch_sweep_tc(bool backward, bool logits_bf16, const smh_dims_t &dims, const smh_layout_t &lay,
-                    const PlanView &plan, const WsView &ws, float temperature, cudaStream_t stream)
+                    const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream)
 {
     if (lay.n_strips == 0) return 0;
-    if (backward) return launch_one<true, true>(dims, lay, plan, ws, temperature, stream);
-    if (logits_bf16) return launch_one<false, true>(dims, lay, plan, ws, temperature, stream);
-    return launch_one<false, false>(dims, lay, plan, ws, temperature, stream);
+    if (backward) return launch_one<true, true>(dims, lay, plan, ws, peers, temperature, stream);
+    if (logits_bf16) return launch_one<false, true>(dims, lay, plan, ws, peers, temperature, stream);
+    return launch_one<false, false>(dims, lay, plan, ws, peers, temperature, stream);
 }
 
 }  // namespace smh

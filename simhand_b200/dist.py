@@ -56,8 +56,119 @@ def dz_out_row(i: int, n: int, n_local: int) -> int:
     return (k // n_local) * 2 * n_local + v * n_local + k % n_local
 
 
+class PeerExchange:
+    """Symmetric buffers of one sharded problem shape, mapped into every rank (torch.distributed._symmetric_memory):
+    the workspace blob (peers add row sums / gradient rows / Dmax into it over NVLink), the gathered-input buffer
+    (peers push their packed inputs into it) and the barrier words.  Built once per (shape, group) and reused."""
+
+    def __init__(self, ctx, group, chunk_floats: int):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = ctx.device
+        lay = ctx.layout
+        # all ranks must allocate the same size: the MPJPE tile region differs by a few tiles between ranks
+        ws_bytes = torch.tensor([int(lay.ws_bytes)], dtype=torch.int64, device=dev)
+        dist.all_reduce(ws_bytes, op=dist.ReduceOp.MAX, group=group)
+        self.ws = symm.empty(int(ws_bytes.item()), dtype=torch.uint8, device=dev)
+        self.xin = symm.empty(self.world * chunk_floats, dtype=torch.float32, device=dev)
+        self.signal = symm.empty(64, dtype=torch.int32, device=dev)
+        self.signal.zero_()
+        self.h_ws = symm.rendezvous(self.ws, group)
+        self.h_xin = symm.rendezvous(self.xin, group)
+        self.h_sig = symm.rendezvous(self.signal, group)
+        ex = _lib.Exchange()
+        ex.world, ex.rank = self.world, self.rank
+        for p in range(self.world):
+            ex.ws_peer[p] = self.h_ws.buffer_ptrs[p]
+            ex.xin_peer[p] = self.h_xin.buffer_ptrs[p]
+            ex.signal_peer[p] = self.h_sig.buffer_ptrs[p]
+        assert ex.ws_peer[self.rank] == self.ws.data_ptr()
+        self.struct = ex
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)                # every rank's barrier words are zero before anyone signals
+
+
+_exchanges = {}
+
+
+def get_exchange(ctx, group, chunk_floats: int) -> PeerExchange:
+    key = (id(ctx), id(group), chunk_floats)
+    ex = _exchanges.get(key)
+    if ex is None:
+        ex = PeerExchange(ctx, group, chunk_floats)
+        _exchanges[key] = ex
+    return ex
+
+
+def peer_exchange_available() -> bool:
+    try:
+        import torch.distributed._symmetric_memory as symm  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, want_grad: bool, group,
+                  grad_scale: float = 1.0, strip_len: int = 0):
+    """Sharded step with the collectives fused into the kernels (peer memory over NVLink): push-gather of the inputs,
+    Dmax pushed by the MPJPE kernel, row sums added into every rank's `neg` by the forward sweep, gradient rows
+    added into the owning rank's accumulator by the backward sweep; four device-side barriers separate the phases.
+    No NCCL call on the data path; the whole step is a fixed kernel sequence (CUDA-graph capturable)."""
+    lib = _lib.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = z1.device
+    n_local, d = z1.shape
+    n = n_local * world
+    eng = _lib.ENGINES[resolve_engine(engine, n)]
+    with torch.cuda.device(dev):
+        ctx = get_context(n, d, world, rank, dev, strip_len)
+        lay, dims = ctx.layout, ctx.dims
+        local = pack_local(z1, z2, joints1, joints2)
+        chunk = local.numel()
+        ex = get_exchange(ctx, group, chunk)
+        px = ctypes.byref(ex.struct)
+        ws = ex.ws
+        (o1, o2, oj1, oj2), _ = gathered_views(ex.xin, world, n_local, d)
+        base = ex.xin.data_ptr()
+        inp = _lib.Inputs(base + 4 * o1, base + 4 * o2, d, base + 4 * oj1, base + 4 * oj2, 42, 2, 1,
+                          n_local, chunk, chunk)
+        st = _stream_ptr(dev)
+        pd, pi = ctypes.byref(dims), ctypes.byref(inp)
+        plan = ctx.plan_dev.data_ptr()
+        # The accumulators this rank owns are zeroed by smh_prep; peers may only add to them after the first barrier.
+        check(lib.smh_push_inputs(px, local.data_ptr(), chunk, st), "smh_push_inputs")
+        check(lib.smh_prep_zero(pd, ws.data_ptr(), st), "smh_prep_zero")
+        check(lib.smh_barrier(px, st), "smh_barrier")
+        check(lib.smh_prep(pd, pi, ws.data_ptr(), eng | _lib.PREP_NO_ZERO, st), "smh_prep")
+        check(lib.smh_mpjpe(pd, plan, ws.data_ptr(), px, st), "smh_mpjpe")
+        check(lib.smh_barrier(px, st), "smh_barrier")
+        check(lib.smh_forward(pd, plan, ws.data_ptr(), temperature, eng, px, st), "smh_forward")
+        check(lib.smh_barrier(px, st), "smh_barrier")
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dz1 = dz2 = None
+        if want_grad:
+            check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng, px, st), "smh_backward")
+            check(lib.smh_barrier(px, st), "smh_barrier")
+            dz1 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
+            dz2 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
+        dz_src = ws.data_ptr() + int(lay.off_dzacc)
+        check(lib.smh_finalize(pd, pi, ws.data_ptr(), dz_src if want_grad else None, temperature, grad_scale,
+                               loss.data_ptr(), dz1.data_ptr() if want_grad else None,
+                               dz2.data_ptr() if want_grad else None, d, st), "smh_finalize")
+        # the next step's push may overwrite xin while a slow peer still reads it in finalize: close the step
+        check(lib.smh_barrier(px, st), "smh_barrier")
+    return loss, dz1, dz2
+
+
 def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, want_grad: bool,
-                     group: Optional[dist.ProcessGroup], grad_scale: float = 1.0, strip_len: int = 0):
+                     group: Optional[dist.ProcessGroup], grad_scale: float = 1.0, strip_len: int = 0,
+                     transport: str = "auto"):
+    """transport: "peer" (collectives fused into the kernels over peer memory), "nccl" (NCCL calls between the
+    kernels) or "auto" (peer when symmetric memory is available and the group fits SMH_MAX_PEERS)."""
+    if transport == "auto":
+        transport = "peer" if (peer_exchange_available() and dist.get_world_size(group) <= _lib.MAX_PEERS) else "nccl"
+    if transport == "peer":
+        return run_step_peer(z1, z2, joints1, joints2, temperature, engine, want_grad, group, grad_scale, strip_len)
     lib = _lib.load()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = z1.device
@@ -79,17 +190,17 @@ def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, 
         pd, pi = ctypes.byref(dims), ctypes.byref(inp)
         plan = ctx.plan_dev.data_ptr()
         check(lib.smh_prep(pd, pi, ws.data_ptr(), eng, st), "smh_prep")
-        check(lib.smh_mpjpe(pd, plan, ws.data_ptr(), st), "smh_mpjpe")
+        check(lib.smh_mpjpe(pd, plan, ws.data_ptr(), None, st), "smh_mpjpe")
         stats3 = ctx.view(ws, lay.off_stats, 3, torch.int32)
         dist.all_reduce(stats3, op=dist.ReduceOp.MAX, group=group)
-        check(lib.smh_forward(pd, plan, ws.data_ptr(), temperature, eng, st), "smh_forward")
+        check(lib.smh_forward(pd, plan, ws.data_ptr(), temperature, eng, None, st), "smh_forward")
         neg = ctx.view(ws, lay.off_neg, lay.m)
         dist.all_reduce(neg, op=dist.ReduceOp.SUM, group=group)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         dz1 = dz2 = None
         dz_local = None
         if want_grad:
-            check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng, st), "smh_backward")
+            check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng, None, st), "smh_backward")
             dzacc = ctx.view(ws, lay.off_dzacc, lay.m * 128)
             dz_local = torch.empty(2 * n_local * 128, dtype=torch.float32, device=dev)
             dist.reduce_scatter_tensor(dz_local, dzacc, op=dist.ReduceOp.SUM, group=group)

@@ -125,12 +125,12 @@ def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _
         st = _stream_ptr(dev)
         pd, pi = ctypes.byref(dims), ctypes.byref(inp)
         check(lib.smh_prep(pd, pi, ws.data_ptr(), eng, st), "smh_prep")
-        check(lib.smh_mpjpe(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), st), "smh_mpjpe")
-        check(lib.smh_forward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, eng, st), "smh_forward")
+        check(lib.smh_mpjpe(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), None, st), "smh_mpjpe")
+        check(lib.smh_forward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, eng, None, st), "smh_forward")
         loss = torch.empty((), dtype=torch.float32, device=dev)
         dz1 = dz2 = None
         if want_grad:
-            check(lib.smh_backward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, eng, st), "smh_backward")
+            check(lib.smh_backward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, eng, None, st), "smh_backward")
             dz1 = torch.empty((n, d), dtype=torch.float32, device=dev)
             dz2 = torch.empty((n, d), dtype=torch.float32, device=dev)
         check(lib.smh_finalize(pd, pi, ws.data_ptr(), None, temperature, grad_scale, loss.data_ptr(),
@@ -233,7 +233,7 @@ def mpjpe_weights(joints1: torch.Tensor, joints2: torch.Tensor, strip_len: int =
         st = _stream_ptr(dev)
         pd = ctypes.byref(ctx.dims)
         check(lib.smh_prep(pd, ctypes.byref(inp), ws.data_ptr(), _lib.ENGINE_FP32, st), "smh_prep")
-        check(lib.smh_mpjpe(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), st), "smh_mpjpe")
+        check(lib.smh_mpjpe(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), None, st), "smh_mpjpe")
         pos_w = torch.empty(n, dtype=torch.float32, device=dev)
         neg_w = torch.empty((2 * n, 2 * n), dtype=torch.float32, device=dev)
         check(lib.smh_weights_dense(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), pos_w.data_ptr(),

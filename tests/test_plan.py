@@ -25,6 +25,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.Dims) == 20
     assert ctypes.sizeof(_lib.Stats) == 32
+    assert ctypes.sizeof(_lib.Exchange) == 8 + 3 * 8 * 8
     assert ctypes.sizeof(_lib.Layout) == 12 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.Inputs) == 88
 
@@ -41,8 +42,9 @@ def test_layout_rejects_bad_dims(args, code):
 def test_compute_calls_reject_null_workspace_without_gpu():
     lib = _lib.load()
     dims = _lib.Dims(8, 128, 1, 0, 0)
-    assert lib.smh_mpjpe(ctypes.byref(dims), None, None, None) == -1
-    assert lib.smh_forward(ctypes.byref(dims), None, None, 0.5, 0, None) == -1
+    assert lib.smh_mpjpe(ctypes.byref(dims), None, None, None, None) == -1
+    assert lib.smh_forward(ctypes.byref(dims), None, None, 0.5, 0, None, None) == -1
+    assert lib.smh_barrier(None, None) == -1 and lib.smh_push_inputs(None, None, 0, None) == -1
     assert lib.smh_l2norm_fwd(None, None, None, 4, 4, 1e-12, None) == -1
 
 

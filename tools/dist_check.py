@@ -13,6 +13,7 @@ from simhand_b200 import ops, synth  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    transport = sys.argv[2] if len(sys.argv) > 2 else "auto"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
     torch.cuda.set_device(dev)
@@ -22,8 +23,12 @@ def main():
     sl = slice(rank * n_local, (rank + 1) * n_local)
     a = z1[sl].to(dev).requires_grad_(True)
     b = z2[sl].to(dev).requires_grad_(True)
-    loss = ops.weighted_ntxent(a, b, j1[sl].to(dev)[:, :, :2], j2[sl].to(dev)[:, :, :2], 0.5, dist.group.WORLD, "tf32")
-    loss.backward()
+    from simhand_b200.dist import run_step_sharded
+    ok_all = True
+    for rep in range(3):          # repeated steps exercise the barrier counters and the buffer reuse
+        loss, g1, g2 = run_step_sharded(a.detach(), b.detach(), j1[sl].to(dev)[:, :, :2], j2[sl].to(dev)[:, :, :2],
+                                        0.5, "tf32", True, dist.group.WORLD, transport=transport)
+    a.grad, b.grad = g1, g2
     full_loss, f1, f2 = ops.run_step(z1.to(dev), z2.to(dev), j1.to(dev)[:, :, :2], j2.to(dev)[:, :, :2], 0.5, "tf32", True)
     torch.cuda.synchronize()
     e_loss = abs(float(loss) - float(full_loss)) / abs(float(full_loss))
@@ -31,7 +36,7 @@ def main():
     e1 = float((a.grad - f1[sl]).abs().max()) / scale
     e2 = float((b.grad - f2[sl]).abs().max()) / scale
     ok = e_loss < 2e-6 and e1 < 1e-4 and e2 < 1e-4
-    print(f"rank {rank}/{world}: n={n} sharded loss {float(loss):.7f} single {float(full_loss):.7f} rel {e_loss:.1e} "
+    print(f"rank {rank}/{world}: n={n} transport={transport} sharded loss {float(loss):.7f} single {float(full_loss):.7f} rel {e_loss:.1e} "
           f"grad err {e1:.1e} {e2:.1e} -> {'OK' if ok else 'MISMATCH'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
