@@ -157,9 +157,10 @@ int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, floa
 int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature,
                  int engine, const smh_exchange_t *exch, void *stream);
 
-/* peer exchange: copy this rank's packed inputs ([z1|z2|joints1|joints2], `floats` fp32) into slot `rank` of every
- * peer's gathered-input buffer (the all-gather of SURVEY.md 8e, push-based over NVLink) */
-int smh_push_inputs(const smh_exchange_t *exch, const float *local_dev, int64_t floats, void *stream);
+/* peer exchange: pack this rank's local inputs (n_local samples per view, described like smh_inputs_t with
+ * rank strides ignored) as [z1|z2|joints1|joints2] into slot `rank` of every peer's gathered-input buffer
+ * (the all-gather of SURVEY.md 8e, push-based over NVLink); chunk = 2 * n_local * (d + 42) floats */
+int smh_push_inputs(const smh_exchange_t *exch, const smh_inputs_t *local_in, int32_t n_local, int32_t d, void *stream);
 /* peer exchange: device-side barrier over all ranks (monotonic counters in signal_peer; CUDA-graph safe) */
 int smh_barrier(const smh_exchange_t *exch, void *stream);
 

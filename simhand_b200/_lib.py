@@ -86,7 +86,7 @@ def load() -> ctypes.CDLL:
     lib.smh_mpjpe.argtypes = [pd, vp, vp, px, vp]
     lib.smh_forward.argtypes = [pd, vp, vp, f32, ctypes.c_int, px, vp]
     lib.smh_backward.argtypes = [pd, vp, vp, f32, ctypes.c_int, px, vp]
-    lib.smh_push_inputs.argtypes = [px, vp, i64, vp]
+    lib.smh_push_inputs.argtypes = [px, pi, i32, i32, vp]
     lib.smh_barrier.argtypes = [px, vp]
     lib.smh_prep_zero.argtypes = [pd, vp, vp]
     lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, vp]

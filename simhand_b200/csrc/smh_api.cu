@@ -54,6 +54,7 @@ struct HostPlan {
     std::vector<int2> tiles;
     std::vector<int4> tasks;
     std::vector<int2> strips;
+    std::vector<int> cta_ptr;          // kNumCtas + 1 offsets into strips
 };
 
 static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out, int *n_stored, int *n_tasks,
@@ -85,32 +86,43 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
             }
         }
     }
-    std::sort(tasks.begin(), tasks.end(), [](const int4 &a, const int4 &b) {
-        return a.x != b.x ? a.x < b.x : a.y < b.y;
-    });
-    std::vector<int2> strips;
-    size_t i = 0;
-    while (i < tasks.size()) {
-        size_t j = i;
-        while (j < tasks.size() && tasks[j].x == tasks[i].x && (int)(j - i) < strip_len) ++j;
-        strips.push_back(make_int2((int)i, (int)j));
-        tasks[i].w |= kTaskFirst;
-        tasks[j - 1].w |= kTaskLast;
-        i = j;
-    }
-    // Execution order of the strips (CTAs take them round-robin, so neighbours in this list run at the same
-    // time): strips of super-tile (A, B) are followed by those of (B, A), which read the same stored MPJPE
-    // tiles transposed -- the second read then hits the 126 MB L2 instead of HBM.
+    // Execution order of the tasks: by super-tile pair {A, B} (16 x 16 row blocks of 128 samples), (A, B) before
+    // (B, A), then row block, then column.  The CTAs take equal contiguous ranges of this list, so the ~5 CTAs that
+    // work inside one super-tile pair at the same time read every stored MPJPE tile twice (direct and transposed)
+    // within a ~32 MB window: the second read hits the 126 MB L2 instead of HBM.  Inside a range, a strip is a
+    // maximal run of tasks with the same row block (the accumulators are flushed at its end).  When all stored tiles
+    // of the rank fit in L2 anyway (sharded runs), plain (row block, column) order gives the longest strips.
     {
-        const int sbk = 16;                                   // row blocks per super block (2048 samples)
-        auto key = [&](const int2 &st) {
-            const int4 &t0 = tasks[st.x];
-            long long a = t0.x / sbk, b = (t0.y / 2) / sbk;
+        // super-block edge: a rank's share of one super-tile pair (2 sbk^2 / world tiles of 64 KiB) stays ~32 MB
+        int sbk = 16;
+        if (dims.world == 2) sbk = 22;
+        if (dims.world >= 3) sbk = 32;
+        if ((long long)tiles.size() * kTileFloats * 4 <= (96ll << 20)) sbk = 4096;
+        auto key = [&](const int4 &t) {
+            long long a = t.x / sbk, b = (t.y / 2) / sbk;
             long long lo = a < b ? a : b, hi = a < b ? b : a;
-            return (((lo * 4096 + hi) * 2 + (a > b ? 1 : 0)) * 4096 + t0.x) * 8192 + t0.y;
+            return (((lo * 4096 + hi) * 2 + (a > b ? 1 : 0)) * 4096 + t.x) * 8192 + t.y;
         };
-        std::stable_sort(strips.begin(), strips.end(), [&](const int2 &x, const int2 &y) { return key(x) < key(y); });
+        std::sort(tasks.begin(), tasks.end(), [&](const int4 &x, const int4 &y) { return key(x) < key(y); });
     }
+    const int n_ctas = (int)std::min<size_t>(kNumCtas, std::max<size_t>(tasks.size(), 1));
+    std::vector<int2> strips;
+    std::vector<int> cta_ptr(kNumCtas + 1, 0);
+    for (int c = 0; c < kNumCtas; ++c) {
+        cta_ptr[c] = (int)strips.size();
+        if (c >= n_ctas) continue;
+        const size_t lo = tasks.size() * (size_t)c / n_ctas, hi = tasks.size() * (size_t)(c + 1) / n_ctas;
+        size_t i = lo;
+        while (i < hi) {
+            size_t j = i;
+            while (j < hi && tasks[j].x == tasks[i].x && (int)(j - i) < strip_len) ++j;
+            strips.push_back(make_int2((int)i, (int)j));
+            tasks[i].w |= kTaskFirst;
+            tasks[j - 1].w |= kTaskLast;
+            i = j;
+        }
+    }
+    cta_ptr[kNumCtas] = (int)strips.size();
     *n_stored = (int)tiles.size();
     *n_tasks = (int)tasks.size();
     *n_strips = (int)strips.size();
@@ -118,6 +130,7 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
         out->tiles.swap(tiles);
         out->tasks.swap(tasks);
         out->strips.swap(strips);
+        out->cta_ptr.swap(cta_ptr);
     }
 }
 
@@ -142,7 +155,7 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     const int64_t mp = (int64_t)tp * kTile;
     lay->m = m;
     lay->tiles_per_side = tp;
-    lay->strip_len = dims.strip_len > 0 ? dims.strip_len : 16;
+    lay->strip_len = dims.strip_len > 0 ? dims.strip_len : 4096;
     enumerate_plan(dims, lay->strip_len, plan, &lay->n_stored_tiles, &lay->n_tasks, &lay->n_strips);
     int64_t off = 0;
     auto take = [&](int64_t bytes) {
@@ -162,7 +175,8 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     lay->off_dist = take((int64_t)lay->n_stored_tiles * kTileFloats * 4);
     lay->ws_bytes = off;
     lay->plan_bytes = align_up((int64_t)sizeof(PlanHeader), 16) + align_up((int64_t)lay->n_stored_tiles * 8, 16) +
-                      (int64_t)lay->n_tasks * 16 + align_up((int64_t)lay->n_strips * 8, 16);
+                      (int64_t)lay->n_tasks * 16 + align_up((int64_t)lay->n_strips * 8, 16) +
+                      align_up((int64_t)(kNumCtas + 1) * 4, 16);
     g_memo.dims = dims;
     g_memo.lay = *lay;
     g_memo.valid = true;
@@ -196,6 +210,8 @@ static PlanView carve_plan(const void *plan, const smh_layout_t &lay)
     v.tasks = (const int4 *)(b + o);
     o += (int64_t)lay.n_tasks * 16;
     v.strips = (const int2 *)(b + o);
+    o += align_up((int64_t)lay.n_strips * 8, 16);
+    v.cta_ptr = (const int *)(b + o);
     return v;
 }
 
@@ -298,6 +314,9 @@ int smh_plan_build(const smh_dims_t *dims, void *plan_host, int64_t plan_bytes)
     o += (int64_t)lay.n_tasks * 16;
     h.off_strips = (uint32_t)o;
     if (!hp.strips.empty()) memcpy(b + o, hp.strips.data(), hp.strips.size() * 8);
+    o += align_up((int64_t)lay.n_strips * 8, 16);
+    h.off_cta = (uint32_t)o;
+    memcpy(b + o, hp.cta_ptr.data(), hp.cta_ptr.size() * 4);
     memcpy(b, &h, sizeof(h));
     return 0;
 }
@@ -403,12 +422,14 @@ int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev
     return launch_weights_dense(*dims, lay, carve_plan(plan_dev, lay), ws, pos_w_dev, neg_w_dev, st);
 }
 
-int smh_push_inputs(const smh_exchange_t *exch, const float *local_dev, int64_t floats, void *stream)
+int smh_push_inputs(const smh_exchange_t *exch, const smh_inputs_t *local_in, int32_t n_local, int32_t d, void *stream)
 {
-    if (!exch || !local_dev || floats <= 0) return set_error(SMH_E_ARG, "push_inputs: null exchange/buffer");
+    if (!exch || !local_in) return set_error(SMH_E_ARG, "push_inputs: null exchange/inputs");
     if (exch->world < 1 || exch->world > SMH_MAX_PEERS) return set_error(SMH_E_DIM, "bad exchange world %d", exch->world);
-    if (floats % 4) return set_error(SMH_E_ALIGN, "push_inputs: length must be a multiple of 4 floats");
-    return launch_push_inputs(*exch, local_dev, floats, (cudaStream_t)stream);
+    if (n_local <= 0 || d <= 0 || d > SMH_MAX_DIM) return set_error(SMH_E_DIM, "push_inputs: bad n_local/d %d/%d", n_local, d);
+    if (!local_in->z1_dev || !local_in->z2_dev || !local_in->j1_dev || !local_in->j2_dev)
+        return set_error(SMH_E_ARG, "push_inputs: null input pointer");
+    return launch_push_inputs(*exch, *local_in, n_local, d, (cudaStream_t)stream);
 }
 
 int smh_barrier(const smh_exchange_t *exch, void *stream)

@@ -1,6 +1,7 @@
 // simhand_b200: the two kernels of the peer exchange that are not fused into a compute kernel.
-//   push_inputs_kernel  push-based all-gather: every rank writes its packed [z1|z2|joints1|joints2] into slot `rank` of
-//                       every peer's gathered-input buffer (plain coalesced 16-byte stores on peer pointers, NVLink)
+//   push_inputs_kernel  push-based all-gather: every rank packs its [z1|z2|joints1|joints2] straight from the caller's
+//                       tensors into slot `rank` of every peer's gathered-input buffer (coalesced stores on peer
+//                       pointers, NVLink)
 //   barrier_kernel      device-side barrier between the phases of a step.  Monotonic counters (word 0 = barriers this
 //                       rank has entered, word 8 + p = last barrier peer p announced), so the same kernel node can be
 //                       replayed from a CUDA graph without host-side epochs.
@@ -12,30 +13,47 @@
 namespace smh {
 
 struct PushArgs {
-    float *dst[kMaxPeers];
+    float *dst[kMaxPeers];      // peer p's gathered-input buffer, already offset to this rank's chunk
     int world;
 };
 
-__global__ void __launch_bounds__(256) push_inputs_kernel(const float4 *__restrict__ src, PushArgs a, int64_t n4)
+// One warp per (view, local sample): gathers the caller's (possibly strided) z row and [21, 2] joint view and writes
+// them in the packed chunk layout [z1 | z2 | joints1 | joints2] straight into every peer's buffer.
+__global__ void __launch_bounds__(256) push_inputs_kernel(smh_inputs_t in, PushArgs a, int n_local, int d)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        const float4 v = src[i];
-        for (int p = 0; p < a.world; ++p) reinterpret_cast<float4 *>(a.dst[p])[i] = v;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int64_t off_z2 = (int64_t)n_local * d, off_j1 = 2 * off_z2, off_j2 = off_j1 + (int64_t)n_local * 42;
+    for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < 2 * n_local; w += gridDim.x * wpb) {
+        const int v = w >= n_local ? 1 : 0;
+        const int k = w - v * n_local;
+        const float *zp = (v ? in.z2_dev : in.z1_dev) + (int64_t)k * in.z_row_stride;
+        const float *jb = (v ? in.j2_dev : in.j1_dev) + (int64_t)k * in.j_sample_stride;
+        const int64_t zo = (v ? off_z2 : 0) + (int64_t)k * d;
+        const int64_t jo = (v ? off_j2 : off_j1) + (int64_t)k * 42;
+        for (int c = lane; c < d; c += 32) {
+            const float val = zp[c];
+            for (int p = 0; p < a.world; ++p) a.dst[p][zo + c] = val;
+        }
+        for (int c = lane; c < 42; c += 32) {
+            const float val = jb[(int64_t)(c >> 1) * in.j_joint_stride + (c & 1) * in.j_coord_stride];
+            for (int p = 0; p < a.world; ++p) a.dst[p][jo + c] = val;
+        }
     }
 }
 
-int launch_push_inputs(const smh_exchange_t &exch, const float *local, int64_t floats, cudaStream_t stream)
+int launch_push_inputs(const smh_exchange_t &exch, const smh_inputs_t &in, int n_local, int d, cudaStream_t stream)
 {
     PushArgs a;
     a.world = exch.world;
+    const int64_t chunk = 2ll * n_local * (d + 42);
     for (int p = 0; p < exch.world; ++p) {
         if (!exch.xin_peer[p]) return set_error(SMH_E_ARG, "exchange xin_peer[%d] is null", p);
-        a.dst[p] = (float *)exch.xin_peer[p] + (int64_t)exch.rank * floats;
+        a.dst[p] = (float *)exch.xin_peer[p] + (int64_t)exch.rank * chunk;
     }
-    const int64_t n4 = floats / 4;
-    int blocks = (int)((n4 + 255) / 256);
+    int blocks = (2 * n_local + 7) / 8;
     if (blocks > 148 * 4) blocks = 148 * 4;
-    push_inputs_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(local), a, n4);
+    push_inputs_kernel<<<blocks, 256, 0, stream>>>(in, a, n_local, d);
     return check_launch("push_inputs_kernel");
 }
 

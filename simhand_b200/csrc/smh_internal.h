@@ -26,6 +26,7 @@ struct PlanView {               // device pointers into the caller's plan blob
     const int2 *tiles;          // (I, J) of each stored tile of this rank
     const int4 *tasks;          // (row block, 64-col tile, stored tile, flags)
     const int2 *strips;         // (first task, one-past-last task)
+    const int *cta_ptr;         // strips of sweep CTA c: [cta_ptr[c], cta_ptr[c + 1])
 };
 
 int set_error(int code, const char *fmt, ...);
@@ -40,7 +41,7 @@ int launch_sweep_fp32(bool backward, const smh_dims_t &dims, const smh_layout_t 
                       const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
 int launch_sweep_tc(bool backward, bool logits_bf16, const smh_dims_t &dims, const smh_layout_t &lay,
                     const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
-int launch_push_inputs(const smh_exchange_t &exch, const float *local, int64_t floats, cudaStream_t stream);
+int launch_push_inputs(const smh_exchange_t &exch, const smh_inputs_t &in, int n_local, int d, cudaStream_t stream);
 int launch_barrier(const smh_exchange_t &exch, cudaStream_t stream);
 int launch_rn(const smh_layout_t &lay, const WsView &ws, cudaStream_t stream);
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,

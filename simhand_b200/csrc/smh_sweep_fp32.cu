@@ -19,7 +19,7 @@ constexpr int kFp32Smem = (kTile * kPitch + 2 * kTaskN * kPitch) * 4;     // As 
 
 template <bool BWD>
 __global__ void __launch_bounds__(256, 1)
-sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, int n_strips,
+sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                   const float *__restrict__ zt, const float *__restrict__ dist, const float *__restrict__ rn,
                   Peers peers, const Stats *__restrict__ stats, int m, int n, int n_local, float k2)
 {
@@ -30,10 +30,11 @@ sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strip
 
     const int t = threadIdx.x;
     const int ty = t >> 4, tx = t & 15;
+    const int s_begin = cta_ptr[blockIdx.x], s_end = cta_ptr[blockIdx.x + 1];      // this CTA's strips
     const float dmax = __uint_as_float(stats->dmax_bits);
     const DivConst divw = make_div(dmax);     // Dmax - Dmin with Dmin = +0 (diagonal)
 
-    for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
+    for (int s = s_begin; s < s_end; ++s) {
         const int2 strip = strips[s];
         const int I = tasks[strip.x].x;
         __syncthreads();
@@ -156,20 +157,21 @@ int launch_sweep_fp32(bool backward, const smh_dims_t &dims, const smh_layout_t 
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = lay.n_strips < sms ? lay.n_strips : sms;
+    (void)sms;
+    const int grid = kNumCtas;                      // the plan is cut for exactly this many CTAs
     const float k2 = 1.4426950408889634f / temperature;
     const int n_local = dims.n / dims.world;
     cudaError_t e;
     if (backward) {
         e = cudaFuncSetAttribute(sweep_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32Smem);
         if (e != cudaSuccess) return set_error((int)e, "fp32 sweep smem attr: %s", cudaGetErrorString(e));
-        sweep_fp32_kernel<true><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
+        sweep_fp32_kernel<true><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt,
                                                                  ws.dist, ws.rn, peers,
                                                                  (const Stats *)ws.stats, lay.m, dims.n, n_local, k2);
     } else {
         e = cudaFuncSetAttribute(sweep_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32Smem);
         if (e != cudaSuccess) return set_error((int)e, "fp32 sweep smem attr: %s", cudaGetErrorString(e));
-        sweep_fp32_kernel<false><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt,
+        sweep_fp32_kernel<false><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt,
                                                                   ws.dist, ws.rn, peers,
                                                                   (const Stats *)ws.stats, lay.m, dims.n, n_local, k2);
     }

@@ -106,7 +106,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned
 // BWD: backward sweep (always reads the bf16 image).  SBF16: logits from the bf16 image (else tf32 image).
 template <bool BWD, bool SBF16>
 __global__ void __launch_bounds__(kTcThreads, 1)
-sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, int n_strips,
+sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
                 const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
                 float k2)
@@ -126,6 +126,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int s_begin = cta_ptr[blockIdx.x], s_end = cta_ptr[blockIdx.x + 1];      // this CTA's strips
     uint32_t *fail = &stats->fail_site;
     constexpr uint32_t kTmemCols = BWD ? 512u : 256u;
     constexpr uint32_t kDzCol = kSBufs * kTaskN;                 // 256: gradient accumulator behind the S buffers
@@ -163,7 +164,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         // ------------------------------------------------------------------ tile producer (MPJPE pieces, HBM)
         int dst = 0;
         uint32_t dph = 0;
-        for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
+        for (int s = s_begin; s < s_end; ++s) {
             const int2 strip = strips[s];
             int4 task = tasks[strip.x];
             for (int ti = strip.x; ti < strip.y; ++ti) {
@@ -192,7 +193,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         if (lane == 0) {
             int bst = 0;
             uint32_t bph = 0, a_ph = 0;
-            for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
+            for (int s = s_begin; s < s_end; ++s) {
                 const int2 strip = strips[s];
                 int4 task = tasks[strip.x];
                 const int I = task.x;
@@ -262,7 +263,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 tc_commit(&bars->empty_b[bstq]);
                 if (last) tc_commit(&bars->dz_full);
             };
-            for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
+            for (int s = s_begin; s < s_end; ++s) {
                 const int2 strip = strips[s];
                 mbar_wait(&bars->a_full, a_ph, fail, 6);
                 a_ph ^= 1u;
@@ -321,7 +322,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         const DivConst divw = make_div(dmax);          // Dmax - Dmin, Dmin = +0
         uint32_t seq = 0, dz_ph = 0;
         float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int s = blockIdx.x; s < n_strips; s += gridDim.x) {
+        for (int s = s_begin; s < s_end; ++s) {
             const int2 strip = strips[s];
             int row_block = -1;
             float rni = 0.f;
@@ -421,13 +422,14 @@ static int launch_one(const smh_dims_t &dims, const smh_layout_t &lay, const Pla
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = lay.n_strips < sms ? lay.n_strips : sms;
+    (void)sms;
+    const int grid = kNumCtas;                      // the plan is cut for exactly this many CTAs
     const float k2 = 1.4426950408889634f / temperature;
     const int n_local = dims.n / dims.world;
     constexpr int smem = TcCfg<SBF16>::kSmem;
     cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-    sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, lay.n_strips, ws.zt, ws.zb,
+    sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, ws.zb,
                                                                    ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
                                                                    dims.n, n_local, k2);
     return check_launch("sweep_tc_kernel");

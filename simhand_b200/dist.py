@@ -123,9 +123,9 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
     with torch.cuda.device(dev):
         ctx = get_context(n, d, world, rank, dev, strip_len)
         lay, dims = ctx.layout, ctx.dims
-        local = pack_local(z1, z2, joints1, joints2)
-        chunk = local.numel()
+        chunk = 2 * n_local * (d + 42)
         ex = get_exchange(ctx, group, chunk)
+        local_in, keep = make_inputs(z1, z2, joints1, joints2)
         px = ctypes.byref(ex.struct)
         ws = ex.ws
         (o1, o2, oj1, oj2), _ = gathered_views(ex.xin, world, n_local, d)
@@ -136,7 +136,8 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
         pd, pi = ctypes.byref(dims), ctypes.byref(inp)
         plan = ctx.plan_dev.data_ptr()
         # The accumulators this rank owns are zeroed by smh_prep; peers may only add to them after the first barrier.
-        check(lib.smh_push_inputs(px, local.data_ptr(), chunk, st), "smh_push_inputs")
+        check(lib.smh_push_inputs(px, ctypes.byref(local_in), n_local, d, st), "smh_push_inputs")
+        del keep
         check(lib.smh_prep_zero(pd, ws.data_ptr(), st), "smh_prep_zero")
         check(lib.smh_barrier(px, st), "smh_barrier")
         check(lib.smh_prep(pd, pi, ws.data_ptr(), eng | _lib.PREP_NO_ZERO, st), "smh_prep")

@@ -11,6 +11,7 @@ import ctypes
 import numpy as np
 
 TILE = 128
+NUM_CTAS = 148                   # persistent sweep CTAs the plan is cut for
 TASK_N = 64
 TILE_FLOATS = TILE * TILE
 BLOCK_ROWS = 64
@@ -48,12 +49,13 @@ def parse_plan(plan_bytes: np.ndarray):
     """Decodes a plan blob built by smh_plan_build into (header dict, tiles[n,2], tasks[n,4], strips[n,2])."""
     hdr = np.frombuffer(plan_bytes[:64].tobytes(), dtype=np.uint32)
     names = ("magic", "m", "world", "rank", "tiles_per_side", "n_stored", "n_tasks", "n_strips", "strip_len",
-             "off_tiles", "off_tasks", "off_strips")
+             "off_tiles", "off_tasks", "off_strips", "off_cta")
     h = {k: int(v) for k, v in zip(names, hdr)}
     raw = plan_bytes.tobytes()
     tiles = np.frombuffer(raw, np.int32, h["n_stored"] * 2, h["off_tiles"]).reshape(-1, 2)
     tasks = np.frombuffer(raw, np.int32, h["n_tasks"] * 4, h["off_tasks"]).reshape(-1, 4)
     strips = np.frombuffer(raw, np.int32, h["n_strips"] * 2, h["off_strips"]).reshape(-1, 2)
+    h["cta_ptr"] = np.frombuffer(raw, np.int32, NUM_CTAS + 1, h["off_cta"])
     return h, tiles, tasks, strips
 
 

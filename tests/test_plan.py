@@ -44,7 +44,7 @@ def test_compute_calls_reject_null_workspace_without_gpu():
     dims = _lib.Dims(8, 128, 1, 0, 0)
     assert lib.smh_mpjpe(ctypes.byref(dims), None, None, None, None) == -1
     assert lib.smh_forward(ctypes.byref(dims), None, None, 0.5, 0, None, None) == -1
-    assert lib.smh_barrier(None, None) == -1 and lib.smh_push_inputs(None, None, 0, None) == -1
+    assert lib.smh_barrier(None, None) == -1 and lib.smh_push_inputs(None, None, 0, 0, None) == -1
     assert lib.smh_l2norm_fwd(None, None, None, 4, 4, 1e-12, None) == -1
 
 
@@ -83,6 +83,14 @@ def test_plan_covers_every_ordered_pair_once(n, world):
             assert len(set(tasks[a:b, 0])) == 1
             assert tasks[a, 3] & L.TASK_FIRST and tasks[b - 1, 3] & L.TASK_LAST
             assert not (tasks[a + 1:b, 3] & L.TASK_FIRST).any() and not (tasks[a:b - 1, 3] & L.TASK_LAST).any()
+        # the sweep CTAs own contiguous, equally sized task ranges
+        cp = h["cta_ptr"]
+        assert cp[0] == 0 and cp[-1] == len(strips) and (np.diff(cp) >= 0).all()
+        per_cta = [int(strips[cp[c]:cp[c + 1], 1].max() - strips[cp[c]:cp[c + 1], 0].min()) if cp[c + 1] > cp[c] else 0
+                   for c in range(L.NUM_CTAS)]
+        assert sum(per_cta) == len(tasks)
+        busy = [x for x in per_cta if x]
+        assert max(busy) - min(busy) <= 1
     assert (stored[np.triu_indices(tp)] == 1).all() and stored.sum() == tp * (tp + 1) // 2
     live = np.array([[cj * 64 < m for cj in range(2 * tp)]] * tp)
     assert (cover[live] == 1).all() and (cover[~live] == 0).all()
