@@ -49,7 +49,11 @@ struct TcCfg {
 };
 
 struct TcBars {
-    uint64_t full_b[kMaxBStages], empty_b[kMaxBStages], full_d[kMaxDStages], empty_d[kMaxDStages];
+    uint64_t full_b[kMaxBStages], empty_b[kMaxBStages], empty_d[kMaxDStages];
+    // One "tile landed" barrier per (stage, consuming epilogue group).  A parity wait can only tell adjacent phases
+    // apart, so a barrier must be waited on by a single party that sees every one of its phases; with an odd number
+    // of stages the fills of a stage alternate between the two groups.
+    uint64_t full_d[kMaxDStages][kEpiGroups];
     uint64_t a_full, a_empty;
     uint64_t sg_full[kSBufs], sg_empty[kSBufs], g_ready[kSBufs];
     uint64_t dz_full, dz_empty;
@@ -137,7 +141,8 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             mbar_init(&bars->empty_b[i], 1);
         }
         for (int i = 0; i < kDStages; ++i) {
-            mbar_init(&bars->full_d[i], 1);
+            mbar_init(&bars->full_d[i][0], 1);
+            mbar_init(&bars->full_d[i][1], 1);
             mbar_init(&bars->empty_d[i], kGroupWarps);
         }
         mbar_init(&bars->a_full, 1);
@@ -163,25 +168,26 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     if (warp == 0) {
         // ------------------------------------------------------------------ tile producer (MPJPE pieces, HBM)
         int dst = 0;
-        uint32_t dph = 0;
+        uint32_t dph = 0, seq = 0;
         for (int s = s_begin; s < s_end; ++s) {
             const int2 strip = strips[s];
             int4 task = tasks[strip.x];
-            for (int ti = strip.x; ti < strip.y; ++ti) {
+            for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
                 const int4 next = (ti + 1 < strip.y) ? tasks[ti + 1] : task;      // prefetch the next record
                 if (lane == 0) {
+                    uint64_t *full = &bars->full_d[dst][seq & 1u];                  // the group that takes task `seq`
                     mbar_wait(&bars->empty_d[dst], dph ^ 1u, fail, 3);
                     task_slot[dst] = task;
-                    mbar_arrive_expect_tx(&bars->full_d[dst], kDBytes);
+                    mbar_arrive_expect_tx(full, kDBytes);
                     const float *tile = dist + (int64_t)task.z * kTileFloats;
                     const int half = task.y & 1;
                     if (task.w & kTaskTransposed) {
                         // stored rows half*64 .. +63, all 128 stored columns: one contiguous 32 KiB slab
-                        bulk_g2s(sD + dst * kDBytes, tile + half * 8192, 32768, &bars->full_d[dst]);
+                        bulk_g2s(sD + dst * kDBytes, tile + half * 8192, 32768, full);
                     } else {
                         // stored columns half*64 .. +63: one 16 KiB slab per 64-row half
-                        bulk_g2s(sD + dst * kDBytes, tile + (half * 16) * 256, 16384, &bars->full_d[dst]);
-                        bulk_g2s(sD + dst * kDBytes + 16384, tile + (32 + half * 16) * 256, 16384, &bars->full_d[dst]);
+                        bulk_g2s(sD + dst * kDBytes, tile + (half * 16) * 256, 16384, full);
+                        bulk_g2s(sD + dst * kDBytes + 16384, tile + (32 + half * 16) * 256, 16384, full);
                     }
                 }
                 task = next;
@@ -329,7 +335,9 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
                 if ((int)(seq & 1u) != group) continue;
                 const uint32_t dst = seq % kDStages, sb = seq % kSBufs;
-                mbar_wait(&bars->full_d[dst], (seq / kDStages) & 1u, fail, 10);
+                // fills of a stage seen by this group: every fill (even stage count) or every other one (odd)
+                const uint32_t my_fill = (kDStages & 1) ? (seq / kDStages) >> 1 : seq / kDStages;
+                mbar_wait(&bars->full_d[dst][group], my_fill & 1u, fail, 10);
                 const int4 task = task_slot[dst];
                 const int gi = task.x * kTile + r;
                 const bool row_ok = gi < m;
