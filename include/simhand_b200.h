@@ -50,6 +50,7 @@ extern "C" {
 #define SMH_ENGINE_TC_TF32 0     /* tcgen05: tf32 logits in the forward sweep, bf16 operands in the backward sweep */
 #define SMH_ENGINE_FP32 1        /* CUDA-core FFMA, fp32 accumulate (exact-fp32 mode) */
 #define SMH_ENGINE_TC_BF16 2     /* tcgen05: bf16 operands in both sweeps (bf16 mode) */
+#define SMH_BACKWARD_RN_ONLY 0x200 /* OR into smh_backward's engine: only reduce the row sums (loss without gradient) */
 #define SMH_PREP_NO_ZERO 0x100   /* OR into smh_prep's engine: the accumulators were already zeroed by smh_prep_zero */
 
 /* problem description shared by all calls */
@@ -74,6 +75,8 @@ typedef struct smh_layout {
     int64_t off_rn;              /* [Tp*128] fp32 1/neg */
     int64_t off_rowloss;         /* [Tp*128] fp32 per-row loss terms */
     int64_t off_dzacc;           /* [M][128] fp32 unscaled gradient accumulator (rank-major rows) */
+    int64_t off_negparts;        /* [world][Tp*128] fp32 row-sum partials received from the ranks (peer exchange) */
+    int64_t off_dzparts;         /* [world][2*n_local][128] fp32 gradient partials received from the ranks (peer exchange) */
     int64_t off_dist;            /* stored MPJPE tiles of this rank, 64 KiB each */
     int32_t m;                   /* 2N */
     int32_t tiles_per_side;      /* Tp = ceil(M / 128) */
@@ -114,11 +117,12 @@ typedef struct smh_inputs {
 } smh_inputs_t;
 
 /* Peer exchange (world > 1, optional): the ranks' workspaces and input staging buffers are symmetric allocations
- * mapped into every process (torch.distributed._symmetric_memory or CUDA IPC); with it the kernels do the
- * collectives themselves over NVLink: the MPJPE kernel's last CTA pushes Dmax to every peer (atomicMax), the
- * forward sweep adds its row sums into every peer's `neg`, the backward sweep adds its gradient rows straight into
- * the owning rank's accumulator (red.global.add.v4.f32 on peer pointers), and smh_barrier separates the phases.
- * Without it (exch == NULL) the caller runs all-reduce / reduce-scatter between the calls. */
+ * mapped into every process (torch.distributed._symmetric_memory or CUDA IPC); with it the library does the
+ * collectives itself over NVLink: the MPJPE kernel's last CTA pushes Dmax to every peer (atomicMax);
+ * smh_exchange_neg / smh_exchange_dz store this rank's partial row sums / gradient rows into slot `rank` of every
+ * peer's (resp. the owning peer's) partial buffers with plain 16-byte stores, and the consumers (1/neg kernel,
+ * finalize) add the `world` partials in rank order, so the reduction is deterministic; smh_barrier separates the
+ * phases.  Without it (exch == NULL) the caller runs all-reduce / reduce-scatter between the calls. */
 #define SMH_MAX_PEERS 8
 typedef struct smh_exchange {
     int32_t world, rank;
@@ -161,17 +165,22 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
  * rank strides ignored) as [z1|z2|joints1|joints2] into slot `rank` of every peer's gathered-input buffer
  * (the all-gather of SURVEY.md 8e, push-based over NVLink); chunk = 2 * n_local * (d + 42) floats */
 int smh_push_inputs(const smh_exchange_t *exch, const smh_inputs_t *local_in, int32_t n_local, int32_t d, void *stream);
+/* peer exchange: all-gather of the partial row sums (after smh_forward) / reduce-scatter payload of the partial
+ * gradient rows (after smh_backward) into the peers' partial buffers */
+int smh_exchange_neg(const smh_dims_t *dims, void *ws_dev, const smh_exchange_t *exch, void *stream);
+int smh_exchange_dz(const smh_dims_t *dims, void *ws_dev, const smh_exchange_t *exch, void *stream);
 /* peer exchange: device-side barrier over all ranks (monotonic counters in signal_peer; CUDA-graph safe) */
 int smh_barrier(const smh_exchange_t *exch, void *stream);
 
 /* loss (utils.py:420-426) over all M rows and, if dz1_dev != NULL, the gradients of the local
  * samples: dz = dzacc_src / (M tau) - 2 Wp z_partner / (M tau), scaled by grad_scale.
  * dzacc_src_dev: NULL = all M rows in ws.dzacc (world == 1); otherwise this rank's own [2 * n_local][128] block
- * (the reduce-scattered buffer, or ws.dzacc itself when the peer exchange accumulated into it). */
+ * (the reduce-scattered buffer).  With exch != NULL the gradient rows are the sum of the `world` partial blocks in
+ * ws.dzparts (dzacc_src_dev is ignored). */
 int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev,
                  const float *dzacc_src_dev, float temperature, float grad_scale,
                  float *loss_dev, float *dz1_dev, float *dz2_dev, int64_t dz_row_stride,
-                 void *stream);
+                 const smh_exchange_t *exch, void *stream);
 
 /* materialised weights with the reference's return shapes: pos_w [N], neg_w [M, M] row-major
  * (utils.py:235, :259).  world == 1 only.  Needs smh_prep + smh_mpjpe. */

@@ -16,6 +16,7 @@ ENGINE_TC_BF16 = 2
 ENGINES = {"tf32": ENGINE_TC_TF32, "tc": ENGINE_TC_TF32, "fp32": ENGINE_FP32, "bf16": ENGINE_TC_BF16}
 
 PREP_NO_ZERO = 0x100
+BACKWARD_RN_ONLY = 0x200
 FLAG_SLOW_DOMAIN = 1
 FLAG_NONFINITE = 2
 
@@ -29,7 +30,8 @@ class Layout(ctypes.Structure):
     _fields_ = [("ws_bytes", ctypes.c_int64), ("plan_bytes", ctypes.c_int64), ("off_stats", ctypes.c_int64),
                 ("off_zt", ctypes.c_int64), ("off_zb", ctypes.c_int64), ("off_jp", ctypes.c_int64), ("off_posd", ctypes.c_int64),
                 ("off_neg", ctypes.c_int64), ("off_rn", ctypes.c_int64), ("off_rowloss", ctypes.c_int64),
-                ("off_dzacc", ctypes.c_int64), ("off_dist", ctypes.c_int64),
+                ("off_dzacc", ctypes.c_int64), ("off_negparts", ctypes.c_int64), ("off_dzparts", ctypes.c_int64),
+                ("off_dist", ctypes.c_int64),
                 ("m", ctypes.c_int32), ("tiles_per_side", ctypes.c_int32), ("n_stored_tiles", ctypes.c_int32),
                 ("n_tasks", ctypes.c_int32), ("n_strips", ctypes.c_int32), ("strip_len", ctypes.c_int32)]
 
@@ -61,7 +63,7 @@ class Stats(ctypes.Structure):
 EXPORTS = ("smh_version", "smh_last_error", "smh_layout", "smh_plan_build", "smh_prep", "smh_mpjpe",
            "smh_forward", "smh_backward", "smh_finalize", "smh_weights_dense", "smh_l2norm_fwd",
            "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params", "smh_push_inputs",
-           "smh_barrier", "smh_prep_zero")
+           "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz")
 
 _lib = None
 
@@ -88,8 +90,10 @@ def load() -> ctypes.CDLL:
     lib.smh_backward.argtypes = [pd, vp, vp, f32, ctypes.c_int, px, vp]
     lib.smh_push_inputs.argtypes = [px, pi, i32, i32, vp]
     lib.smh_barrier.argtypes = [px, vp]
+    lib.smh_exchange_neg.argtypes = [pd, vp, px, vp]
+    lib.smh_exchange_dz.argtypes = [pd, vp, px, vp]
     lib.smh_prep_zero.argtypes = [pd, vp, vp]
-    lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, vp]
+    lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, ctypes.POINTER(Exchange), vp]
     lib.smh_weights_dense.argtypes = [pd, vp, vp, vp, vp, vp]
     lib.smh_l2norm_fwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     lib.smh_l2norm_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]

@@ -172,6 +172,9 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     lay->off_zt = take(mp * kD * 4);
     lay->off_zb = take(mp * kD * 2);
     lay->off_jp = take(mp * kJP * 4);
+    // partial buffers of the peer exchange (unused, and not allocated, on a single rank)
+    lay->off_negparts = take(dims.world > 1 ? (int64_t)dims.world * mp * 4 : 0);
+    lay->off_dzparts = take(dims.world > 1 ? (int64_t)m * kD * 4 : 0);
     lay->off_dist = take((int64_t)lay->n_stored_tiles * kTileFloats * 4);
     lay->ws_bytes = off;
     lay->plan_bytes = align_up((int64_t)sizeof(PlanHeader), 16) + align_up((int64_t)lay->n_stored_tiles * 8, 16) +
@@ -196,6 +199,8 @@ static WsView carve(void *ws, const smh_layout_t &lay)
     v.rn = (float *)(b + lay.off_rn);
     v.rowloss = (float *)(b + lay.off_rowloss);
     v.dzacc = (float *)(b + lay.off_dzacc);
+    v.negparts = (float *)(b + lay.off_negparts);
+    v.dzparts = (float *)(b + lay.off_dzparts);
     v.dist = (float *)(b + lay.off_dist);
     return v;
 }
@@ -222,6 +227,8 @@ static int make_peers(const smh_dims_t &dims, const smh_layout_t &lay, void *ws_
     out->off_stats = lay.off_stats;
     out->off_neg = lay.off_neg;
     out->off_dzacc = lay.off_dzacc;
+    out->off_negparts = lay.off_negparts;
+    out->off_dzparts = lay.off_dzparts;
     if (!exch) {
         out->world = 1;
         out->rank = 0;
@@ -372,8 +379,9 @@ int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, floa
     SMH_COMMON_PROLOGUE(true)
     if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
     PlanView pv = carve_plan(plan_dev, lay);
+    (void)exch;                       // the sweep accumulates locally; smh_exchange_neg ships the partial sums
     Peers peers;
-    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
+    if ((rc = make_peers(*dims, lay, ws_dev, nullptr, &peers))) return rc;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
         return launch_sweep_tc(false, engine == SMH_ENGINE_TC_BF16, *dims, lay, pv, ws, peers, temperature, st);
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, *dims, lay, pv, ws, peers, temperature, st);
@@ -387,8 +395,10 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
     if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
     PlanView pv = carve_plan(plan_dev, lay);
     Peers peers;
-    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
-    if ((rc = launch_rn(lay, ws, st))) return rc;
+    if ((rc = make_peers(*dims, lay, ws_dev, nullptr, &peers))) return rc;
+    // peer exchange: the row sums are the rank-ordered sum of the partials every rank delivered
+    if ((rc = launch_rn(lay, ws, exch ? dims->world : 1, st))) return rc;
+    if (engine & SMH_BACKWARD_RN_ONLY) return 0;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
         return launch_sweep_tc(true, true, *dims, lay, pv, ws, peers, temperature, st);
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, *dims, lay, pv, ws, peers, temperature, st);
@@ -397,7 +407,7 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
 
 int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, const float *dzacc_src_dev,
                  float temperature, float grad_scale, float *loss_dev, float *dz1_dev, float *dz2_dev,
-                 int64_t dz_row_stride, void *stream)
+                 int64_t dz_row_stride, const smh_exchange_t *exch, void *stream)
 {
     const void *plan_dev = nullptr;
     SMH_COMMON_PROLOGUE(false)
@@ -407,10 +417,17 @@ int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, c
     if ((dz1_dev == nullptr) != (dz2_dev == nullptr)) return set_error(SMH_E_ARG, "dz1/dz2 must both be set or null");
     if (dz1_dev && dz_row_stride < dims->d) return set_error(SMH_E_ARG, "dz_row_stride < d");
     // NULL: all rows in the local accumulator (rank-major); otherwise this rank's own [2 n_local][128] block
-    const bool local_block = dzacc_src_dev != nullptr;
+    bool local_block = dzacc_src_dev != nullptr;
+    int n_parts = 1;
     if (!dzacc_src_dev) dzacc_src_dev = ws.dzacc;
-    return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, local_block, temperature, grad_scale, loss_dev, dz1_dev,
-                           dz2_dev, dz_row_stride, st);
+    if (exch) {
+        if (exch->world != dims->world) return set_error(SMH_E_DIM, "exchange world does not match dims");
+        dzacc_src_dev = ws.dzparts;           // [world][2 n_local][128], summed in rank order
+        local_block = true;
+        n_parts = dims->world;
+    }
+    return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, local_block, n_parts, temperature, grad_scale, loss_dev,
+                           dz1_dev, dz2_dev, dz_row_stride, st);
 }
 
 int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float *pos_w_dev,
@@ -430,6 +447,30 @@ int smh_push_inputs(const smh_exchange_t *exch, const smh_inputs_t *local_in, in
     if (!local_in->z1_dev || !local_in->z2_dev || !local_in->j1_dev || !local_in->j2_dev)
         return set_error(SMH_E_ARG, "push_inputs: null input pointer");
     return launch_push_inputs(*exch, *local_in, n_local, d, (cudaStream_t)stream);
+}
+
+int smh_exchange_neg(const smh_dims_t *dims, void *ws_dev, const smh_exchange_t *exch, void *stream)
+{
+    const void *plan_dev = nullptr;
+    SMH_COMMON_PROLOGUE(false)
+    (void)plan_dev;
+    (void)ws;
+    Peers peers;
+    if (!exch) return set_error(SMH_E_ARG, "exchange_neg: null exchange");
+    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
+    return launch_exchange_neg(lay, peers, st);
+}
+
+int smh_exchange_dz(const smh_dims_t *dims, void *ws_dev, const smh_exchange_t *exch, void *stream)
+{
+    const void *plan_dev = nullptr;
+    SMH_COMMON_PROLOGUE(false)
+    (void)plan_dev;
+    (void)ws;
+    Peers peers;
+    if (!exch) return set_error(SMH_E_ARG, "exchange_dz: null exchange");
+    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
+    return launch_exchange_dz(*dims, lay, peers, st);
 }
 
 int smh_barrier(const smh_exchange_t *exch, void *stream)

@@ -5,8 +5,12 @@
 //   barrier_kernel      device-side barrier between the phases of a step.  Monotonic counters (word 0 = barriers this
 //                       rank has entered, word 8 + p = last barrier peer p announced), so the same kernel node can be
 //                       replayed from a CUDA graph without host-side epochs.
-// The fused parts live in the compute kernels: Dmax push (smh_mpjpe.cu), row-sum all-reduce and gradient reduce-scatter
-// in the sweep epilogues (smh_sweep_tc.cu / smh_sweep_fp32.cu).
+//   exchange_neg_kernel / exchange_dz_kernel   all-gather of the partial row sums and reduce-scatter payload of the
+//                       partial gradient rows: plain 16-byte stores into slot `rank` of the peers' partial buffers; the
+//                       consumers add the partials in rank order (deterministic).  (Adding straight into the peers'
+//                       accumulators from the sweep epilogues was measured 4-5x slower at 8 ranks: ~1 M small remote
+//                       reductions per rank and step.)
+// The Dmax all-reduce is fused into the MPJPE kernel (its last CTA pushes the rank's maximum to every peer).
 #include "smh_common.cuh"
 #include "smh_internal.h"
 
@@ -55,6 +59,48 @@ int launch_push_inputs(const smh_exchange_t &exch, const smh_inputs_t &in, int n
     if (blocks > 148 * 4) blocks = 148 * 4;
     push_inputs_kernel<<<blocks, 256, 0, stream>>>(in, a, n_local, d);
     return check_launch("push_inputs_kernel");
+}
+
+// all-gather of the partial row sums: this rank's neg[0, Mp) -> negparts[rank][.] on every rank (16-byte stores)
+__global__ void __launch_bounds__(256) exchange_neg_kernel(Peers pe, int mp)
+{
+    const float4 *src = reinterpret_cast<const float4 *>(pe.neg(pe.rank));
+    const int n4 = mp / 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 v = src[i];
+        for (int p = 0; p < pe.world; ++p)
+            reinterpret_cast<float4 *>(pe.negparts(p) + (int64_t)pe.rank * mp)[i] = v;
+    }
+}
+
+int launch_exchange_neg(const smh_layout_t &lay, const Peers &peers, cudaStream_t stream)
+{
+    const int mp = lay.tiles_per_side * kTile;
+    int blocks = (mp / 4 + 255) / 256;
+    exchange_neg_kernel<<<blocks, 256, 0, stream>>>(peers, mp);
+    return check_launch("exchange_neg_kernel");
+}
+
+// payload of the reduce-scatter: rows [p * 2 n_local, (p + 1) * 2 n_local) of this rank's full (rank-major) partial
+// gradient go to dzparts[rank][.] on rank p; the owner adds the `world` blocks in rank order in smh_finalize
+__global__ void __launch_bounds__(256) exchange_dz_kernel(Peers pe, int n_local)
+{
+    const int64_t block4 = (int64_t)2 * n_local * kD / 4;                 // float4 per destination rank
+    const float4 *src = reinterpret_cast<const float4 *>(pe.dzacc(pe.rank));
+    const int64_t total = block4 * pe.world;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i / block4);
+        const int64_t j = i - (int64_t)p * block4;
+        reinterpret_cast<float4 *>(pe.dzparts(p))[(int64_t)pe.rank * block4 + j] = src[i];
+    }
+}
+
+int launch_exchange_dz(const smh_dims_t &dims, const smh_layout_t &lay, const Peers &peers, cudaStream_t stream)
+{
+    (void)lay;
+    const int n_local = dims.n / dims.world;
+    exchange_dz_kernel<<<148 * 4, 256, 0, stream>>>(peers, n_local);
+    return check_launch("exchange_dz_kernel");
 }
 
 struct BarrierArgs {

@@ -13,16 +13,25 @@
 
 namespace smh {
 
-__global__ void rn_kernel(const float *__restrict__ neg, float *__restrict__ rn, int m, int mp)
+// n_parts > 1 (peer exchange): neg_i = sum over ranks, in rank order, of the partial row sums delivered into negparts
+__global__ void rn_kernel(float *__restrict__ neg, const float *__restrict__ negparts, int n_parts,
+                          float *__restrict__ rn, int m, int mp)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < mp) rn[i] = (i < m) ? __frcp_rn(neg[i]) : 0.f;
+    if (i >= mp) return;
+    float v = neg[i];
+    if (n_parts > 1) {
+        v = 0.f;
+        for (int p = 0; p < n_parts; ++p) v += negparts[(int64_t)p * mp + i];
+        neg[i] = v;
+    }
+    rn[i] = (i < m) ? __frcp_rn(v) : 0.f;
 }
 
-int launch_rn(const smh_layout_t &lay, const WsView &ws, cudaStream_t stream)
+int launch_rn(const smh_layout_t &lay, const WsView &ws, int n_parts, cudaStream_t stream)
 {
     const int mp = lay.tiles_per_side * kTile;
-    rn_kernel<<<(mp + 255) / 256, 256, 0, stream>>>(ws.neg, ws.rn, lay.m, mp);
+    rn_kernel<<<(mp + 255) / 256, 256, 0, stream>>>(ws.neg, ws.negparts, n_parts, ws.rn, lay.m, mp);
     return check_launch("rn_kernel");
 }
 
@@ -35,7 +44,8 @@ __device__ __forceinline__ const float *sample_ptr_f(const float *base, int k, i
 __global__ void __launch_bounds__(256)
 finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict__ neg,
                 const float *__restrict__ posd, float *__restrict__ rowloss, Stats *__restrict__ stats,
-                const float *__restrict__ dzacc_src, int64_t src_row_offset, float inv_tau, float grad_scale,
+                const float *__restrict__ dzacc_src, int64_t src_row_offset, int n_parts, int64_t part_stride,
+                float inv_tau, float grad_scale,
                 float *__restrict__ loss_out, float *__restrict__ dz1, float *__restrict__ dz2,
                 int64_t dz_row_stride)
 {
@@ -63,7 +73,11 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
             const float *src = dzacc_src + (dz_out_row(row, n, n_local) - src_row_offset) * kD;
             float *dst = (v ? dz2 : dz1) + (int64_t)(k - k_lo) * dz_row_stride;
             const float two_wp = 2.f * wp;
-            for (int c = lane; c < d; c += 32) dst[c] = gs * (src[c] - two_wp * zp[c]);
+            for (int c = lane; c < d; c += 32) {
+                float acc = src[c];
+                for (int p = 1; p < n_parts; ++p) acc += src[(int64_t)p * part_stride + c];     // rank order
+                dst[c] = gs * (acc - two_wp * zp[c]);
+            }
         }
     }
 
@@ -97,8 +111,8 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
 }
 
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
-                    const float *dzacc_src, bool local_block, float temperature, float grad_scale, float *loss, float *dz1,
-                    float *dz2, int64_t dz_row_stride, cudaStream_t stream)
+                    const float *dzacc_src, bool local_block, int n_parts, float temperature, float grad_scale,
+                    float *loss, float *dz1, float *dz2, int64_t dz_row_stride, cudaStream_t stream)
 {
     const int blocks = (lay.m + 7) / 8 < 1184 ? (lay.m + 7) / 8 : 1184;
     const int n_local = dims.n / dims.world;
@@ -107,8 +121,9 @@ int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_i
     smh_inputs_t inp = in;
     inp.n_local = in.n_local;
     finalize_kernel<<<blocks, 256, 0, stream>>>(inp, dims.n, dims.d, dims.rank, ws.neg, ws.posd, ws.rowloss,
-                                                (Stats *)ws.stats, dzacc_src, src_off, 1.0f / temperature,
-                                                grad_scale, loss, dz1, dz2, dz_row_stride);
+                                                (Stats *)ws.stats, dzacc_src, src_off, n_parts,
+                                                (int64_t)2 * n_local * kD, 1.0f / temperature, grad_scale, loss, dz1,
+                                                dz2, dz_row_stride);
     return check_launch("finalize_kernel");
 }
 

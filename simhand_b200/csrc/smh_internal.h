@@ -19,6 +19,8 @@ struct WsView {                 // device pointers carved out of the caller's wo
     float *rn;
     float *rowloss;
     float *dzacc;
+    float *negparts;
+    float *dzparts;
     float *dist;
 };
 
@@ -43,9 +45,12 @@ int launch_sweep_tc(bool backward, bool logits_bf16, const smh_dims_t &dims, con
                     const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
 int launch_push_inputs(const smh_exchange_t &exch, const smh_inputs_t &in, int n_local, int d, cudaStream_t stream);
 int launch_barrier(const smh_exchange_t &exch, cudaStream_t stream);
-int launch_rn(const smh_layout_t &lay, const WsView &ws, cudaStream_t stream);
+int launch_rn(const smh_layout_t &lay, const WsView &ws, int n_parts, cudaStream_t stream);
+int launch_exchange_neg(const smh_layout_t &lay, const Peers &peers, cudaStream_t stream);
+int launch_exchange_dz(const smh_dims_t &dims, const smh_layout_t &lay, const Peers &peers, cudaStream_t stream);
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
-                    const float *dzacc_src, bool local_block, float temperature, float grad_scale, float *loss, float *dz1,
+                    const float *dzacc_src, bool local_block, int n_parts, float temperature, float grad_scale, float *loss,
+                    float *dz1,
                     float *dz2, int64_t dz_row_stride, cudaStream_t stream);
 int launch_weights_dense(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
                          float *pos_w, float *neg_w, cudaStream_t stream);

@@ -110,10 +110,10 @@ def peer_exchange_available() -> bool:
 
 def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, want_grad: bool, group,
                   grad_scale: float = 1.0, strip_len: int = 0):
-    """Sharded step with the collectives fused into the kernels (peer memory over NVLink): push-gather of the inputs,
-    Dmax pushed by the MPJPE kernel, row sums added into every rank's `neg` by the forward sweep, gradient rows
-    added into the owning rank's accumulator by the backward sweep; four device-side barriers separate the phases.
-    No NCCL call on the data path; the whole step is a fixed kernel sequence (CUDA-graph capturable)."""
+    """Sharded step with the collectives done by the library over peer memory (NVLink): push-gather of the inputs,
+    Dmax pushed by the MPJPE kernel's last CTA, partial row sums / gradient rows stored into the peers' partial
+    buffers and reduced in rank order by their consumers; device-side barriers separate the phases.  No NCCL call
+    on the data path; the whole step is a fixed kernel sequence (CUDA-graph capturable) and bitwise reproducible."""
     lib = _lib.load()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = z1.device
@@ -144,18 +144,22 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
         check(lib.smh_mpjpe(pd, plan, ws.data_ptr(), px, st), "smh_mpjpe")
         check(lib.smh_barrier(px, st), "smh_barrier")
         check(lib.smh_forward(pd, plan, ws.data_ptr(), temperature, eng, px, st), "smh_forward")
+        check(lib.smh_exchange_neg(pd, ws.data_ptr(), px, st), "smh_exchange_neg")
         check(lib.smh_barrier(px, st), "smh_barrier")
         loss = torch.empty((), dtype=torch.float32, device=dev)
         dz1 = dz2 = None
         if want_grad:
             check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng, px, st), "smh_backward")
+            check(lib.smh_exchange_dz(pd, ws.data_ptr(), px, st), "smh_exchange_dz")
             check(lib.smh_barrier(px, st), "smh_barrier")
             dz1 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
             dz2 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
-        dz_src = ws.data_ptr() + int(lay.off_dzacc)
-        check(lib.smh_finalize(pd, pi, ws.data_ptr(), dz_src if want_grad else None, temperature, grad_scale,
+        else:
+            # the loss needs the summed row sums: same reduction the backward's first kernel would do
+            check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng | _lib.BACKWARD_RN_ONLY, px, st), "smh_rn")
+        check(lib.smh_finalize(pd, pi, ws.data_ptr(), None, temperature, grad_scale,
                                loss.data_ptr(), dz1.data_ptr() if want_grad else None,
-                               dz2.data_ptr() if want_grad else None, d, st), "smh_finalize")
+                               dz2.data_ptr() if want_grad else None, d, px, st), "smh_finalize")
         # the next step's push may overwrite xin while a slow peer still reads it in finalize: close the step
         check(lib.smh_barrier(px, st), "smh_barrier")
     return loss, dz1, dz2
@@ -209,7 +213,7 @@ def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, 
             dz2 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
         check(lib.smh_finalize(pd, pi, ws.data_ptr(), dz_local.data_ptr() if want_grad else None, temperature,
                                grad_scale, loss.data_ptr(), dz1.data_ptr() if want_grad else None,
-                               dz2.data_ptr() if want_grad else None, d, st), "smh_finalize")
+                               dz2.data_ptr() if want_grad else None, d, None, st), "smh_finalize")
         # keep the gathered inputs alive until the stream has consumed them
         gathered.record_stream(torch.cuda.current_stream(dev))
     return loss, dz1, dz2

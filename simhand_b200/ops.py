@@ -135,7 +135,7 @@ def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _
             dz2 = torch.empty((n, d), dtype=torch.float32, device=dev)
         check(lib.smh_finalize(pd, pi, ws.data_ptr(), None, temperature, grad_scale, loss.data_ptr(),
                                dz1.data_ptr() if want_grad else None, dz2.data_ptr() if want_grad else None,
-                               d, st), "smh_finalize")
+                               d, None, st), "smh_finalize")
         del keep
         if return_aux:
             aux = dict(ws=ws, ctx=ctx, neg=ctx.view(ws, lay.off_neg, lay.m),

@@ -51,11 +51,13 @@ def main():
         ("mpjpe", lambda: lib.smh_mpjpe(pd, plan, ws.data_ptr(), px, st)),
         ("barrier2", lambda: lib.smh_barrier(px, st)),
         ("fwd", lambda: lib.smh_forward(pd, plan, ws.data_ptr(), 0.5, eng, px, st)),
+        ("xneg", lambda: lib.smh_exchange_neg(pd, ws.data_ptr(), px, st)),
         ("barrier3", lambda: lib.smh_barrier(px, st)),
         ("bwd", lambda: lib.smh_backward(pd, plan, ws.data_ptr(), 0.5, eng, px, st)),
+        ("xdz", lambda: lib.smh_exchange_dz(pd, ws.data_ptr(), px, st)),
         ("barrier4", lambda: lib.smh_barrier(px, st)),
-        ("finalize", lambda: lib.smh_finalize(pd, pi, ws.data_ptr(), dz_src, 0.5, 1.0, loss.data_ptr(), g1.data_ptr(),
-                                              g2.data_ptr(), 128, st)),
+        ("finalize", lambda: lib.smh_finalize(pd, pi, ws.data_ptr(), None, 0.5, 1.0, loss.data_ptr(), g1.data_ptr(),
+                                              g2.data_ptr(), 128, px, st)),
         ("barrier5", lambda: lib.smh_barrier(px, st)),
     ]
     iters = 20
