@@ -19,6 +19,7 @@ namespace smh {
 struct PushArgs {
     float *dst[kMaxPeers];      // peer p's gathered-input buffer, already offset to this rank's chunk
     int world;
+    int aligned16;              // every dst base is 16-byte aligned
 };
 
 // One warp per (view, local sample): gathers the caller's (possibly strided) z row and [21, 2] joint view and writes
@@ -35,9 +36,17 @@ __global__ void __launch_bounds__(256) push_inputs_kernel(smh_inputs_t in, PushA
         const float *jb = (v ? in.j2_dev : in.j1_dev) + (int64_t)k * in.j_sample_stride;
         const int64_t zo = (v ? off_z2 : 0) + (int64_t)k * d;
         const int64_t jo = (v ? off_j2 : off_j1) + (int64_t)k * 42;
-        for (int c = lane; c < d; c += 32) {
-            const float val = zp[c];
-            for (int p = 0; p < a.world; ++p) a.dst[p][zo + c] = val;
+        if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(zp) | (uintptr_t)(zo * 4)) & 15) == 0 && a.aligned16) {
+            for (int c = lane * 4; c < d; c += 128) {
+                const float4 val = *reinterpret_cast<const float4 *>(zp + c);
+#pragma unroll 4
+                for (int p = 0; p < a.world; ++p) *reinterpret_cast<float4 *>(a.dst[p] + zo + c) = val;
+            }
+        } else {
+            for (int c = lane; c < d; c += 32) {
+                const float val = zp[c];
+                for (int p = 0; p < a.world; ++p) a.dst[p][zo + c] = val;
+            }
         }
         for (int c = lane; c < 42; c += 32) {
             const float val = jb[(int64_t)(c >> 1) * in.j_joint_stride + (c & 1) * in.j_coord_stride];
@@ -55,6 +64,9 @@ int launch_push_inputs(const smh_exchange_t &exch, const smh_inputs_t &in, int n
         if (!exch.xin_peer[p]) return set_error(SMH_E_ARG, "exchange xin_peer[%d] is null", p);
         a.dst[p] = (float *)exch.xin_peer[p] + (int64_t)exch.rank * chunk;
     }
+    a.aligned16 = 1;
+    for (int p = 0; p < exch.world; ++p)
+        if (reinterpret_cast<uintptr_t>(a.dst[p]) & 15) a.aligned16 = 0;
     int blocks = (2 * n_local + 7) / 8;
     if (blocks > 148 * 4) blocks = 148 * 4;
     push_inputs_kernel<<<blocks, 256, 0, stream>>>(in, a, n_local, d);
