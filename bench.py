@@ -45,36 +45,56 @@ def _peaks():
     return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)", sm_max_mhz=1965.0)
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+class ClockSampler:
+    """Streams nvidia-smi clocks / throttle reasons of one GPU (-lms 50) while the timed region runs."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.samples, self.proc, self.thread = index, [], None, None
 
-    def run(self):
-        while not self.stop_flag.is_set():
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [x.strip() for x in out.stdout.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                self.proc.wait(timeout=2)
             except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [v for v in (num(s[0]) for s in self.samples) if v is not None]
+        mx = [v for v in (num(s[1]) for s in self.samples) if v is not None]
+        pw = [v for v in (num(s[2]) for s in self.samples) if v is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples for i in range(4) if s[3 + i].lower().startswith("active")})
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=reasons, samples=len(self.samples))
+                    power_w_max=max(pw) if pw else None, reasons=reasons, samples=len(self.samples))
 
 
 def _make_batch(n):
@@ -227,8 +247,7 @@ def run_ours(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     if sampler:
-        sampler.stop_flag.set()
-        sampler.join(timeout=2)
+        sampler.stop()
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -326,7 +345,7 @@ def time_kernels(ops, _lib, z1, z2, j1, j2, engine, iters):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="tf32", choices=["tf32", "fp32", "auto", "bf16"])
