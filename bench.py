@@ -325,7 +325,7 @@ def time_kernels(ops, _lib, z1, z2, j1, j2, engine, iters):
         ("sweep_fwd", lambda: lib.smh_forward(pd, plan, ws.data_ptr(), TAU, eng, None, st)),
         ("sweep_bwd", lambda: lib.smh_backward(pd, plan, ws.data_ptr(), TAU, eng, None, st)),
         ("finalize", lambda: lib.smh_finalize(pd, pi, ws.data_ptr(), None, TAU, 1.0, loss.data_ptr(), g1.data_ptr(),
-                                              g2.data_ptr(), d, None, st)),
+                                              g2.data_ptr(), d, 0, None, st)),
     ]
     acc = {k: 0.0 for k, _ in calls}
     for it in range(iters + 1):

@@ -51,6 +51,9 @@ extern "C" {
 #define SMH_ENGINE_FP32 1        /* CUDA-core FFMA, fp32 accumulate (exact-fp32 mode) */
 #define SMH_ENGINE_TC_BF16 2     /* tcgen05: bf16 operands in both sweeps (bf16 mode) */
 #define SMH_BACKWARD_RN_ONLY 0x200 /* OR into smh_backward's engine: only reduce the row sums (loss without gradient) */
+#define SMH_UNIT_NEG_WEIGHTS 0x400 /* OR into smh_forward/backward's engine and smh_finalize's flags: W_ij == 1 (the reference's
+                                    * vanila_pos_weights_contrastive_loss / vanila_contrastive_loss; smh_mpjpe can be skipped) */
+#define SMH_UNIT_POS_WEIGHTS 0x800 /* OR into smh_finalize's flags: Wp_k == 1 (vanila_neg_weights_contrastive_loss, vanila_contrastive_loss) */
 #define SMH_PREP_NO_ZERO 0x100   /* OR into smh_prep's engine: the accumulators were already zeroed by smh_prep_zero */
 
 /* problem description shared by all calls */
@@ -180,7 +183,7 @@ int smh_barrier(const smh_exchange_t *exch, void *stream);
 int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev,
                  const float *dzacc_src_dev, float temperature, float grad_scale,
                  float *loss_dev, float *dz1_dev, float *dz2_dev, int64_t dz_row_stride,
-                 const smh_exchange_t *exch, void *stream);
+                 int flags, const smh_exchange_t *exch, void *stream);
 
 /* materialised weights with the reference's return shapes: pos_w [N], neg_w [M, M] row-major
  * (utils.py:235, :259).  world == 1 only.  Needs smh_prep + smh_mpjpe. */

@@ -45,6 +45,16 @@ def run_case(ns, n, d, jset, seed):
         out[f"loss_{tag}"] = loss.detach().numpy()
         out[f"dz1_{tag}"] = x1.grad.numpy()
         out[f"dz2_{tag}"] = x2.grad.numpy()
+    # the other weightings of the same loss (pos_neg == "pos" / "neg", and plain NT-Xent), fp64
+    for tag, call in (("pos", lambda a, c: ns["vanila_pos_weights_contrastive_loss"](a, c, pos_w.double())),
+                      ("neg", lambda a, c: ns["vanila_neg_weights_contrastive_loss"](a, c, neg_w.double())),
+                      ("plain", lambda a, c: ns["vanila_contrastive_loss"](a, c))):
+        x1 = z1.double().clone().detach().requires_grad_(True)
+        x2 = z2.double().clone().detach().requires_grad_(True)
+        loss = call(x1, x2)
+        loss.backward()
+        out[f"loss_{tag}_f64"] = loss.detach().numpy()
+        out[f"dz1_{tag}_f64"] = x1.grad.numpy()
     out.update(z1=z1.numpy(), z2=z2.numpy(), joints1=j1.numpy(), joints2=j2.numpy(),
                pos_w=pos_w.numpy(), neg_w=neg_w.numpy(), temperature=np.float64(0.5))
     return out

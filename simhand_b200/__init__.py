@@ -4,6 +4,7 @@ Public API (mirrors `src/models/utils.py` of the reference):
     get_weights_linear, vanila_weights_contrastive_loss, weighted_ntxent, l2_normalize, install
 """
 from .ops import (LazyWeights, get_weights_linear, install, l2_normalize, mpjpe_weights, run_step,  # noqa: F401
-                  vanila_weights_contrastive_loss, weighted_ntxent)
+                  vanila_contrastive_loss, vanila_neg_weights_contrastive_loss,
+                  vanila_pos_weights_contrastive_loss, vanila_weights_contrastive_loss, weighted_ntxent)
 
 __version__ = "0.1.0"

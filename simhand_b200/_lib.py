@@ -17,6 +17,8 @@ ENGINES = {"tf32": ENGINE_TC_TF32, "tc": ENGINE_TC_TF32, "fp32": ENGINE_FP32, "b
 
 PREP_NO_ZERO = 0x100
 BACKWARD_RN_ONLY = 0x200
+UNIT_NEG_WEIGHTS = 0x400
+UNIT_POS_WEIGHTS = 0x800
 FLAG_SLOW_DOMAIN = 1
 FLAG_NONFINITE = 2
 
@@ -93,7 +95,7 @@ def load() -> ctypes.CDLL:
     lib.smh_exchange_neg.argtypes = [pd, vp, px, vp]
     lib.smh_exchange_dz.argtypes = [pd, vp, px, vp]
     lib.smh_prep_zero.argtypes = [pd, vp, vp]
-    lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, ctypes.POINTER(Exchange), vp]
+    lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, ctypes.c_int, ctypes.POINTER(Exchange), vp]
     lib.smh_weights_dense.argtypes = [pd, vp, vp, vp, vp, vp]
     lib.smh_l2norm_fwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     lib.smh_l2norm_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]

@@ -382,9 +382,11 @@ int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, floa
     (void)exch;                       // the sweep accumulates locally; smh_exchange_neg ships the partial sums
     Peers peers;
     if ((rc = make_peers(*dims, lay, ws_dev, nullptr, &peers))) return rc;
+    const bool unit_w = (engine & SMH_UNIT_NEG_WEIGHTS) != 0;
+    engine &= 0xff;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
-        return launch_sweep_tc(false, engine == SMH_ENGINE_TC_BF16, *dims, lay, pv, ws, peers, temperature, st);
-    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, *dims, lay, pv, ws, peers, temperature, st);
+        return launch_sweep_tc(false, engine == SMH_ENGINE_TC_BF16, unit_w, *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, unit_w, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
 
@@ -399,15 +401,17 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
     // peer exchange: the row sums are the rank-ordered sum of the partials every rank delivered
     if ((rc = launch_rn(lay, ws, exch ? dims->world : 1, st))) return rc;
     if (engine & SMH_BACKWARD_RN_ONLY) return 0;
+    const bool unit_w = (engine & SMH_UNIT_NEG_WEIGHTS) != 0;
+    engine &= 0xff;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
-        return launch_sweep_tc(true, true, *dims, lay, pv, ws, peers, temperature, st);
-    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, *dims, lay, pv, ws, peers, temperature, st);
+        return launch_sweep_tc(true, true, unit_w, *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, unit_w, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
 
 int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, const float *dzacc_src_dev,
                  float temperature, float grad_scale, float *loss_dev, float *dz1_dev, float *dz2_dev,
-                 int64_t dz_row_stride, const smh_exchange_t *exch, void *stream)
+                 int64_t dz_row_stride, int flags, const smh_exchange_t *exch, void *stream)
 {
     const void *plan_dev = nullptr;
     SMH_COMMON_PROLOGUE(false)
@@ -426,8 +430,8 @@ int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, c
         local_block = true;
         n_parts = dims->world;
     }
-    return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, local_block, n_parts, temperature, grad_scale, loss_dev,
-                           dz1_dev, dz2_dev, dz_row_stride, st);
+    return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, local_block, n_parts, (flags & SMH_UNIT_POS_WEIGHTS) != 0,
+                           temperature, grad_scale, loss_dev, dz1_dev, dz2_dev, dz_row_stride, st);
 }
 
 int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float *pos_w_dev,

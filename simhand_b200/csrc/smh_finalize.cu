@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256)
 finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict__ neg,
                 const float *__restrict__ posd, float *__restrict__ rowloss, Stats *__restrict__ stats,
                 const float *__restrict__ dzacc_src, int64_t src_row_offset, int n_parts, int64_t part_stride,
-                float inv_tau, float grad_scale,
+                bool unit_pos_w, float inv_tau, float grad_scale,
                 float *__restrict__ loss_out, float *__restrict__ dz1, float *__restrict__ dz2,
                 int64_t dz_row_stride)
 {
@@ -67,7 +67,7 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
         float dot = 0.f;
         for (int c = lane; c < d; c += 32) dot = fmaf(zi[c], zp[c], dot);
         dot = warp_sum(dot);
-        const float wp = __fdiv_rn(__fsub_rn(pmax, posd[k]), pden);            // utils.py:235
+        const float wp = unit_pos_w ? 1.0f : __fdiv_rn(__fsub_rn(pmax, posd[k]), pden);   // utils.py:235
         if (lane == 0) rowloss[row] = logf(neg[row]) - dot * wp * inv_tau;      // utils.py:420-426
         if (dz1 != nullptr && k >= k_lo && k < k_hi) {
             const float *src = dzacc_src + (dz_out_row(row, n, n_local) - src_row_offset) * kD;
@@ -111,7 +111,8 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
 }
 
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
-                    const float *dzacc_src, bool local_block, int n_parts, float temperature, float grad_scale,
+                    const float *dzacc_src, bool local_block, int n_parts, bool unit_pos_w, float temperature,
+                    float grad_scale,
                     float *loss, float *dz1, float *dz2, int64_t dz_row_stride, cudaStream_t stream)
 {
     const int blocks = (lay.m + 7) / 8 < 1184 ? (lay.m + 7) / 8 : 1184;
@@ -122,7 +123,7 @@ int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_i
     inp.n_local = in.n_local;
     finalize_kernel<<<blocks, 256, 0, stream>>>(inp, dims.n, dims.d, dims.rank, ws.neg, ws.posd, ws.rowloss,
                                                 (Stats *)ws.stats, dzacc_src, src_off, n_parts,
-                                                (int64_t)2 * n_local * kD, 1.0f / temperature, grad_scale, loss, dz1,
+                                                (int64_t)2 * n_local * kD, unit_pos_w, 1.0f / temperature, grad_scale, loss, dz1,
                                                 dz2, dz_row_stride);
     return check_launch("finalize_kernel");
 }

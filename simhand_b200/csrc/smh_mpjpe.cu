@@ -10,6 +10,8 @@
 //
 // CUDA-core kernel: per ordered pair 21 MUFU.RSQ and ~190 FMA-pipe lane-operations; the packed
 // FADD2/FMUL2/FFMA2 forms halve the issue slots.  This is the kernel the roofline in bench.py is quoted on.
+#include <cstdlib>
+
 #include "smh_common.cuh"
 #include "smh_internal.h"
 
@@ -62,7 +64,7 @@ __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10
 }
 
 // MODE as in joint_pair.  vmax_bits: running maximum of the integer image of D (D >= 0; NaN is larger than any finite).
-template <int MODE>
+template <int MODE, int UN>
 __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, float *__restrict__ tile_out, int I,
                                                 int J, int m, const float *cs, uint32_t &vmax_bits)
 {
@@ -88,19 +90,22 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, fl
     const bool row_ok = (I * kTile + r) < m;
     const int col_limit = m - J * kTile;          // columns >= col_limit are padding
 #pragma unroll 1
-    for (int cq = 0; cq < 16; ++cq) {
-        const int c0 = h * 64 + cq * 4;
-        float dv[4];
+    for (int cq = 0; cq < 64 / UN; ++cq) {
+        const int c0 = h * 64 + cq * UN;
+        float dv[UN];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < UN; ++u) {
             dv[u] = mpjpe_one<MODE>(ax, ay, ax20, ay20, cs + (c0 + u) * kJP, div21);
             if (row_ok && (c0 + u) < col_limit) vmax_bits = max(vmax_bits, __float_as_uint(dv[u]));
         }
-        *reinterpret_cast<float4 *>(tile_out + dist_index(r, c0)) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+#pragma unroll
+        for (int u = 0; u < UN; u += 4)
+            *reinterpret_cast<float4 *>(tile_out + dist_index(r, c0 + u)) = make_float4(dv[u], dv[u + 1], dv[u + 2], dv[u + 3]);
     }
 }
 
-__global__ void __launch_bounds__(256, 2)
+template <int UN, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float *__restrict__ dist, int m,
              Stats *__restrict__ stats, Peers peers)
 {
@@ -119,11 +124,11 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float
     const bool slow = flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE);
     uint32_t vmax_bits = 0u;
     if (slow)
-        mpjpe_tile_body<0>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
+        mpjpe_tile_body<0, 4>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
     else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
-        mpjpe_tile_body<1>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);     // zero distances: diagonal, zero padding
+        mpjpe_tile_body<1, 4>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);     // zero distances: diagonal, zero padding
     else
-        mpjpe_tile_body<2>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
+        mpjpe_tile_body<2, UN>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
     auto block_max = [&](uint32_t v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -139,7 +144,7 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float
     if (!slow && bmax > 0x7f800000u) {
         // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo the tile guarded
         vmax_bits = 0u;
-        mpjpe_tile_body<1>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
+        mpjpe_tile_body<1, 4>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
         bmax = block_max(vmax_bits);
     }
     if (threadIdx.x == 0) {
@@ -167,7 +172,16 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
 {
     (void)dims;
     if (lay.n_stored_tiles == 0) return 0;
-    mpjpe_kernel<<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, (Stats *)ws.stats, peers);
+    static const int variant = getenv("SMH_MPJPE_VARIANT") ? atoi(getenv("SMH_MPJPE_VARIANT")) : 0;   // tuning knob
+    const int grid = lay.n_stored_tiles;
+    Stats *st = (Stats *)ws.stats;
+    switch (variant) {
+        case 1: mpjpe_kernel<8, 2><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
+        case 2: mpjpe_kernel<8, 1><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
+        case 3: mpjpe_kernel<4, 1><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
+        case 4: mpjpe_kernel<16, 1><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
+        default: mpjpe_kernel<4, 2><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
+    }
     return check_launch("mpjpe_kernel");
 }
 

@@ -65,7 +65,7 @@ template <bool BWD, bool TRANSPOSED, bool MASKED>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned char *dstage, int r, int chunk,
                                                int gi, int gj0, int m, bool diagonal, float dmax,
                                                const DivConst &divw, float k2, float rni,
-                                               const float *__restrict__ rn, float (&rowsum)[4])
+                                               const float *__restrict__ rn, float (&rowsum)[4], bool unit_w)
 {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -89,7 +89,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned
         for (int u = 0; u < 4; ++u) {
             const int c = q * 4 + u;
             const float s = __uint_as_float(v[c]);
-            const float w = div_fast(__fsub_rn(dmax, dv[u]), divw);
+            const float w = unit_w ? 1.0f : div_fast(__fsub_rn(dmax, dv[u]), divw);   // unit_w: unweighted negatives
             float e = ex2_approx(s * (w * k2));
             float g = BWD ? w * e * (rni + rnjv[u]) : 0.f;
             if (MASKED) {
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
                 const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
-                float k2)
+                float k2, bool unit_w)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
     using Cfg = TcCfg<SBF16>;
@@ -357,14 +357,14 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 tc_wait_ld();
                 if (masked) {
                     if (transposed)
-                        epilogue_chunk<BWD, true, true>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
+                        epilogue_chunk<BWD, true, true>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum, unit_w);
                     else
-                        epilogue_chunk<BWD, false, true>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
+                        epilogue_chunk<BWD, false, true>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum, unit_w);
                 } else {
                     if (transposed)
-                        epilogue_chunk<BWD, true, false>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
+                        epilogue_chunk<BWD, true, false>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum, unit_w);
                     else
-                        epilogue_chunk<BWD, false, false>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum);
+                        epilogue_chunk<BWD, false, false>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum, unit_w);
                 }
                 if (BWD) {
                     // G as packed bf16x2 over the first half of this warp's own S columns
@@ -424,8 +424,8 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
 }
 
 template <bool BWD, bool SBF16>
-static int launch_one(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
-                      const Peers &peers, float temperature, cudaStream_t stream)
+static int launch_one(bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
+                      const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream)
 {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -439,17 +439,17 @@ static int launch_one(const smh_dims_t &dims, const smh_layout_t &lay, const Pla
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
     sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, ws.zb,
                                                                    ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
-                                                                   dims.n, n_local, k2);
+                                                                   dims.n, n_local, k2, unit_w);
     return check_launch("sweep_tc_kernel");
 }
 
-int launch_sweep_tc(bool backward, bool logits_bf16, const smh_dims_t &dims, const smh_layout_t &lay,
+int launch_sweep_tc(bool backward, bool logits_bf16, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay,
                     const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream)
 {
     if (lay.n_strips == 0) return 0;
-    if (backward) return launch_one<true, true>(dims, lay, plan, ws, peers, temperature, stream);
-    if (logits_bf16) return launch_one<false, true>(dims, lay, plan, ws, peers, temperature, stream);
-    return launch_one<false, false>(dims, lay, plan, ws, peers, temperature, stream);
+    if (backward) return launch_one<true, true>(unit_w, dims, lay, plan, ws, peers, temperature, stream);
+    if (logits_bf16) return launch_one<false, true>(unit_w, dims, lay, plan, ws, peers, temperature, stream);
+    return launch_one<false, false>(unit_w, dims, lay, plan, ws, peers, temperature, stream);
 }
 
 }  // namespace smh

@@ -159,7 +159,7 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
             check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng | _lib.BACKWARD_RN_ONLY, px, st), "smh_rn")
         check(lib.smh_finalize(pd, pi, ws.data_ptr(), None, temperature, grad_scale,
                                loss.data_ptr(), dz1.data_ptr() if want_grad else None,
-                               dz2.data_ptr() if want_grad else None, d, px, st), "smh_finalize")
+                               dz2.data_ptr() if want_grad else None, d, 0, px, st), "smh_finalize")
         # the next step's push may overwrite xin while a slow peer still reads it in finalize: close the step
         check(lib.smh_barrier(px, st), "smh_barrier")
     return loss, dz1, dz2
@@ -213,7 +213,7 @@ def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, 
             dz2 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
         check(lib.smh_finalize(pd, pi, ws.data_ptr(), dz_local.data_ptr() if want_grad else None, temperature,
                                grad_scale, loss.data_ptr(), dz1.data_ptr() if want_grad else None,
-                               dz2.data_ptr() if want_grad else None, d, None, st), "smh_finalize")
+                               dz2.data_ptr() if want_grad else None, d, 0, None, st), "smh_finalize")
         # keep the gathered inputs alive until the stream has consumed them
         gathered.record_stream(torch.cuda.current_stream(dev))
     return loss, dz1, dz2

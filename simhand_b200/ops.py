@@ -109,8 +109,11 @@ def _stream_ptr(device) -> int:
 
 
 def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _DEFAULT_ENGINE,
-             want_grad: bool = True, grad_scale: float = 1.0, strip_len: int = 0, return_aux: bool = False):
-    """One fused fwd(+bwd) step on a single GPU.  Returns (loss[()], dz1, dz2[, aux])."""
+             want_grad: bool = True, grad_scale: float = 1.0, strip_len: int = 0, return_aux: bool = False,
+             pos_weighted: bool = True, neg_weighted: bool = True):
+    """One fused fwd(+bwd) step on a single GPU.  Returns (loss[()], dz1, dz2[, aux]).
+    pos_weighted / neg_weighted = False give the reference's neg-only / pos-only / unweighted losses
+    (utils.py:468, :430, :157): the corresponding weight is 1."""
     for t, nm in ((z1, "z1"), (z2, "z2"), (joints1, "joints1"), (joints2, "joints2")):
         _require_cuda(t, nm)
     lib = _lib.load()
@@ -124,18 +127,21 @@ def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _
         ws = torch.empty(int(lay.ws_bytes), dtype=torch.uint8, device=dev)
         st = _stream_ptr(dev)
         pd, pi = ctypes.byref(dims), ctypes.byref(inp)
+        sweep_eng = eng | (0 if neg_weighted else _lib.UNIT_NEG_WEIGHTS)
+        fin_flags = 0 if pos_weighted else _lib.UNIT_POS_WEIGHTS
         check(lib.smh_prep(pd, pi, ws.data_ptr(), eng, st), "smh_prep")
-        check(lib.smh_mpjpe(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), None, st), "smh_mpjpe")
-        check(lib.smh_forward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, eng, None, st), "smh_forward")
+        if neg_weighted:                  # unweighted negatives need no distance matrix at all
+            check(lib.smh_mpjpe(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), None, st), "smh_mpjpe")
+        check(lib.smh_forward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, sweep_eng, None, st), "smh_forward")
         loss = torch.empty((), dtype=torch.float32, device=dev)
         dz1 = dz2 = None
         if want_grad:
-            check(lib.smh_backward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, eng, None, st), "smh_backward")
+            check(lib.smh_backward(pd, ctx.plan_dev.data_ptr(), ws.data_ptr(), temperature, sweep_eng, None, st), "smh_backward")
             dz1 = torch.empty((n, d), dtype=torch.float32, device=dev)
             dz2 = torch.empty((n, d), dtype=torch.float32, device=dev)
         check(lib.smh_finalize(pd, pi, ws.data_ptr(), None, temperature, grad_scale, loss.data_ptr(),
                                dz1.data_ptr() if want_grad else None, dz2.data_ptr() if want_grad else None,
-                               d, None, st), "smh_finalize")
+                               d, fin_flags, None, st), "smh_finalize")
         del keep
         if return_aux:
             aux = dict(ws=ws, ctx=ctx, neg=ctx.view(ws, lay.off_neg, lay.m),
@@ -151,11 +157,14 @@ class _WeightedNTXentFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, z1, z2, joints1, joints2, temperature, engine, group):
+    def forward(ctx, z1, z2, joints1, joints2, temperature, engine, group, pos_weighted=True, neg_weighted=True):
         want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         if group is None:
-            loss, dz1, dz2 = run_step(z1, z2, joints1, joints2, temperature, engine, want)
+            loss, dz1, dz2 = run_step(z1, z2, joints1, joints2, temperature, engine, want,
+                                      pos_weighted=pos_weighted, neg_weighted=neg_weighted)
         else:
+            if not (pos_weighted and neg_weighted):
+                raise NotImplementedError("the sharded path implements the pos_neg weighting only")
             from .dist import run_step_sharded
             loss, dz1, dz2 = run_step_sharded(z1, z2, joints1, joints2, temperature, engine, want, group)
         if want:
@@ -168,16 +177,18 @@ class _WeightedNTXentFn(torch.autograd.Function):
         dz1, dz2 = ctx.saved_tensors
         g1 = grad_out * dz1 if ctx.needs_input_grad[0] else None
         g2 = grad_out * dz2 if ctx.needs_input_grad[1] else None
-        return g1, g2, None, None, None, None, None
+        return g1, g2, None, None, None, None, None, None, None
 
 
 def weighted_ntxent(z1: torch.Tensor, z2: torch.Tensor, joints1: torch.Tensor, joints2: torch.Tensor,
-                    temperature: float = 0.5, group=None, engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
+                    temperature: float = 0.5, group=None, engine: str = _DEFAULT_ENGINE,
+                    pos_weighted: bool = True, neg_weighted: bool = True) -> torch.Tensor:
     """Fused similarity-weighted NT-Xent (weight_type linear, diff_type mpjpe, pos_neg): equals
     `vanila_weights_contrastive_loss(z1, z2, *get_weights_linear(joints1, joints2, 'mpjpe'), temperature)`
     of the reference.  With `group` (a torch.distributed process group) the batch is the concatenation of
     every rank's local batch and the work is sharded over the ranks."""
-    return _WeightedNTXentFn.apply(z1, z2, joints1, joints2, float(temperature), engine, group)
+    return _WeightedNTXentFn.apply(z1, z2, joints1, joints2, float(temperature), engine, group,
+                                   bool(pos_weighted), bool(neg_weighted))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -268,15 +279,46 @@ def vanila_weights_contrastive_loss(z1: torch.Tensor, z2: torch.Tensor, pos_weig
         "handles returned by simhand_b200.get_weights_linear (fused path)")
 
 
+def _source_of(weights, kind: str) -> _WeightSource:
+    if not isinstance(weights, LazyWeights) or weights.kind != kind:
+        raise NotImplementedError(
+            f"simhand_b200: expected the {kind}-weights handle returned by simhand_b200.get_weights_linear "
+            "(dense weight tensors are not accepted yet)")
+    return weights._source
+
+
+def vanila_pos_weights_contrastive_loss(z1, z2, pos_weights, temperature: float = 0.5,
+                                        engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
+    """Drop-in for `src/models/utils.py:430` (`pos_neg == "pos"`): only the positive logits are weighted."""
+    src = _source_of(pos_weights, "pos")
+    return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, True, False)
+
+
+def vanila_neg_weights_contrastive_loss(z1, z2, neg_weights, temperature: float = 0.5,
+                                        engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
+    """Drop-in for `src/models/utils.py:468` (`pos_neg == "neg"`): only the negative logits are weighted."""
+    src = _source_of(neg_weights, "neg")
+    return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, False, True)
+
+
+def vanila_contrastive_loss(z1, z2, temperature: float = 0.5, engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
+    """Drop-in for `src/models/utils.py:157`: plain NT-Xent (both weights 1), same fused sweeps."""
+    zero = torch.zeros((z1.shape[0], 21, 2), dtype=torch.float32, device=z1.device)
+    return weighted_ntxent(z1, z2, zero, zero, temperature, None, engine, False, False)
+
+
+_DROP_INS = ("get_weights_linear", "vanila_weights_contrastive_loss", "vanila_pos_weights_contrastive_loss",
+             "vanila_neg_weights_contrastive_loss", "vanila_contrastive_loss")
+
+
 def install(*modules) -> None:
     """Rebinds `get_weights_linear` / `vanila_weights_contrastive_loss` in the given modules (the reference's
     `src.models.utils` and the model modules that imported the names: simhand_w_model, peclr_w_model,
     simclr_w_model).  See INTEGRATION.md."""
     for mod in modules:
-        for name, fn in (("get_weights_linear", get_weights_linear),
-                         ("vanila_weights_contrastive_loss", vanila_weights_contrastive_loss)):
+        for name in _DROP_INS:
             if hasattr(mod, name):
-                setattr(mod, name, fn)
+                setattr(mod, name, globals()[name])
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -115,6 +115,26 @@ def test_step_matches_c_oracle_mid_size(n, jset):
         assert rel.max() < (4e-3 if engine == "bf16" else 2e-4)
 
 
+@pytest.mark.parametrize("variant", ["pos", "neg", "plain"])
+def test_other_weightings_match_reference(golden, variant):
+    """pos-only, neg-only and unweighted NT-Xent (utils.py:430, :468, :157) through the same kernels."""
+    z1, z2, a, b = _to_dev(golden)
+    z1 = z1.clone().requires_grad_(True)
+    z2 = z2.clone().requires_grad_(True)
+    pw, nw = ops.get_weights_linear(a, b, "mpjpe")
+    if variant == "pos":
+        loss = ops.vanila_pos_weights_contrastive_loss(z1, z2, pw)
+    elif variant == "neg":
+        loss = ops.vanila_neg_weights_contrastive_loss(z1, z2, nw)
+    else:
+        loss = ops.vanila_contrastive_loss(z1, z2)
+    loss.backward()
+    ref = float(golden[f"loss_{variant}_f64"])
+    assert abs(float(loss.detach()) - ref) <= LOSS_RTOL * abs(ref), (variant, float(loss.detach()), ref)
+    cos, mx = R.grad_metrics(z1.grad.cpu().numpy(), golden[f"dz1_{variant}_f64"])
+    assert cos >= GRAD_COS and mx <= GRAD_MAXABS, (variant, cos, mx)
+
+
 def test_non_contiguous_and_half_inputs():
     dev = _dev()
     z1, z2, j1, j2 = synth.make_batch(96, 128, 23, "hand")

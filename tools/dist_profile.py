@@ -57,7 +57,7 @@ def main():
         ("xdz", lambda: lib.smh_exchange_dz(pd, ws.data_ptr(), px, st)),
         ("barrier4", lambda: lib.smh_barrier(px, st)),
         ("finalize", lambda: lib.smh_finalize(pd, pi, ws.data_ptr(), None, 0.5, 1.0, loss.data_ptr(), g1.data_ptr(),
-                                              g2.data_ptr(), 128, px, st)),
+                                              g2.data_ptr(), 128, 0, px, st)),
         ("barrier5", lambda: lib.smh_barrier(px, st)),
     ]
     iters = 20
