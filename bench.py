@@ -270,7 +270,9 @@ def run_ours(args):
     m = 2 * N_PER_VIEW
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
-                dtype={"tf32": "tf32", "bf16": "bf16"}.get(engine, "f32"), data="synthetic",
+                dtype={"tf32": "tf32 logits / bf16 value operands, fp32 accumulate", "bf16": "bf16",
+                       "fp16": "f16 logits (11-bit significand, as tf32) / bf16 value operands, fp32 accumulate"
+                       }.get(engine, "f32"), data="synthetic",
                 config=dict(workload="handclr_w loss fwd+bwd, global batch 8192 (2N=16384), d=128, 21 joints, "
                                      "mpjpe/linear/pos_neg, tau 0.5", global_batch=N_PER_VIEW, proj_dim=DIM,
                             engine=engine, parallelism=f"tile-pair sharded x{world}" if world > 1 else "single GPU",
@@ -348,7 +350,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="tf32", choices=["tf32", "fp32", "auto", "bf16"])
+    ap.add_argument("--engine", default="fp16", choices=["tf32", "fp32", "auto", "bf16", "fp16"])
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
                     help="multi-GPU exchange: collectives fused into the kernels over peer memory, or NCCL calls")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the step eagerly")

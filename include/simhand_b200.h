@@ -50,6 +50,9 @@ extern "C" {
 #define SMH_ENGINE_TC_TF32 0     /* tcgen05: tf32 logits in the forward sweep, bf16 operands in the backward sweep */
 #define SMH_ENGINE_FP32 1        /* CUDA-core FFMA, fp32 accumulate (exact-fp32 mode) */
 #define SMH_ENGINE_TC_BF16 2     /* tcgen05: bf16 operands in both sweeps (bf16 mode) */
+#define SMH_ENGINE_TC_FP16 3     /* tcgen05: fp16 logit operands in the forward sweep (11-bit significand, the precision of
+                                  * tf32, at half the staging traffic; |z| <= 1 after L2 normalisation so the fp16 range is
+                                  * no issue), bf16 operands in the backward sweep */
 #define SMH_BACKWARD_RN_ONLY 0x200 /* OR into smh_backward's engine: only reduce the row sums (loss without gradient) */
 #define SMH_UNIT_NEG_WEIGHTS 0x400 /* OR into smh_forward/backward's engine and smh_finalize's flags: W_ij == 1 (the reference's
                                     * vanila_pos_weights_contrastive_loss / vanila_contrastive_loss; smh_mpjpe can be skipped) */
@@ -72,6 +75,7 @@ typedef struct smh_layout {
     int64_t off_stats;           /* smh_stats_t */
     int64_t off_zt;              /* [Tp*128][128] fp32, tf32-rounded z, pre-swizzled 64-row blocks */
     int64_t off_zb;              /* [Tp*128][128] bf16 copy of z, pre-swizzled 64-row blocks (backward value operand) */
+    int64_t off_zh;              /* [Tp*128][128] fp16 copy of z, same block layout as zb (forward logit operand, fp16 engine) */
     int64_t off_jp;              /* [Tp*128][44] fp32 packed joints */
     int64_t off_posd;            /* [N] fp32 positive-pair MPJPE */
     int64_t off_neg;             /* [Tp*128] fp32 off-diagonal row sums (partial until all-reduced) */

@@ -13,7 +13,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsimhand_b200.so")
 ENGINE_TC_TF32 = 0
 ENGINE_FP32 = 1
 ENGINE_TC_BF16 = 2
-ENGINES = {"tf32": ENGINE_TC_TF32, "tc": ENGINE_TC_TF32, "fp32": ENGINE_FP32, "bf16": ENGINE_TC_BF16}
+ENGINE_TC_FP16 = 3
+ENGINES = {"tf32": ENGINE_TC_TF32, "tc": ENGINE_TC_TF32, "fp32": ENGINE_FP32, "bf16": ENGINE_TC_BF16,
+           "fp16": ENGINE_TC_FP16}
 
 PREP_NO_ZERO = 0x100
 BACKWARD_RN_ONLY = 0x200
@@ -30,7 +32,8 @@ class Dims(ctypes.Structure):
 
 class Layout(ctypes.Structure):
     _fields_ = [("ws_bytes", ctypes.c_int64), ("plan_bytes", ctypes.c_int64), ("off_stats", ctypes.c_int64),
-                ("off_zt", ctypes.c_int64), ("off_zb", ctypes.c_int64), ("off_jp", ctypes.c_int64), ("off_posd", ctypes.c_int64),
+                ("off_zt", ctypes.c_int64), ("off_zb", ctypes.c_int64), ("off_zh", ctypes.c_int64),
+                ("off_jp", ctypes.c_int64), ("off_posd", ctypes.c_int64),
                 ("off_neg", ctypes.c_int64), ("off_rn", ctypes.c_int64), ("off_rowloss", ctypes.c_int64),
                 ("off_dzacc", ctypes.c_int64), ("off_negparts", ctypes.c_int64), ("off_dzparts", ctypes.c_int64),
                 ("off_dist", ctypes.c_int64),

@@ -171,6 +171,7 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     lay->off_posd = take((int64_t)dims.n * 4);
     lay->off_zt = take(mp * kD * 4);
     lay->off_zb = take(mp * kD * 2);
+    lay->off_zh = take(mp * kD * 2);
     lay->off_jp = take(mp * kJP * 4);
     // partial buffers of the peer exchange (unused, and not allocated, on a single rank)
     lay->off_negparts = take(dims.world > 1 ? (int64_t)dims.world * mp * 4 : 0);
@@ -193,6 +194,7 @@ static WsView carve(void *ws, const smh_layout_t &lay)
     v.stats = b + lay.off_stats;
     v.zt = (float *)(b + lay.off_zt);
     v.zb = (uint16_t *)(b + lay.off_zb);
+    v.zh = (uint16_t *)(b + lay.off_zh);
     v.jp = (float *)(b + lay.off_jp);
     v.posd = (float *)(b + lay.off_posd);
     v.neg = (float *)(b + lay.off_neg);
@@ -346,7 +348,8 @@ int smh_prep(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, int e
     if ((rc = check_inputs(*dims, in))) return rc;
     const bool zero = !(engine & SMH_PREP_NO_ZERO);
     engine &= ~SMH_PREP_NO_ZERO;
-    if (engine != SMH_ENGINE_TC_TF32 && engine != SMH_ENGINE_FP32 && engine != SMH_ENGINE_TC_BF16)
+    if (engine != SMH_ENGINE_TC_TF32 && engine != SMH_ENGINE_FP32 && engine != SMH_ENGINE_TC_BF16 &&
+        engine != SMH_ENGINE_TC_FP16)
         return set_error(SMH_E_MODE, "unknown engine %d", engine);
     if (zero) {
         cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)(lay.off_posd - lay.off_stats), st);
@@ -384,8 +387,9 @@ int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, floa
     if ((rc = make_peers(*dims, lay, ws_dev, nullptr, &peers))) return rc;
     const bool unit_w = (engine & SMH_UNIT_NEG_WEIGHTS) != 0;
     engine &= 0xff;
-    if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
-        return launch_sweep_tc(false, engine == SMH_ENGINE_TC_BF16, unit_w, *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16 || engine == SMH_ENGINE_TC_FP16)
+        return launch_sweep_tc(false, engine == SMH_ENGINE_TC_TF32 ? 0 : (engine == SMH_ENGINE_TC_BF16 ? 1 : 2), unit_w,
+                               *dims, lay, pv, ws, peers, temperature, st);
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, unit_w, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
@@ -403,8 +407,8 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
     if (engine & SMH_BACKWARD_RN_ONLY) return 0;
     const bool unit_w = (engine & SMH_UNIT_NEG_WEIGHTS) != 0;
     engine &= 0xff;
-    if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16)
-        return launch_sweep_tc(true, true, unit_w, *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16 || engine == SMH_ENGINE_TC_FP16)
+        return launch_sweep_tc(true, 1, unit_w, *dims, lay, pv, ws, peers, temperature, st);
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, unit_w, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }

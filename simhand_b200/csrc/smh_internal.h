@@ -13,6 +13,7 @@ struct WsView {                 // device pointers carved out of the caller's wo
     void *stats;                // Stats
     float *zt;
     uint16_t *zb;
+    uint16_t *zh;
     float *jp;
     float *posd;
     float *neg;
@@ -41,7 +42,7 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
                  const Peers &peers, cudaStream_t stream);
 int launch_sweep_fp32(bool backward, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
                       const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
-int launch_sweep_tc(bool backward, bool logits_bf16, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay,
+int launch_sweep_tc(bool backward, int logit_format /* 0 tf32, 1 bf16, 2 fp16 */, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay,
                     const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
 int launch_push_inputs(const smh_exchange_t &exch, const smh_inputs_t &in, int n_local, int d, cudaStream_t stream);
 int launch_barrier(const smh_exchange_t &exch, cudaStream_t stream);

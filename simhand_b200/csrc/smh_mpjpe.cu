@@ -10,8 +10,6 @@
 //
 // CUDA-core kernel: per ordered pair 21 MUFU.RSQ and ~190 FMA-pipe lane-operations; the packed
 // FADD2/FMUL2/FFMA2 forms halve the issue slots.  This is the kernel the roofline in bench.py is quoted on.
-#include <cstdlib>
-
 #include "smh_common.cuh"
 #include "smh_internal.h"
 
@@ -64,13 +62,14 @@ __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10
 }
 
 // MODE as in joint_pair.  vmax_bits: running maximum of the integer image of D (D >= 0; NaN is larger than any finite).
-template <int MODE, int UN>
+// NCOLS: columns per thread (64: one CTA per stored tile; 32: one CTA per 64-column half).  col0: first column (inside
+// the tile) of this thread's run; cs holds the staged columns starting at tile column cs0.
+template <int MODE, int UN, int NCOLS>
 __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, float *__restrict__ tile_out, int I,
-                                                int J, int m, const float *cs, uint32_t &vmax_bits)
+                                                int J, int m, const float *cs, int cs0, int col0,
+                                                uint32_t &vmax_bits)
 {
-    const int t = threadIdx.x;
-    const int r = t & 127;
-    const int h = t >> 7;
+    const int r = threadIdx.x & 127;
     // this thread's row sample in registers
     f2 ax[10], ay[10];
     float ax20, ay20;
@@ -90,12 +89,12 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, fl
     const bool row_ok = (I * kTile + r) < m;
     const int col_limit = m - J * kTile;          // columns >= col_limit are padding
 #pragma unroll 1
-    for (int cq = 0; cq < 64 / UN; ++cq) {
-        const int c0 = h * 64 + cq * UN;
+    for (int cq = 0; cq < NCOLS / UN; ++cq) {
+        const int c0 = col0 + cq * UN;
         float dv[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-            dv[u] = mpjpe_one<MODE>(ax, ay, ax20, ay20, cs + (c0 + u) * kJP, div21);
+            dv[u] = mpjpe_one<MODE>(ax, ay, ax20, ay20, cs + (c0 - cs0 + u) * kJP, div21);
             if (row_ok && (c0 + u) < col_limit) vmax_bits = max(vmax_bits, __float_as_uint(dv[u]));
         }
 #pragma unroll
@@ -104,31 +103,38 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, fl
     }
 }
 
-template <int UN, int OCC>
-__global__ void __launch_bounds__(256, OCC)
+// HALF = false: one CTA per stored tile (thread = row x 64 columns).  HALF = true: one CTA per 64-column half of a
+// stored tile (thread = row x 32 columns) -- twice as many, half as long CTAs, used when a rank has few tiles (sharded
+// runs) so that the last wave of the 2-CTAs-per-SM grid is not mostly empty (1032 tiles = 3.5 waves -> 7.0 waves).
+template <bool HALF>
+__global__ void __launch_bounds__(256, 2)
 mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float *__restrict__ dist, int m,
              Stats *__restrict__ stats, Peers peers)
 {
-    __shared__ __align__(16) float cs[kTile * kJP];
+    constexpr int kCols = HALF ? 64 : 128;            // columns staged per CTA
+    constexpr int kPerThread = kCols / 2;
+    __shared__ __align__(16) float cs[kCols * kJP];
     __shared__ uint32_t wmax[8];
-    const int2 ij = tiles[blockIdx.x];
-    float *tile_out = dist + (int64_t)blockIdx.x * kTileFloats;
-    // stage the 128 column samples (contiguous 128 x 44 floats)
+    const int tile_id = HALF ? (blockIdx.x >> 1) : blockIdx.x;
+    const int cs0 = HALF ? (blockIdx.x & 1) * 64 : 0;
+    const int col0 = cs0 + (threadIdx.x >> 7) * kPerThread;
+    const int2 ij = tiles[tile_id];
+    float *tile_out = dist + (int64_t)tile_id * kTileFloats;
     {
-        const float4 *src = reinterpret_cast<const float4 *>(jp + (int64_t)ij.y * kTile * kJP);
+        const float4 *src = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.y * kTile + cs0) * kJP);
         float4 *dst = reinterpret_cast<float4 *>(cs);
-        for (int i = threadIdx.x; i < kTile * kJP / 4; i += 256) dst[i] = src[i];
+        for (int i = threadIdx.x; i < kCols * kJP / 4; i += 256) dst[i] = src[i];
     }
     __syncthreads();
     const uint32_t flags = stats->flags;
     const bool slow = flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE);
     uint32_t vmax_bits = 0u;
     if (slow)
-        mpjpe_tile_body<0, 4>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
+        mpjpe_tile_body<0, 4, kPerThread>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits);
     else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
-        mpjpe_tile_body<1, 4>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);     // zero distances: diagonal, zero padding
+        mpjpe_tile_body<1, 4, kPerThread>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits);   // zero distances
     else
-        mpjpe_tile_body<2, UN>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
+        mpjpe_tile_body<2, 4, kPerThread>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits);
     auto block_max = [&](uint32_t v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -142,9 +148,9 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float
     };
     uint32_t bmax = block_max(vmax_bits);
     if (!slow && bmax > 0x7f800000u) {
-        // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo the tile guarded
+        // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo it guarded
         vmax_bits = 0u;
-        mpjpe_tile_body<1, 4>(jp, tile_out, ij.x, ij.y, m, cs, vmax_bits);
+        mpjpe_tile_body<1, 4, kPerThread>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits);
         bmax = block_max(vmax_bits);
     }
     if (threadIdx.x == 0) {
@@ -172,16 +178,12 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
 {
     (void)dims;
     if (lay.n_stored_tiles == 0) return 0;
-    static const int variant = getenv("SMH_MPJPE_VARIANT") ? atoi(getenv("SMH_MPJPE_VARIANT")) : 0;   // tuning knob
-    const int grid = lay.n_stored_tiles;
     Stats *st = (Stats *)ws.stats;
-    switch (variant) {
-        case 1: mpjpe_kernel<8, 2><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
-        case 2: mpjpe_kernel<8, 1><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
-        case 3: mpjpe_kernel<4, 1><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
-        case 4: mpjpe_kernel<16, 1><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
-        default: mpjpe_kernel<4, 2><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers); break;
-    }
+    // fewer than ~8 waves of whole tiles (2 CTAs x 148 SMs per wave): cut the tiles in halves
+    if (lay.n_stored_tiles < 8 * 2 * kNumCtas)
+        mpjpe_kernel<true><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
+    else
+        mpjpe_kernel<false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
     return check_launch("mpjpe_kernel");
 }
 

@@ -6,6 +6,7 @@
 //   zt  : z rounded to tf32 (round-to-nearest) in the pre-swizzled 64-row block layout the sweeps stage
 //         with one linear bulk copy (smh_common.cuh: zt_index)
 //   zb  : bf16 copy of z in the pre-swizzled block layout the backward sweep reads MN-major (zb_index)
+//   zh  : fp16 copy of z, same layout (forward logit operand of the fp16 engine)
 //   jp  : joints packed as 10 x (x_k, x_k+1, y_k, y_k+1) + (x_20, y_20, 0, 0) per sample
 //   posd: D_{k,k+N}, with the exact operation order of the all-pairs kernel, so posd[k] is bitwise
 //         D[k, k+N]
@@ -23,6 +24,7 @@ __device__ __forceinline__ const float *sample_ptr(const float *base, int k, int
 
 __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d, int mp, bool round_tf32,
                                                    float *__restrict__ zt, uint16_t *__restrict__ zb,
+                                                   uint16_t *__restrict__ zh,
                                                    float *__restrict__ jp, float *__restrict__ posd,
                                                    Stats *__restrict__ stats)
 {
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
         *reinterpret_cast<float4 *>(zt + zt_index(row, 4 * lane)) = zv;
         // bf16 copy (value operand of dz += G z): 4 consecutive columns = 8 bytes inside one 16-byte chunk
         *reinterpret_cast<uint2 *>(zb + zb_index(row, 4 * lane)) = make_uint2(pack_bf16x2(zv.x, zv.y), pack_bf16x2(zv.z, zv.w));
+        // fp16 copy, same layout: 11-bit significand = the precision of tf32 for |z| <= 1 (forward logit operand)
+        *reinterpret_cast<uint2 *>(zh + zb_index(row, 4 * lane)) = make_uint2(pack_f16x2(zv.x, zv.y), pack_f16x2(zv.z, zv.w));
 
         // packed joints
         float *jrow = jp + (int64_t)row * kJP;
@@ -130,7 +134,7 @@ int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_input
 {
     const int mp = lay.tiles_per_side * kTile;
     const int blocks = (mp + 7) / 8;
-    prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, ws.zt, ws.zb, ws.jp, ws.posd, (Stats *)ws.stats);
+    prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, ws.zt, ws.zb, ws.zh, ws.jp, ws.posd, (Stats *)ws.stats);
     return check_launch("prep_kernel");
 }
 

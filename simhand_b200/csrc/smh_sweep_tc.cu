@@ -107,13 +107,15 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned
     }
 }
 
-// BWD: backward sweep (always reads the bf16 image).  SBF16: logits from the bf16 image (else tf32 image).
+// BWD: backward sweep (always reads the bf16 image).  SBF16: logits from a 16-bit image `zb` (bf16, or fp16 in the
+// forward sweep of the fp16 engine: the caller passes that image and the matching instruction descriptor idesc1),
+// else from the tf32 image `zt`.
 template <bool BWD, bool SBF16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
                 const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
-                float k2, bool unit_w)
+                float k2, bool unit_w, uint32_t idesc1)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
     using Cfg = TcCfg<SBF16>;
@@ -238,7 +240,6 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            constexpr uint32_t idesc1 = SBF16 ? umma_idesc_bf16(kTile, kTaskN, 0, 0) : umma_idesc_tf32(kTile, kTaskN, 0, 0);
             constexpr uint32_t idesc2 = umma_idesc_bf16(kTile, kD, 0, 1);
             const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
             uint32_t a_ph = 0, dz_ph = 0;
@@ -424,8 +425,9 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
 }
 
 template <bool BWD, bool SBF16>
-static int launch_one(bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
-                      const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream)
+static int launch_one(bool unit_w, const uint16_t *half_image, uint32_t idesc1, const smh_dims_t &dims,
+                      const smh_layout_t &lay, const PlanView &plan, const WsView &ws, const Peers &peers,
+                      float temperature, cudaStream_t stream)
 {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -437,19 +439,24 @@ static int launch_one(bool unit_w, const smh_dims_t &dims, const smh_layout_t &l
     constexpr int smem = TcCfg<SBF16>::kSmem;
     cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-    sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, ws.zb,
+    sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
                                                                    ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
-                                                                   dims.n, n_local, k2, unit_w);
+                                                                   dims.n, n_local, k2, unit_w, idesc1);
     return check_launch("sweep_tc_kernel");
 }
 
-int launch_sweep_tc(bool backward, bool logits_bf16, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay,
+int launch_sweep_tc(bool backward, int logit_format, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay,
                     const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream)
 {
     if (lay.n_strips == 0) return 0;
-    if (backward) return launch_one<true, true>(unit_w, dims, lay, plan, ws, peers, temperature, stream);
-    if (logits_bf16) return launch_one<false, true>(unit_w, dims, lay, plan, ws, peers, temperature, stream);
-    return launch_one<false, false>(unit_w, dims, lay, plan, ws, peers, temperature, stream);
+    const uint32_t id_bf16 = umma_idesc_bf16(kTile, kTaskN, 0, 0), id_f16 = umma_idesc_f16(kTile, kTaskN, 0, 0),
+                   id_tf32 = umma_idesc_tf32(kTile, kTaskN, 0, 0);
+    if (backward) return launch_one<true, true>(unit_w, ws.zb, id_bf16, dims, lay, plan, ws, peers, temperature, stream);
+    if (logit_format == 1)
+        return launch_one<false, true>(unit_w, ws.zb, id_bf16, dims, lay, plan, ws, peers, temperature, stream);
+    if (logit_format == 2)
+        return launch_one<false, true>(unit_w, ws.zh, id_f16, dims, lay, plan, ws, peers, temperature, stream);
+    return launch_one<false, false>(unit_w, ws.zb, id_tf32, dims, lay, plan, ws, peers, temperature, stream);
 }
 
 }  // namespace smh

@@ -30,11 +30,13 @@ _AUTO_FP32_MAX_M = 256     # below this many samples the exact-fp32 engine is us
 
 
 def resolve_engine(engine: str, n: int) -> str:
-    """'auto' -> 'fp32' for tiny batches (2N <= 256), else 'tf32' (tcgen05)."""
+    """'auto' -> 'fp32' for tiny batches (2N <= 256), else 'fp16' (tcgen05; fp16 logit operands carry the same 11-bit
+    significand as tf32 for L2-normalised z and measure bit-identical losses to the tf32 engine at half the staging
+    traffic)."""
     if engine == "auto":
-        return "fp32" if 2 * n <= _AUTO_FP32_MAX_M else "tf32"
+        return "fp32" if 2 * n <= _AUTO_FP32_MAX_M else "fp16"
     if engine not in _lib.ENGINES:
-        raise ValueError(f"unknown engine {engine!r}; choose from auto, tf32, fp32")
+        raise ValueError(f"unknown engine {engine!r}; choose from auto, fp16, tf32, bf16, fp32")
     return engine
 _ctx_lock = threading.Lock()
 _ctx_cache = {}

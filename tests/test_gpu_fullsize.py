@@ -119,7 +119,7 @@ def test_weight_tile_checksum_against_oracle(batch, host_minmax):
         assert R.ulp_distance(got[k], want).max() == 0
 
 
-@pytest.mark.parametrize("engine", ["tf32", "bf16"])
+@pytest.mark.parametrize("engine", ["tf32", "bf16", "fp16"])
 def test_back_to_back_steps_are_stable(batch, engine):
     """300 steps issued back to back (no host sync in between): no pipeline timeout, no device fault and the same
     loss bits every time.  Guards the mbarrier protocol of the sweeps (a parity wait shared by two consumer groups

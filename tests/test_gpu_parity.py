@@ -52,10 +52,10 @@ def test_weights_match_reference_bitwise(golden):
     assert R.ulp_distance(neg_w.cpu().numpy(), golden["neg_w"]).max() == 0
 
 
-@pytest.mark.parametrize("engine", ["fp32", "tf32", "auto", "bf16"])
+@pytest.mark.parametrize("engine", ["fp32", "tf32", "auto", "bf16", "fp16"])
 def test_step_matches_reference(golden, engine):
     z1, z2, a, b = _to_dev(golden)
-    if engine == "tf32" and z1.shape[0] < 8:
+    if engine in ("tf32", "fp16") and z1.shape[0] < 8:
         pytest.skip("tf32 logits over < 16 samples do not average to 1e-5; 'auto' picks the fp32 engine there")
     loss_rtol = 1e-3 if engine == "bf16" else LOSS_RTOL          # BASELINE.json: bf16 mode within 1e-3
     loss, dz1, dz2, aux = ops.run_step(z1, z2, a, b, 0.5, engine, True, return_aux=True)
@@ -72,7 +72,7 @@ def test_step_matches_reference(golden, engine):
     _, _, _, neg = R.closed_form_fp64(torch.from_numpy(golden["z1"]), torch.from_numpy(golden["z2"]),
                                       torch.from_numpy(golden["pos_w"]), torch.from_numpy(golden["neg_w"]))
     rel = (aux["neg"].cpu().double() - neg).abs() / neg
-    assert rel.max() < {"fp32": 2e-6, "tf32": 2e-4, "bf16": 4e-3}[ops.resolve_engine(engine, z1.shape[0])]
+    assert rel.max() < {"fp32": 2e-6, "tf32": 2e-4, "fp16": 2e-4, "bf16": 4e-3}[ops.resolve_engine(engine, z1.shape[0])]
 
 
 def test_drop_in_api_and_autograd(golden):
@@ -102,7 +102,7 @@ def test_step_matches_c_oracle_mid_size(n, jset):
     a, b = j1[:, :, :2], j2[:, :, :2]
     ref = R.c_step(z1, z2, a, b)
     dev = _dev()
-    for engine in ("tf32", "fp32", "bf16"):
+    for engine in ("tf32", "fp32", "bf16", "fp16"):
         loss, dz1, dz2, aux = ops.run_step(z1.to(dev), z2.to(dev), j1.to(dev)[:, :, :2], j2.to(dev)[:, :, :2],
                                            0.5, engine, True, return_aux=True)
         assert aux["stats"].cpu().numpy()[6] == 0

@@ -26,7 +26,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.Dims) == 20
     assert ctypes.sizeof(_lib.Stats) == 32
     assert ctypes.sizeof(_lib.Exchange) == 8 + 3 * 8 * 8
-    assert ctypes.sizeof(_lib.Layout) == 14 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.Layout) == 15 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.Inputs) == 88
 
 

@@ -192,7 +192,7 @@ def main():
             rc |= p.returncode
         sys.exit(1 if rc else 0)
     fn = {"selftest": stage_selftest, "weights": stage_weights, "fp32": lambda: stage_engine("fp32"),
-          "probe": stage_probe, "tc": lambda: stage_engine("tf32"), "bf16": lambda: stage_engine("bf16"),
+          "probe": stage_probe, "tc": lambda: stage_engine("tf32"), "bf16": lambda: stage_engine("bf16"), "fp16": lambda: stage_engine("fp16"),
           "big": stage_big}[what]
     fn()
 
