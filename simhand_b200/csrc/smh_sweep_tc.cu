@@ -60,49 +60,93 @@ struct TcBars {
 };
 static_assert(sizeof(TcBars) <= kNumBars * 8, "barrier block too small");
 
-// the 32 columns [half * 32, half * 32 + 32) of one task for one row.  v[] holds S on entry and (backward) G on exit.
-template <bool BWD, bool TRANSPOSED, bool MASKED>
-__device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], const unsigned char *dstage, int r, int chunk,
-                                               int gi, int gj0, int m, bool diagonal, float dmax,
-                                               const DivConst &divw, float k2, float rni,
-                                               const float *__restrict__ rn, float (&rowsum)[4], bool unit_w)
+// Shared-memory reads of the staged MPJPE tile by 32-bit shared address (the generic-pointer form costs an address
+// translation per load).
+__device__ __forceinline__ void lds_f2x2(uint32_t addr, f2 &a, f2 &b)
 {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// The 32 columns [chunk * 32, chunk * 32 + 32) of one task for one row; v[] holds S on entry.
+//   forward : rowsum += E,  E = 2^(S * wk),  wk = W * k2 = k2 - D * (k2 / Dmax)      (one FFMA per weight)
+//   backward: pk[] = bf16x2 of G' = wk * E * (1/neg_i + 1/neg_j) = k2 * G; the strip flush multiplies by 1 / k2
+// The tensor-core engines do not need the correctly rounded W of the fp32 engine (the logits carry 2^-11 operand
+// rounding): the fused form is within 1 ulp of k2 in absolute terms.  Packed f32x2 arithmetic throughout.
+// negc2 = (-k2 / Dmax) x2 (zero for unit weights), k2c2 = k2 x2.
+template <bool BWD, bool TRANSPOSED, bool MASKED>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], uint32_t dstage_s, int r,
+                                               int chunk, int gi, int gj0, int m, bool diagonal, f2 negc2, f2 k2c2,
+                                               float rni, const float *__restrict__ rn, f2 (&rowsum)[2])
+{
+    uint32_t ta[8];                                   // transposed reads: one address per (row & 7) XOR pattern
+    uint32_t dbase = 0, rx = 0;
+    if (TRANSPOSED) {
+        const uint32_t c4 = (uint32_t)r >> 2, x = c4 & 7u;
+        const uint32_t base = dstage_s + c4 * 1024u + ((uint32_t)r & 3u) * 4u + (uint32_t)chunk * 512u;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) ta[k] = base + ((k ^ x) << 4);
+    } else {
+        dbase = dstage_s + ((uint32_t)r >> 6) * 16384u + (uint32_t)chunk * 8192u;
+        rx = ((uint32_t)r & 63u) << 4;
+    }
+    const f2 rni2 = pack2(rni, rni);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int jl = chunk * 32 + q * 4;                       // first of 4 columns inside the task
-        float dv[4];
+        f2 d01, d23;
         if (!TRANSPOSED) {
-            const int c4l = jl >> 2;                              // == (global c4) mod 16; its low 3 bits drive the XOR
-            const float4 t4 = *reinterpret_cast<const float4 *>(dstage + ((r >> 6) * 16 + c4l) * 1024 +
-                                                                ((r & 63) ^ (c4l & 7)) * 16);
-            dv[0] = t4.x; dv[1] = t4.y; dv[2] = t4.z; dv[3] = t4.w;
+            // column group c4 = chunk * 8 + q of the staged half: its low 3 bits (q) drive the XOR
+            lds_f2x2(dbase + (uint32_t)q * 1024u + (rx ^ ((uint32_t)q << 4)), d01, d23);
         } else {
-            const int c4 = r >> 2;
-            const unsigned char *base = dstage + c4 * 1024 + (r & 3) * 4;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) dv[u] = *reinterpret_cast<const float *>(base + ((jl + u) ^ (c4 & 7)) * 16);
+            const uint32_t off = (uint32_t)(q >> 1) * 128u;      // stored rows jl .. jl + 3: bits 3.. of the row index
+            const int k0 = (q & 1) * 4;
+            d01 = pack2(lds_f32(ta[k0] + off), lds_f32(ta[k0 + 1] + off));
+            d23 = pack2(lds_f32(ta[k0 + 2] + off), lds_f32(ta[k0 + 3] + off));
         }
-        float4 rnj = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (BWD) rnj = __ldg(reinterpret_cast<const float4 *>(rn + gj0 + jl));
-        const float rnjv[4] = {rnj.x, rnj.y, rnj.z, rnj.w};
+        f2 rs01 = 0, rs23 = 0;
+        if (BWD) {
+            const float4 rnj = __ldg(reinterpret_cast<const float4 *>(rn + gj0 + jl));
+            rs01 = add2(rni2, pack2(rnj.x, rnj.y));
+            rs23 = add2(rni2, pack2(rnj.z, rnj.w));
+        }
+        const f2 wk01 = fma2(d01, negc2, k2c2), wk23 = fma2(d23, negc2, k2c2);
+        const f2 a01 = mul2(pack2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), wk01);
+        const f2 a23 = mul2(pack2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), wk23);
+        float a[4], e[4];
+        unpack2(a01, a[0], a[1]);
+        unpack2(a23, a[2], a[3]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int c = q * 4 + u;
-            const float s = __uint_as_float(v[c]);
-            const float w = unit_w ? 1.0f : div_fast(__fsub_rn(dmax, dv[u]), divw);   // unit_w: unweighted negatives
-            float e = ex2_approx(s * (w * k2));
-            float g = BWD ? w * e * (rni + rnjv[u]) : 0.f;
-            if (MASKED) {
+        for (int u = 0; u < 4; ++u) e[u] = ex2_approx(a[u]);
+        bool valid[4];
+        if (MASKED) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
                 const int gj = gj0 + jl + u;
-                const bool valid = (gi < m) && (gj < m) && !(diagonal && gi == gj);
-                e = valid ? e : 0.f;
-                g = valid ? g : 0.f;
+                valid[u] = (gi < m) && (gj < m) && !(diagonal && gi == gj);
+                e[u] = valid[u] ? e[u] : 0.f;
             }
-            if (!BWD) {
-                rowsum[u] += e;
-            } else {
-                v[c] = __float_as_uint(g);
+        }
+        if (!BWD) {
+            rowsum[0] = add2(rowsum[0], pack2(e[0], e[1]));
+            rowsum[1] = add2(rowsum[1], pack2(e[2], e[3]));
+        } else {
+            const f2 g01 = mul2(mul2(wk01, pack2(e[0], e[1])), rs01);
+            const f2 g23 = mul2(mul2(wk23, pack2(e[2], e[3])), rs23);
+            float g[4];
+            unpack2(g01, g[0], g[1]);
+            unpack2(g23, g[2], g[3]);
+            if (MASKED) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) g[u] = valid[u] ? g[u] : 0.f;     // also drops NaN from padded distances
             }
+            pk[2 * q] = pack_bf16x2(g[0], g[1]);
+            pk[2 * q + 1] = pack_bf16x2(g[2], g[3]);
         }
     }
 }
@@ -115,7 +159,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
                 const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
-                float k2, bool unit_w, uint32_t idesc1)
+                float k2, float inv_k2, bool unit_w, uint32_t idesc1)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
     using Cfg = TcCfg<SBF16>;
@@ -243,18 +287,44 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             constexpr uint32_t idesc2 = umma_idesc_bf16(kTile, kD, 0, 1);
             const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
             uint32_t a_ph = 0, dz_ph = 0;
-            uint32_t seq = 0;                       // tasks issued so far by this CTA
+            uint32_t seq = 0;                       // logit MMAs issued so far by this CTA
             uint32_t done2 = 0;                     // value MMAs issued so far (backward)
             uint32_t first_mask = 0, last_mask = 0; // per pending task (bit = seq % 32): first / last of its strip
-            // value contraction of task q (the q-th task of this CTA): dz (+)= G_q z_J
+            // logit contraction of task `seq` into S buffer seq % kSBufs (operands and buffer are known to be ready)
+            auto mma1 = [&](bool last_of_strip) {
+                const uint32_t sb = seq % kSBufs, bst = seq % kBStages;
+                tc_fence_after();
+                if (SBF16) {
+                    // K-major 16-bit: 64 columns (128 B) per box, 16 columns (32 B) per K step
+#pragma unroll
+                    for (int db = 0; db < 2; ++db) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t adesc = umma_desc_sw128(sA_u + db * 16384 + ks * 32, 16, 1024);
+                            const uint64_t bdesc = umma_desc_sw128(sB_u + bst * kBBytes + db * 8192 + ks * 32, 16, 1024);
+                            tc_mma_ss_f16(tmem_base + sb * kTaskN, adesc, bdesc, idesc1, (db | ks) ? 1u : 0u);
+                        }
+                    }
+                } else {
+                    // K-major tf32: 32 columns (128 B) per box, 8 columns (32 B) per K step
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t adesc = umma_desc_sw128(sA_u + kb * 16384 + ks * 32, 16, 1024);
+                            const uint64_t bdesc = umma_desc_sw128(sB_u + bst * kBBytes + kb * 8192 + ks * 32, 16, 1024);
+                            tc_mma_ss_tf32(tmem_base + sb * kTaskN, adesc, bdesc, idesc1, (kb | ks) ? 1u : 0u);
+                        }
+                    }
+                }
+                tc_commit(&bars->sg_full[sb]);
+                if (!BWD) tc_commit(&bars->empty_b[bst]);
+                if (last_of_strip) tc_commit(&bars->a_empty);           // every logit MMA of the strip has read sA
+            };
+            // value contraction of task q (the q-th task of this CTA): dz (+)= G_q z_J  (G and the accumulator are ready)
             auto mma2 = [&](uint32_t q) {
                 const uint32_t sbq = q % kSBufs, bstq = q % kBStages;
                 const bool first = (first_mask >> (q & 31)) & 1u, last = (last_mask >> (q & 31)) & 1u;
-                mbar_wait(&bars->g_ready[sbq], (q / kSBufs) & 1u, fail, 4);
-                if (first) {
-                    mbar_wait(&bars->dz_empty, dz_ph ^ 1u, fail, 5);
-                    dz_ph ^= 1u;
-                }
                 tc_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < kTaskN / 16; ++ks) {
@@ -270,52 +340,74 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 tc_commit(&bars->empty_b[bstq]);
                 if (last) tc_commit(&bars->dz_full);
             };
-            for (int s = s_begin; s < s_end; ++s) {
-                const int2 strip = strips[s];
-                mbar_wait(&bars->a_full, a_ph, fail, 6);
-                a_ph ^= 1u;
-                for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
-                    const uint32_t sb = seq % kSBufs, bst = seq % kBStages;
-                    mbar_wait(&bars->full_b[bst], (seq / kBStages) & 1u, fail, 7);
-                    mbar_wait(&bars->sg_empty[sb], ((seq / kSBufs) & 1u) ^ 1u, fail, 8);
-                    tc_fence_after();
-                    if (SBF16) {
-                        // K-major bf16: 64 columns (128 B) per box, 16 columns (32 B) per K step
-#pragma unroll
-                        for (int db = 0; db < 2; ++db) {
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t adesc = umma_desc_sw128(sA_u + db * 16384 + ks * 32, 16, 1024);
-                                const uint64_t bdesc = umma_desc_sw128(sB_u + bst * kBBytes + db * 8192 + ks * 32, 16, 1024);
-                                tc_mma_ss_f16(tmem_base + sb * kTaskN, adesc, bdesc, idesc1, (db | ks) ? 1u : 0u);
-                            }
-                        }
-                    } else {
-                        // K-major tf32: 32 columns (128 B) per box, 8 columns (32 B) per K step
-#pragma unroll
-                        for (int kb = 0; kb < 4; ++kb) {
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t adesc = umma_desc_sw128(sA_u + kb * 16384 + ks * 32, 16, 1024);
-                                const uint64_t bdesc = umma_desc_sw128(sB_u + bst * kBBytes + kb * 8192 + ks * 32, 16, 1024);
-                                tc_mma_ss_tf32(tmem_base + sb * kTaskN, adesc, bdesc, idesc1, (kb | ks) ? 1u : 0u);
-                            }
+            if (!BWD) {
+                for (int s = s_begin; s < s_end; ++s) {
+                    const int2 strip = strips[s];
+                    mbar_wait(&bars->a_full, a_ph, fail, 6);
+                    a_ph ^= 1u;
+                    for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
+                        mbar_wait(&bars->full_b[seq % kBStages], (seq / kBStages) & 1u, fail, 7);
+                        mbar_wait(&bars->sg_empty[seq % kSBufs], ((seq / kSBufs) & 1u) ^ 1u, fail, 8);
+                        mma1(ti + 1 == strip.y);
+                    }
+                }
+            } else if (s_begin < s_end) {
+                // Event-driven issue: the logit MMA of task t + k only needs its operands and a free S buffer, the
+                // value MMA of task t only needs G_t from the epilogue.  Issuing them in a fixed interleave makes the
+                // logit MMAs queue behind the epilogue of an older task; polling both conditions keeps up to kSBufs
+                // logit tiles ahead of the epilogue groups.
+                const uint32_t total = (uint32_t)(strips[s_end - 1].y - strips[s_begin].x);
+                int s1 = s_begin;                                // strip of the next logit MMA
+                int2 strip1 = strips[s1];
+                int ti1 = strip1.x;
+                bool a_ok = false;
+                uint32_t idle = 0;
+                const long long t0 = clock64();
+                while (done2 < total) {
+                    bool progress = false;
+                    // value MMA first: it frees an S buffer and a z block
+                    if (done2 < seq && mbar_test_wait(&bars->g_ready[done2 % kSBufs], (done2 / kSBufs) & 1u)) {
+                        const bool first = (first_mask >> (done2 & 31)) & 1u;
+                        if (!first || mbar_test_wait(&bars->dz_empty, dz_ph ^ 1u)) {
+                            if (first) dz_ph ^= 1u;
+                            mma2(done2++);
+                            progress = true;
                         }
                     }
-                    tc_commit(&bars->sg_full[sb]);
-                    if (!BWD) tc_commit(&bars->empty_b[bst]);
-                    if (ti + 1 == strip.y) tc_commit(&bars->a_empty);     // every MMA1 of the strip has read sA
-                    if (BWD) {
-                        const uint32_t bit = 1u << (seq & 31);
-                        first_mask = (ti == strip.x) ? (first_mask | bit) : (first_mask & ~bit);
-                        last_mask = (ti + 1 == strip.y) ? (last_mask | bit) : (last_mask & ~bit);
-                        // keep the logit MMAs two tasks ahead of the value MMAs: both epilogue groups stay fed
-                        if (seq >= 2) mma2(done2++);
+                    if (seq < total && seq - done2 < (uint32_t)kSBufs) {
+                        if (!a_ok && mbar_test_wait(&bars->a_full, a_ph)) {
+                            a_ok = true;
+                            a_ph ^= 1u;
+                        }
+                        if (a_ok && mbar_test_wait(&bars->full_b[seq % kBStages], (seq / kBStages) & 1u) &&
+                            mbar_test_wait(&bars->sg_empty[seq % kSBufs], ((seq / kSBufs) & 1u) ^ 1u)) {
+                            const uint32_t bit = 1u << (seq & 31);
+                            const bool last1 = ti1 + 1 == strip1.y;
+                            first_mask = (ti1 == strip1.x) ? (first_mask | bit) : (first_mask & ~bit);
+                            last_mask = last1 ? (last_mask | bit) : (last_mask & ~bit);
+                            mma1(last1);
+                            ++seq;
+                            if (last1) {
+                                a_ok = false;
+                                if (++s1 < s_end) {
+                                    strip1 = strips[s1];
+                                    ti1 = strip1.x;
+                                }
+                            } else {
+                                ++ti1;
+                            }
+                            progress = true;
+                        }
+                    }
+                    if (progress) {
+                        idle = 0;
+                    } else if ((++idle & 1023u) == 0u &&
+                               (clock64() - t0 > 4000000000ll || *(volatile uint32_t *)fail != 0u)) {
+                        atomicCAS(fail, 0u, 7u);
+                        break;
                     }
                 }
             }
-            if (BWD)
-                while (done2 < seq) mma2(done2++);
         }
     } else if (warp >= 2 && warp < 2 + kEpiWarps) {
         // ------------------------------------------------------------------ epilogue (warps 2..17)
@@ -326,9 +418,12 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         const int r = w4 * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16);
         const float dmax = __uint_as_float(stats->dmax_bits);
-        const DivConst divw = make_div(dmax);          // Dmax - Dmin, Dmin = +0
+        // wk = W * k2 = k2 - D * (k2 / Dmax)  (Dmin = +0, the diagonal); unit weights: wk = k2
+        const float negc = unit_w ? 0.f : -__fdiv_rn(k2, dmax);
+        const f2 negc2 = pack2(negc, negc), k2c2 = pack2(k2, k2);
+        const uint32_t sD_s = smem_u32(sD);
         uint32_t seq = 0, dz_ph = 0;
-        float rowsum[4] = {0.f, 0.f, 0.f, 0.f};
+        f2 rowsum[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
         for (int s = s_begin; s < s_end; ++s) {
             const int2 strip = strips[s];
             int row_block = -1;
@@ -352,27 +447,23 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 }
                 mbar_wait(&bars->sg_full[sb], (seq / kSBufs) & 1u, fail, 9);
                 tc_fence_after();
-                const unsigned char *dstage = sD + dst * kDBytes;
-                uint32_t v[32];
+                const uint32_t dstage = sD_s + dst * kDBytes;
+                uint32_t v[32], pk[16];
                 tc_ld32(lane_addr + sb * kTaskN + half * 32, v);
                 tc_wait_ld();
                 if (masked) {
                     if (transposed)
-                        epilogue_chunk<BWD, true, true>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum, unit_w);
+                        epilogue_chunk<BWD, true, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni, rn, rowsum);
                     else
-                        epilogue_chunk<BWD, false, true>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum, unit_w);
+                        epilogue_chunk<BWD, false, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni, rn, rowsum);
                 } else {
                     if (transposed)
-                        epilogue_chunk<BWD, true, false>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum, unit_w);
+                        epilogue_chunk<BWD, true, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni, rn, rowsum);
                     else
-                        epilogue_chunk<BWD, false, false>(v, dstage, r, half, gi, gj0, m, diagonal, dmax, divw, k2, rni, rn, rowsum, unit_w);
+                        epilogue_chunk<BWD, false, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni, rn, rowsum);
                 }
                 if (BWD) {
-                    // G as packed bf16x2 over the first half of this warp's own S columns
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        pk[c] = pack_bf16x2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+                    // G' as packed bf16x2 over the first half of this warp's own S columns
                     tc_st16(lane_addr + sb * kTaskN + half * 32, pk);
                     tc_wait_st();
                 }
@@ -389,10 +480,13 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             if (!BWD) {
                 // fused all-reduce(SUM): the row sums go into every rank's `neg` (peer pointers over NVLink)
                 if (row_ok) {
-                    const float part = (rowsum[0] + rowsum[1]) + (rowsum[2] + rowsum[3]);
+                    float r0, r1, r2, r3;
+                    unpack2(rowsum[0], r0, r1);
+                    unpack2(rowsum[1], r2, r3);
+                    const float part = (r0 + r1) + (r2 + r3);
                     for (int p = 0; p < peers.world; ++p) atomicAdd(peers.neg(p) + gi, part);
                 }
-                rowsum[0] = rowsum[1] = rowsum[2] = rowsum[3] = 0.f;
+                rowsum[0] = rowsum[1] = pack2(0.f, 0.f);
             } else {
                 // every epilogue warp drains 32 of the 128 gradient columns of its lane quadrant
                 mbar_wait(&bars->dz_full, dz_ph, fail, 11);
@@ -409,8 +503,9 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 if (ok2) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        red_add_v4(orow + chunk * 32 + q * 4, __uint_as_float(dv[4 * q]), __uint_as_float(dv[4 * q + 1]),
-                                   __uint_as_float(dv[4 * q + 2]), __uint_as_float(dv[4 * q + 3]));
+                        red_add_v4(orow + chunk * 32 + q * 4, inv_k2 * __uint_as_float(dv[4 * q]),
+                                   inv_k2 * __uint_as_float(dv[4 * q + 1]), inv_k2 * __uint_as_float(dv[4 * q + 2]),
+                                   inv_k2 * __uint_as_float(dv[4 * q + 3]));        // the accumulator holds k2 * dz
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -435,13 +530,14 @@ static int launch_one(bool unit_w, const uint16_t *half_image, uint32_t idesc1, 
     (void)sms;
     const int grid = kNumCtas;                      // the plan is cut for exactly this many CTAs
     const float k2 = 1.4426950408889634f / temperature;
+    const float inv_k2 = (float)(0.6931471805599453 * (double)temperature);
     const int n_local = dims.n / dims.world;
     constexpr int smem = TcCfg<SBF16>::kSmem;
     cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
     sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
                                                                    ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
-                                                                   dims.n, n_local, k2, unit_w, idesc1);
+                                                                   dims.n, n_local, k2, inv_k2, unit_w, idesc1);
     return check_launch("sweep_tc_kernel");
 }
 
