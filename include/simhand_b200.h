@@ -58,6 +58,15 @@ extern "C" {
                                     * vanila_pos_weights_contrastive_loss / vanila_contrastive_loss; smh_mpjpe can be skipped) */
 #define SMH_UNIT_POS_WEIGHTS 0x800 /* OR into smh_finalize's flags: Wp_k == 1 (vanila_neg_weights_contrastive_loss, vanila_contrastive_loss) */
 #define SMH_PREP_NO_ZERO 0x100   /* OR into smh_prep's engine: the accumulators were already zeroed by smh_prep_zero */
+#define SMH_DENSE_WEIGHTS 0x2000 /* OR into smh_forward/backward's engine and smh_finalize's flags: the weights are the
+                                  * materialised tensors handed to smh_import_weights (dims.flags has SMH_DIMS_DENSE_WEIGHTS) */
+
+/* smh_dims_t.flags */
+#define SMH_DIMS_DENSE_WEIGHTS 1  /* materialised-weights path (the reference's two-call API with real tensors,
+                                   * utils.py:391): every (I, J) tile is stored, nothing is assumed symmetric; world == 1 */
+#define SMH_DIMS_DENSE_BACKWARD 2 /* with SMH_DIMS_DENSE_WEIGHTS: the task list of the backward sweep, which visits every
+                                   * tile twice (W_ij for the row term, W_ji read transposed for the column term).  Same
+                                   * layout as the forward list: one workspace, two plans. */
 
 /* problem description shared by all calls */
 typedef struct smh_dims {
@@ -66,6 +75,7 @@ typedef struct smh_dims {
     int32_t world;               /* ranks sharing the batch (1 = single GPU) */
     int32_t rank;                /* this rank, 0..world-1 */
     int32_t strip_len;           /* sweep tasks per strip (<= 0: library default) */
+    int32_t flags;               /* SMH_DIMS_*; 0 = fused path (weights from the joints) */
 } smh_dims_t;
 
 /* byte offsets into the workspace blob (all 256-byte aligned) and table sizes */
@@ -154,6 +164,13 @@ int smh_plan_build(const smh_dims_t *dims, void *plan_host, int64_t plan_bytes);
 int smh_prep(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, int engine, void *stream);
 /* zeroes the accumulators only (peer exchange: must precede the barrier after which peers may add into them) */
 int smh_prep_zero(const smh_dims_t *dims, void *ws_dev, void *stream);
+
+/* Materialised-weights path (dims.flags & SMH_DIMS_DENSE_WEIGHTS; replaces smh_mpjpe): copies neg_w [M, M] (fp32, row
+ * stride neg_row_stride elements; any values, not assumed symmetric) into the tile layout the sweeps stage, and pos_w
+ * [N] into ws.posd.  Either pointer may be NULL (that operand then comes from the unit-weight flags).  smh_prep may be
+ * called with NULL joints on this path. */
+int smh_import_weights(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, const float *neg_w_dev,
+                       int64_t neg_row_stride, const float *pos_w_dev, void *stream);
 
 /* K0: all-pairs MPJPE tiles of this rank (upper triangle) + running max (utils.py:251-255). */
 int smh_mpjpe(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, const smh_exchange_t *exch, void *stream);

@@ -21,13 +21,16 @@ PREP_NO_ZERO = 0x100
 BACKWARD_RN_ONLY = 0x200
 UNIT_NEG_WEIGHTS = 0x400
 UNIT_POS_WEIGHTS = 0x800
+DENSE_WEIGHTS = 0x2000
+DIMS_DENSE_WEIGHTS = 1
+DIMS_DENSE_BACKWARD = 2
 FLAG_SLOW_DOMAIN = 1
 FLAG_NONFINITE = 2
 
 
 class Dims(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int32), ("d", ctypes.c_int32), ("world", ctypes.c_int32),
-                ("rank", ctypes.c_int32), ("strip_len", ctypes.c_int32)]
+                ("rank", ctypes.c_int32), ("strip_len", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
 class Layout(ctypes.Structure):
@@ -68,7 +71,7 @@ class Stats(ctypes.Structure):
 EXPORTS = ("smh_version", "smh_last_error", "smh_layout", "smh_plan_build", "smh_prep", "smh_mpjpe",
            "smh_forward", "smh_backward", "smh_finalize", "smh_weights_dense", "smh_l2norm_fwd",
            "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params", "smh_push_inputs",
-           "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz")
+           "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz", "smh_import_weights")
 
 _lib = None
 
@@ -100,6 +103,7 @@ def load() -> ctypes.CDLL:
     lib.smh_prep_zero.argtypes = [pd, vp, vp]
     lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, ctypes.c_int, ctypes.POINTER(Exchange), vp]
     lib.smh_weights_dense.argtypes = [pd, vp, vp, vp, vp, vp]
+    lib.smh_import_weights.argtypes = [pd, vp, vp, vp, i64, vp, vp]
     lib.smh_l2norm_fwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     lib.smh_l2norm_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]
     lib.smh_selftest.argtypes = [ctypes.c_int, vp, i64, vp]

@@ -44,6 +44,12 @@ static int validate_dims(const smh_dims_t *dims)
     if (dims->n % dims->world != 0)
         return set_error(SMH_E_DIM, "n (%d) must be a multiple of world (%d)", dims->n, dims->world);
     if ((int64_t)dims->n * 2 > (1 << 22)) return set_error(SMH_E_DIM, "2N too large (%d)", dims->n * 2);
+    if (dims->flags & ~(SMH_DIMS_DENSE_WEIGHTS | SMH_DIMS_DENSE_BACKWARD))
+        return set_error(SMH_E_ARG, "unknown dims.flags 0x%x", dims->flags);
+    if ((dims->flags & SMH_DIMS_DENSE_BACKWARD) && !(dims->flags & SMH_DIMS_DENSE_WEIGHTS))
+        return set_error(SMH_E_ARG, "SMH_DIMS_DENSE_BACKWARD needs SMH_DIMS_DENSE_WEIGHTS");
+    if ((dims->flags & SMH_DIMS_DENSE_WEIGHTS) && dims->world != 1)
+        return set_error(SMH_E_DIM, "the materialised-weights path is single-rank (world == 1)");
     return 0;
 }
 
@@ -64,7 +70,27 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
     const int tp = (m + kTile - 1) / kTile;
     std::vector<int2> tiles;
     std::vector<int4> tasks;
-    for (int I = 0; I < tp; ++I) {
+    const bool dense = dims.flags & SMH_DIMS_DENSE_WEIGHTS;
+    if (dense) {
+        // materialised weights: every (I, J) tile is stored (tile id = I * tp + J) and visited directly by row block I;
+        // the backward list adds the transposed visit of the mirror tile (J, I) for the column term of the gradient
+        for (int I = 0; I < tp; ++I)
+            for (int J = 0; J < tp; ++J) tiles.push_back(make_int2(I, J));
+        for (int I = 0; I < tp; ++I) {
+            for (int J = 0; J < tp; ++J) {
+                for (int half = 0; half < 2; ++half) {
+                    const int cj = 2 * J + half;
+                    if (cj * kTaskN >= m) continue;
+                    int flags = (I == J ? kTaskDiagonal : 0);
+                    if (I * kTile + kTile > m || cj * kTaskN + kTaskN > m) flags |= kTaskRagged;
+                    tasks.push_back(make_int4(I, cj, I * tp + J, flags));
+                    if (dims.flags & SMH_DIMS_DENSE_BACKWARD)
+                        tasks.push_back(make_int4(I, cj, J * tp + I, flags | kTaskTransposed));
+                }
+            }
+        }
+    }
+    for (int I = 0; I < tp && !dense; ++I) {
         if (row_owner(I, tp, dims.world) != dims.rank) continue;
         for (int J = I; J < tp; ++J) {
             int lt = (int)tiles.size();
@@ -98,6 +124,7 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
         if (dims.world == 2) sbk = 22;
         if (dims.world >= 3) sbk = 32;
         if ((long long)tiles.size() * kTileFloats * 4 <= (96ll << 20)) sbk = 4096;
+        if (dense) sbk = 4096;                 // every tile is read once per visit type: longest strips
         auto key = [&](const int4 &t) {
             long long a = t.x / sbk, b = (t.y / 2) / sbk;
             long long lo = a < b ? a : b, hi = a < b ? b : a;
@@ -264,11 +291,34 @@ static int check_inputs(const smh_dims_t &dims, const smh_inputs_t *in)
     int rc;
     if ((rc = check_ptr(in->z1_dev, "z1", 4))) return rc;
     if ((rc = check_ptr(in->z2_dev, "z2", 4))) return rc;
-    if ((rc = check_ptr(in->j1_dev, "joints1", 4))) return rc;
-    if ((rc = check_ptr(in->j2_dev, "joints2", 4))) return rc;
+    if (!(dims.flags & SMH_DIMS_DENSE_WEIGHTS) || in->j1_dev || in->j2_dev) {      // joints are optional with materialised weights
+        if ((rc = check_ptr(in->j1_dev, "joints1", 4))) return rc;
+        if ((rc = check_ptr(in->j2_dev, "joints2", 4))) return rc;
+    }
     if (in->z_row_stride < dims.d) return set_error(SMH_E_ARG, "z_row_stride < d");
     if (in->n_local <= 0 || dims.n % in->n_local != 0)
         return set_error(SMH_E_DIM, "n_local (%d) must divide n (%d)", in->n_local, dims.n);
+    return 0;
+}
+
+// 0: weights from the stored MPJPE tiles, 1: unit weights, 2: the tiles hold the materialised weights
+static int weight_mode(const smh_dims_t &dims, int engine, bool backward, int *out)
+{
+    const bool dense_dims = dims.flags & SMH_DIMS_DENSE_WEIGHTS;
+    if (engine & SMH_DENSE_WEIGHTS) {
+        if (!dense_dims) return set_error(SMH_E_MODE, "SMH_DENSE_WEIGHTS needs dims.flags & SMH_DIMS_DENSE_WEIGHTS");
+        if (backward != ((dims.flags & SMH_DIMS_DENSE_BACKWARD) != 0))
+            return set_error(SMH_E_MODE, "materialised weights: smh_forward takes the plan without, smh_backward the "
+                                         "plan with SMH_DIMS_DENSE_BACKWARD");
+        *out = 2;
+        return 0;
+    }
+    if (engine & SMH_UNIT_NEG_WEIGHTS) {
+        *out = 1;
+        return 0;
+    }
+    if (dense_dims) return set_error(SMH_E_MODE, "dense dims need SMH_DENSE_WEIGHTS or SMH_UNIT_NEG_WEIGHTS in engine");
+    *out = 0;
     return 0;
 }
 
@@ -368,9 +418,25 @@ int smh_prep_zero(const smh_dims_t *dims, void *ws_dev, void *stream)
     return 0;
 }
 
+int smh_import_weights(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, const float *neg_w_dev,
+                       int64_t neg_row_stride, const float *pos_w_dev, void *stream)
+{
+    SMH_COMMON_PROLOGUE(true)
+    if (!neg_w_dev && !pos_w_dev) return set_error(SMH_E_ARG, "import_weights: nothing to import");
+    if (neg_w_dev) {
+        if (!(dims->flags & SMH_DIMS_DENSE_WEIGHTS))
+            return set_error(SMH_E_MODE, "import_weights: neg_w needs dims.flags & SMH_DIMS_DENSE_WEIGHTS");
+        if (neg_row_stride < 2 * (int64_t)dims->n) return set_error(SMH_E_ARG, "neg_row_stride < 2N");
+        if ((rc = check_ptr(neg_w_dev, "neg_w", 4))) return rc;
+    }
+    return launch_import_weights(*dims, lay, carve_plan(plan_dev, lay), ws, neg_w_dev, neg_row_stride, pos_w_dev, st);
+}
+
 int smh_mpjpe(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, const smh_exchange_t *exch, void *stream)
 {
     SMH_COMMON_PROLOGUE(true)
+    if (dims->flags & SMH_DIMS_DENSE_WEIGHTS)
+        return set_error(SMH_E_MODE, "smh_mpjpe: the materialised-weights path takes smh_import_weights instead");
     Peers peers;
     if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
     return launch_mpjpe(*dims, lay, carve_plan(plan_dev, lay), ws, peers, st);
@@ -385,12 +451,13 @@ int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, floa
     (void)exch;                       // the sweep accumulates locally; smh_exchange_neg ships the partial sums
     Peers peers;
     if ((rc = make_peers(*dims, lay, ws_dev, nullptr, &peers))) return rc;
-    const bool unit_w = (engine & SMH_UNIT_NEG_WEIGHTS) != 0;
+    int wmode;
+    if ((rc = weight_mode(*dims, engine, false, &wmode))) return rc;
     engine &= 0xff;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16 || engine == SMH_ENGINE_TC_FP16)
-        return launch_sweep_tc(false, engine == SMH_ENGINE_TC_TF32 ? 0 : (engine == SMH_ENGINE_TC_BF16 ? 1 : 2), unit_w,
+        return launch_sweep_tc(false, engine == SMH_ENGINE_TC_TF32 ? 0 : (engine == SMH_ENGINE_TC_BF16 ? 1 : 2), wmode,
                                *dims, lay, pv, ws, peers, temperature, st);
-    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, unit_w, *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, wmode, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
 
@@ -405,11 +472,12 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
     // peer exchange: the row sums are the rank-ordered sum of the partials every rank delivered
     if ((rc = launch_rn(lay, ws, exch ? dims->world : 1, st))) return rc;
     if (engine & SMH_BACKWARD_RN_ONLY) return 0;
-    const bool unit_w = (engine & SMH_UNIT_NEG_WEIGHTS) != 0;
+    int wmode;
+    if ((rc = weight_mode(*dims, engine, true, &wmode))) return rc;
     engine &= 0xff;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16 || engine == SMH_ENGINE_TC_FP16)
-        return launch_sweep_tc(true, 1, unit_w, *dims, lay, pv, ws, peers, temperature, st);
-    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, unit_w, *dims, lay, pv, ws, peers, temperature, st);
+        return launch_sweep_tc(true, 1, wmode, *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, wmode, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
 
@@ -434,7 +502,8 @@ int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, c
         local_block = true;
         n_parts = dims->world;
     }
-    return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, local_block, n_parts, (flags & SMH_UNIT_POS_WEIGHTS) != 0,
+    const int pos_mode = (flags & SMH_UNIT_POS_WEIGHTS) ? 1 : ((flags & SMH_DENSE_WEIGHTS) ? 2 : 0);
+    return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, local_block, n_parts, pos_mode,
                            temperature, grad_scale, loss_dev, dz1_dev, dz2_dev, dz_row_stride, st);
 }
 

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256)
 finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict__ neg,
                 const float *__restrict__ posd, float *__restrict__ rowloss, Stats *__restrict__ stats,
                 const float *__restrict__ dzacc_src, int64_t src_row_offset, int n_parts, int64_t part_stride,
-                bool unit_pos_w, float inv_tau, float grad_scale,
+                int pos_mode, float inv_tau, float grad_scale,
                 float *__restrict__ loss_out, float *__restrict__ dz1, float *__restrict__ dz2,
                 int64_t dz_row_stride)
 {
@@ -67,7 +67,8 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
         float dot = 0.f;
         for (int c = lane; c < d; c += 32) dot = fmaf(zi[c], zp[c], dot);
         dot = warp_sum(dot);
-        const float wp = unit_pos_w ? 1.0f : __fdiv_rn(__fsub_rn(pmax, posd[k]), pden);   // utils.py:235
+        // utils.py:235; 1: unit weights; 2: posd holds the caller's materialised Wp (smh_import_weights)
+        const float wp = pos_mode == 1 ? 1.0f : (pos_mode == 2 ? posd[k] : __fdiv_rn(__fsub_rn(pmax, posd[k]), pden));
         if (lane == 0) rowloss[row] = logf(neg[row]) - dot * wp * inv_tau;      // utils.py:420-426
         if (dz1 != nullptr && k >= k_lo && k < k_hi) {
             const float *src = dzacc_src + (dz_out_row(row, n, n_local) - src_row_offset) * kD;
@@ -111,7 +112,7 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
 }
 
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
-                    const float *dzacc_src, bool local_block, int n_parts, bool unit_pos_w, float temperature,
+                    const float *dzacc_src, bool local_block, int n_parts, int pos_mode, float temperature,
                     float grad_scale,
                     float *loss, float *dz1, float *dz2, int64_t dz_row_stride, cudaStream_t stream)
 {
@@ -123,13 +124,52 @@ int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_i
     inp.n_local = in.n_local;
     finalize_kernel<<<blocks, 256, 0, stream>>>(inp, dims.n, dims.d, dims.rank, ws.neg, ws.posd, ws.rowloss,
                                                 (Stats *)ws.stats, dzacc_src, src_off, n_parts,
-                                                (int64_t)2 * n_local * kD, unit_pos_w, 1.0f / temperature, grad_scale, loss, dz1,
+                                                (int64_t)2 * n_local * kD, pos_mode, 1.0f / temperature, grad_scale, loss, dz1,
                                                 dz2, dz_row_stride);
     return check_launch("finalize_kernel");
 }
 
 // ----------------------------------------------------------------------------------------------
-// materialised weights
+// materialised weights in: the caller's row-major neg_w [M, M] -> the stored-tile layout of the sweeps
+// (one CTA per 128 x 128 tile; reads coalesced along rows, 16-byte swizzled stores; padding = 0)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+import_weights_kernel(const int2 *__restrict__ tiles, const float *__restrict__ neg_w, int64_t row_stride,
+                      float *__restrict__ dist, int m)
+{
+    const int2 ij = tiles[blockIdx.x];
+    float *tile = dist + (int64_t)blockIdx.x * kTileFloats;
+    for (int idx = threadIdx.x; idx < kTileFloats / 4; idx += 256) {
+        const int r = idx >> 5, c4 = idx & 31;
+        const int gi = ij.x * kTile + r, gj = ij.y * kTile + 4 * c4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (gi < m) {
+            const float *src = neg_w + (int64_t)gi * row_stride + gj;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (gj + u < m) v[u] = src[u];
+        }
+        *reinterpret_cast<float4 *>(tile + dist_index(r, 4 * c4)) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__global__ void import_pos_kernel(const float *__restrict__ pos_w, float *__restrict__ posd, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) posd[i] = pos_w[i];
+}
+
+int launch_import_weights(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
+                          const float *neg_w, int64_t neg_row_stride, const float *pos_w, cudaStream_t stream)
+{
+    if (neg_w && lay.n_stored_tiles > 0)
+        import_weights_kernel<<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, neg_w, neg_row_stride, ws.dist, lay.m);
+    if (pos_w) import_pos_kernel<<<(dims.n + 255) / 256, 256, 0, stream>>>(pos_w, ws.posd, dims.n);
+    return check_launch("import_weights_kernel");
+}
+
+// ----------------------------------------------------------------------------------------------
+// materialised weights out
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 weights_dense_kernel(const int2 *__restrict__ tiles, const float *__restrict__ dist, const Stats *__restrict__ stats,

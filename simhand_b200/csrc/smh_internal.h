@@ -40,17 +40,19 @@ int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_input
                 bool round_tf32, cudaStream_t stream);
 int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
                  const Peers &peers, cudaStream_t stream);
-int launch_sweep_fp32(bool backward, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
+int launch_sweep_fp32(bool backward, int wmode /* 0 fused, 1 unit, 2 materialised */, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
                       const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
-int launch_sweep_tc(bool backward, int logit_format /* 0 tf32, 1 bf16, 2 fp16 */, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay,
+int launch_sweep_tc(bool backward, int logit_format /* 0 tf32, 1 bf16, 2 fp16 */, int wmode, const smh_dims_t &dims, const smh_layout_t &lay,
                     const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
 int launch_push_inputs(const smh_exchange_t &exch, const smh_inputs_t &in, int n_local, int d, cudaStream_t stream);
 int launch_barrier(const smh_exchange_t &exch, cudaStream_t stream);
 int launch_rn(const smh_layout_t &lay, const WsView &ws, int n_parts, cudaStream_t stream);
 int launch_exchange_neg(const smh_layout_t &lay, const Peers &peers, cudaStream_t stream);
 int launch_exchange_dz(const smh_dims_t &dims, const smh_layout_t &lay, const Peers &peers, cudaStream_t stream);
+int launch_import_weights(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
+                          const float *neg_w, int64_t neg_row_stride, const float *pos_w, cudaStream_t stream);
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
-                    const float *dzacc_src, bool local_block, int n_parts, bool unit_pos_w, float temperature, float grad_scale, float *loss,
+                    const float *dzacc_src, bool local_block, int n_parts, int pos_mode /* 0 fused, 1 unit, 2 given */, float temperature, float grad_scale, float *loss,
                     float *dz1,
                     float *dz2, int64_t dz_row_stride, cudaStream_t stream);
 int launch_weights_dense(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int m = 2 * n;
+    const bool has_joints = in.j1_dev != nullptr;         // optional on the materialised-weights path
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < mp; row += gridDim.x * warps_per_block) {
         float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
         float jx = 0.f, jy = 0.f;
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
                 zv.z = to_tf32(zv.z);
                 zv.w = to_tf32(zv.w);
             }
-            if (lane < kJ) {
+            if (has_joints && lane < kJ) {
                 const float *jb = sample_ptr(v ? in.j2_dev : in.j1_dev, k, in.n_local, in.j_rank_stride,
                                              in.j_sample_stride) +
                                   (int64_t)lane * in.j_joint_stride;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
         if (bad && lane == 0) atomicOr(&stats->flags, bad);
 
         // positive pair (k, k + N): utils.py:229-231, IEEE sqrt/div (any domain), ATen summation order
-        if (row < n) {
+        if (has_joints && row < n) {
             float nk = 0.f;
             if (lane < kJ) {
                 const float *pb = sample_ptr(in.j2_dev, k, in.n_local, in.j_rank_stride, in.j_sample_stride) +

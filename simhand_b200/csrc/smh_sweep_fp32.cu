@@ -21,7 +21,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(256, 1)
 sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                   const float *__restrict__ zt, const float *__restrict__ dist, const float *__restrict__ rn,
-                  Peers peers, const Stats *__restrict__ stats, int m, int n, int n_local, float k2, bool unit_w)
+                  Peers peers, const Stats *__restrict__ stats, int m, int n, int n_local, float k2, int wmode)
 {
     extern __shared__ __align__(16) float smem[];
     float *As = smem;                         // [128][129]  row block of z
@@ -94,8 +94,9 @@ sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strip
                     const int jl = tx + 16 * q;
                     const int gj = cj * kTaskN + jl;
                     const int cc = (cj & 1) * 64 + jl;            // column inside the 128-wide stored tile
-                    const float dv = transposed ? tile[dist_index(cc, r)] : tile[dist_index(r, cc)];
-                    const float w = unit_w ? 1.0f : div_fast(__fsub_rn(dmax, dv), divw);
+                    // wmode 1: unit weights, the tile is never read; 2: the tile holds the materialised W
+                    const float dv = wmode == 1 ? 0.f : (transposed ? tile[dist_index(cc, r)] : tile[dist_index(r, cc)]);
+                    const float w = wmode == 1 ? 1.0f : (wmode == 2 ? dv : div_fast(__fsub_rn(dmax, dv), divw));
                     float e = ex2_approx(acc[p][q] * w * k2);
                     const bool valid = (gi < m) && (gj < m) && !(diagonal && gi == gj);
                     e = valid ? e : 0.f;
@@ -103,7 +104,10 @@ sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strip
                         rowsum[p] += e;
                     } else {
                         const float rnj = (gj < m) ? rn[gj] : 0.f;
-                        Gs[jl * kPitch + r] = valid ? w * e * (rni[p] + rnj) : 0.f;
+                        // materialised W is not symmetric in general: row term from the direct visit of the tile,
+                        // column term from the transposed visit of its mirror
+                        const float rs = wmode == 2 ? (transposed ? rnj : rni[p]) : rni[p] + rnj;
+                        Gs[jl * kPitch + r] = valid ? w * e * rs : 0.f;
                     }
                 }
             }
@@ -150,7 +154,7 @@ sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strip
     }
 }
 
-int launch_sweep_fp32(bool backward, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
+int launch_sweep_fp32(bool backward, int wmode, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
                       const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream)
 {
     if (lay.n_strips == 0) return 0;
@@ -167,13 +171,13 @@ int launch_sweep_fp32(bool backward, bool unit_w, const smh_dims_t &dims, const 
         if (e != cudaSuccess) return set_error((int)e, "fp32 sweep smem attr: %s", cudaGetErrorString(e));
         sweep_fp32_kernel<true><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt,
                                                                  ws.dist, ws.rn, peers,
-                                                                 (const Stats *)ws.stats, lay.m, dims.n, n_local, k2, unit_w);
+                                                                 (const Stats *)ws.stats, lay.m, dims.n, n_local, k2, wmode);
     } else {
         e = cudaFuncSetAttribute(sweep_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32Smem);
         if (e != cudaSuccess) return set_error((int)e, "fp32 sweep smem attr: %s", cudaGetErrorString(e));
         sweep_fp32_kernel<false><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt,
                                                                   ws.dist, ws.rn, peers,
-                                                                  (const Stats *)ws.stats, lay.m, dims.n, n_local, k2, unit_w);
+                                                                  (const Stats *)ws.stats, lay.m, dims.n, n_local, k2, wmode);
     }
     return check_launch("sweep_fp32_kernel");
 }

@@ -78,11 +78,15 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 //   backward: pk[] = bf16x2 of G' = wk * E * (1/neg_i + 1/neg_j) = k2 * G; the strip flush multiplies by 1 / k2
 // The tensor-core engines do not need the correctly rounded W of the fp32 engine (the logits carry 2^-11 operand
 // rounding): the fused form is within 1 ulp of k2 in absolute terms.  Packed f32x2 arithmetic throughout.
-// negc2 = (-k2 / Dmax) x2 (zero for unit weights), k2c2 = k2 x2.
+// negc2 = (-k2 / Dmax) x2, k2c2 = k2 x2.  Unit weights: negc2 = 0 and the tile is not read.  Materialised weights
+// (the tile holds W itself): negc2 = k2, k2c2 = 0, and, W not being symmetric in general, the backward visits a tile
+// once for the row term (cs2 = 0: G = W_ij E_ij / neg_i) and once transposed for the column term (rni = 0, cs2 = 1:
+// G = W_ji E_ji / neg_j).
 template <bool BWD, bool TRANSPOSED, bool MASKED>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], uint32_t dstage_s, int r,
                                                int chunk, int gi, int gj0, int m, bool diagonal, f2 negc2, f2 k2c2,
-                                               float rni, const float *__restrict__ rn, f2 (&rowsum)[2])
+                                               float rni, f2 cs2, bool no_tile, const float *__restrict__ rn,
+                                               f2 (&rowsum)[2])
 {
     uint32_t ta[8];                                   // transposed reads: one address per (row & 7) XOR pattern
     uint32_t dbase = 0, rx = 0;
@@ -99,8 +103,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int jl = chunk * 32 + q * 4;                       // first of 4 columns inside the task
-        f2 d01, d23;
-        if (!TRANSPOSED) {
+        f2 d01 = 0, d23 = 0;                                     // unit weights: the tile is never read (0.0f x2)
+        if (no_tile) {
+        } else if (!TRANSPOSED) {
             // column group c4 = chunk * 8 + q of the staged half: its low 3 bits (q) drive the XOR
             lds_f2x2(dbase + (uint32_t)q * 1024u + (rx ^ ((uint32_t)q << 4)), d01, d23);
         } else {
@@ -112,8 +117,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
         f2 rs01 = 0, rs23 = 0;
         if (BWD) {
             const float4 rnj = __ldg(reinterpret_cast<const float4 *>(rn + gj0 + jl));
-            rs01 = add2(rni2, pack2(rnj.x, rnj.y));
-            rs23 = add2(rni2, pack2(rnj.z, rnj.w));
+            rs01 = fma2(pack2(rnj.x, rnj.y), cs2, rni2);        // cs = 1: 1/neg_i + 1/neg_j (exact, as an add)
+            rs23 = fma2(pack2(rnj.z, rnj.w), cs2, rni2);
         }
         const f2 wk01 = fma2(d01, negc2, k2c2), wk23 = fma2(d23, negc2, k2c2);
         const f2 a01 = mul2(pack2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), wk01);
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
                 const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
-                float k2, float inv_k2, bool unit_w, uint32_t idesc1)
+                float k2, float inv_k2, int wmode, uint32_t idesc1)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
     using Cfg = TcCfg<SBF16>;
@@ -419,8 +424,9 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16);
         const float dmax = __uint_as_float(stats->dmax_bits);
         // wk = W * k2 = k2 - D * (k2 / Dmax)  (Dmin = +0, the diagonal); unit weights: wk = k2
-        const float negc = unit_w ? 0.f : -__fdiv_rn(k2, dmax);
-        const f2 negc2 = pack2(negc, negc), k2c2 = pack2(k2, k2);
+        const bool no_tile = wmode == 1, dense = wmode == 2;
+        const float negc = no_tile ? 0.f : (dense ? k2 : -__fdiv_rn(k2, dmax));
+        const f2 negc2 = pack2(negc, negc), k2c2 = dense ? pack2(0.f, 0.f) : pack2(k2, k2);
         const uint32_t sD_s = smem_u32(sD);
         uint32_t seq = 0, dz_ph = 0;
         f2 rowsum[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
@@ -445,6 +451,9 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                     row_block = task.x;
                     if (BWD) rni = row_ok ? rn[gi] : 0.f;
                 }
+                const float rni_t = (dense && transposed) ? 0.f : rni;
+                const float cs = (dense && !transposed) ? 0.f : 1.f;
+                const f2 cs2 = pack2(cs, cs);
                 mbar_wait(&bars->sg_full[sb], (seq / kSBufs) & 1u, fail, 9);
                 tc_fence_after();
                 const uint32_t dstage = sD_s + dst * kDBytes;
@@ -453,14 +462,14 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 tc_wait_ld();
                 if (masked) {
                     if (transposed)
-                        epilogue_chunk<BWD, true, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni, rn, rowsum);
+                        epilogue_chunk<BWD, true, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, rn, rowsum);
                     else
-                        epilogue_chunk<BWD, false, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni, rn, rowsum);
+                        epilogue_chunk<BWD, false, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, rn, rowsum);
                 } else {
                     if (transposed)
-                        epilogue_chunk<BWD, true, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni, rn, rowsum);
+                        epilogue_chunk<BWD, true, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, rn, rowsum);
                     else
-                        epilogue_chunk<BWD, false, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni, rn, rowsum);
+                        epilogue_chunk<BWD, false, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, rn, rowsum);
                 }
                 if (BWD) {
                     // G' as packed bf16x2 over the first half of this warp's own S columns
@@ -520,7 +529,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
 }
 
 template <bool BWD, bool SBF16>
-static int launch_one(bool unit_w, const uint16_t *half_image, uint32_t idesc1, const smh_dims_t &dims,
+static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, const smh_dims_t &dims,
                       const smh_layout_t &lay, const PlanView &plan, const WsView &ws, const Peers &peers,
                       float temperature, cudaStream_t stream)
 {
@@ -537,22 +546,22 @@ static int launch_one(bool unit_w, const uint16_t *half_image, uint32_t idesc1, 
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
     sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
                                                                    ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
-                                                                   dims.n, n_local, k2, inv_k2, unit_w, idesc1);
+                                                                   dims.n, n_local, k2, inv_k2, wmode, idesc1);
     return check_launch("sweep_tc_kernel");
 }
 
-int launch_sweep_tc(bool backward, int logit_format, bool unit_w, const smh_dims_t &dims, const smh_layout_t &lay,
+int launch_sweep_tc(bool backward, int logit_format, int wmode, const smh_dims_t &dims, const smh_layout_t &lay,
                     const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream)
 {
     if (lay.n_strips == 0) return 0;
     const uint32_t id_bf16 = umma_idesc_bf16(kTile, kTaskN, 0, 0), id_f16 = umma_idesc_f16(kTile, kTaskN, 0, 0),
                    id_tf32 = umma_idesc_tf32(kTile, kTaskN, 0, 0);
-    if (backward) return launch_one<true, true>(unit_w, ws.zb, id_bf16, dims, lay, plan, ws, peers, temperature, stream);
+    if (backward) return launch_one<true, true>(wmode, ws.zb, id_bf16, dims, lay, plan, ws, peers, temperature, stream);
     if (logit_format == 1)
-        return launch_one<false, true>(unit_w, ws.zb, id_bf16, dims, lay, plan, ws, peers, temperature, stream);
+        return launch_one<false, true>(wmode, ws.zb, id_bf16, dims, lay, plan, ws, peers, temperature, stream);
     if (logit_format == 2)
-        return launch_one<false, true>(unit_w, ws.zh, id_f16, dims, lay, plan, ws, peers, temperature, stream);
-    return launch_one<false, false>(unit_w, ws.zb, id_tf32, dims, lay, plan, ws, peers, temperature, stream);
+        return launch_one<false, true>(wmode, ws.zh, id_f16, dims, lay, plan, ws, peers, temperature, stream);
+    return launch_one<false, false>(wmode, ws.zb, id_tf32, dims, lay, plan, ws, peers, temperature, stream);
 }
 
 }  // namespace smh

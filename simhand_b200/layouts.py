@@ -59,10 +59,10 @@ def parse_plan(plan_bytes: np.ndarray):
     return h, tiles, tasks, strips
 
 
-def build_plan(n: int, d: int = 128, world: int = 1, rank: int = 0, strip_len: int = 0):
+def build_plan(n: int, d: int = 128, world: int = 1, rank: int = 0, strip_len: int = 0, flags: int = 0):
     from . import _lib
     lib = _lib.load()
-    dims = _lib.Dims(n, d, world, rank, strip_len)
+    dims = _lib.Dims(n, d, world, rank, strip_len, flags)
     lay = _lib.Layout()
     _lib.check(lib.smh_layout(ctypes.byref(dims), ctypes.byref(lay)), "smh_layout")
     buf = np.zeros(int(lay.plan_bytes), np.uint8)

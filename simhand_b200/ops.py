@@ -45,9 +45,9 @@ _ctx_cache = {}
 class _Context:
     """Layout + device copy of the task plan for one (n, d, world, rank, strip_len, device)."""
 
-    def __init__(self, n: int, d: int, world: int, rank: int, strip_len: int, device: torch.device):
+    def __init__(self, n: int, d: int, world: int, rank: int, strip_len: int, device: torch.device, flags: int = 0):
         lib = _lib.load()
-        self.dims = Dims(n, d, world, rank, strip_len)
+        self.dims = Dims(n, d, world, rank, strip_len, flags)
         self.layout = Layout()
         check(lib.smh_layout(ctypes.byref(self.dims), ctypes.byref(self.layout)), "smh_layout")
         host = torch.empty(int(self.layout.plan_bytes), dtype=torch.uint8).pin_memory() \
@@ -62,13 +62,13 @@ class _Context:
         return ws[off:off + nbytes].view(dtype)
 
 
-def get_context(n: int, d: int, world: int, rank: int, device, strip_len: int = 0) -> _Context:
+def get_context(n: int, d: int, world: int, rank: int, device, strip_len: int = 0, flags: int = 0) -> _Context:
     device = torch.device(device)
-    key = (n, d, world, rank, strip_len, device.type, device.index)
+    key = (n, d, world, rank, strip_len, device.type, device.index, flags)
     with _ctx_lock:
         ctx = _ctx_cache.get(key)
         if ctx is None:
-            ctx = _Context(n, d, world, rank, strip_len, device)
+            ctx = _Context(n, d, world, rank, strip_len, device, flags)
             _ctx_cache[key] = ctx
     return ctx
 
@@ -151,6 +151,95 @@ def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _
                        posd=ctx.view(ws, lay.off_posd, n))
             return loss, dz1, dz2, aux
     return loss, dz1, dz2
+
+
+def run_step_dense(z1, z2, pos_weights, neg_weights, temperature: float = 0.5, engine: str = _DEFAULT_ENGINE,
+                   want_grad: bool = True, grad_scale: float = 1.0):
+    """The reference's two-call API with MATERIALISED weights (`src/models/utils.py:391-427`, and :430 / :468 when one
+    of the tensors is None = unit weights): `neg_weights` is any fp32 `[2N, 2N]` tensor (not assumed symmetric),
+    `pos_weights` any `[N]` tensor.  Same sweeps as the fused path; the weight tiles are copied from the dense matrix
+    instead of being computed from the joints (HBM-bound: one read of the matrix per sweep).  Single GPU.
+    Returns (loss[()], dz1, dz2)."""
+    _require_cuda(z1, "z1")
+    _require_cuda(z2, "z2")
+    lib = _lib.load()
+    dev = z1.device
+    n, d = z1.shape
+    m = 2 * n
+    if neg_weights is not None:
+        _require_cuda(neg_weights, "neg_weights")
+        if tuple(neg_weights.shape) != (m, m):
+            raise ValueError(f"neg_weights must be [{m}, {m}], got {tuple(neg_weights.shape)}")
+        neg_weights = _as_f32(neg_weights)
+        if neg_weights.stride(1) != 1:
+            neg_weights = neg_weights.contiguous()
+    if pos_weights is not None:
+        _require_cuda(pos_weights, "pos_weights")
+        if pos_weights.numel() != n:
+            raise ValueError(f"pos_weights must have {n} elements, got {tuple(pos_weights.shape)}")
+        pos_weights = _as_f32(pos_weights).reshape(n).contiguous()
+    eng = _lib.ENGINES[resolve_engine(engine, n)]
+    with torch.cuda.device(dev):
+        dense = neg_weights is not None
+        fwd = get_context(n, d, 1, 0, dev, 0, _lib.DIMS_DENSE_WEIGHTS if dense else 0)
+        bwd = get_context(n, d, 1, 0, dev, 0, _lib.DIMS_DENSE_WEIGHTS | _lib.DIMS_DENSE_BACKWARD) if dense else fwd
+        lay = fwd.layout
+        if dense and int(bwd.layout.ws_bytes) != int(lay.ws_bytes):
+            raise RuntimeError("simhand_b200: forward/backward dense layouts differ")
+        z1c, z2c = _as_f32(z1), _as_f32(z2)
+        if z1c.stride(1) != 1 or z2c.stride(1) != 1 or z1c.stride(0) != z2c.stride(0):
+            z1c, z2c = z1c.contiguous(), z2c.contiguous()
+        inp = Inputs(z1c.data_ptr(), z2c.data_ptr(), z1c.stride(0) if n > 1 else d, None, None, 0, 0, 0, n, 0, 0)
+        if not dense:
+            # unit negatives on the fused plan: the sweeps never read the tiles, joints are not needed either
+            zero = torch.zeros((n, 21, 2), dtype=torch.float32, device=dev)
+            inp, _keep = make_inputs(z1c, z2c, zero, zero)
+        ws = torch.empty(int(lay.ws_bytes), dtype=torch.uint8, device=dev)
+        st = _stream_ptr(dev)
+        pf, pb, pi = ctypes.byref(fwd.dims), ctypes.byref(bwd.dims), ctypes.byref(inp)
+        sweep_eng = eng | (_lib.DENSE_WEIGHTS if dense else _lib.UNIT_NEG_WEIGHTS)
+        fin_flags = _lib.DENSE_WEIGHTS if pos_weights is not None else _lib.UNIT_POS_WEIGHTS
+        check(lib.smh_prep(pf, pi, ws.data_ptr(), eng, st), "smh_prep")
+        if dense or pos_weights is not None:
+            check(lib.smh_import_weights(pf, fwd.plan_dev.data_ptr(), ws.data_ptr(),
+                                         neg_weights.data_ptr() if dense else None,
+                                         neg_weights.stride(0) if dense else 0,
+                                         pos_weights.data_ptr() if pos_weights is not None else None, st),
+                  "smh_import_weights")
+        check(lib.smh_forward(pf, fwd.plan_dev.data_ptr(), ws.data_ptr(), temperature, sweep_eng, None, st), "smh_forward")
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dz1 = dz2 = None
+        if want_grad:
+            check(lib.smh_backward(pb, bwd.plan_dev.data_ptr(), ws.data_ptr(), temperature, sweep_eng, None, st),
+                  "smh_backward")
+            dz1 = torch.empty((n, d), dtype=torch.float32, device=dev)
+            dz2 = torch.empty((n, d), dtype=torch.float32, device=dev)
+        check(lib.smh_finalize(pf, pi, ws.data_ptr(), None, temperature, grad_scale, loss.data_ptr(),
+                               dz1.data_ptr() if want_grad else None, dz2.data_ptr() if want_grad else None,
+                               d, fin_flags, None, st), "smh_finalize")
+    return loss, dz1, dz2
+
+
+class _DenseWeightedNTXentFn(torch.autograd.Function):
+    """Weighted NT-Xent with materialised weight tensors (no gradient flows to the weights, as in the reference,
+    where they are built from the joints outside the graph)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, z1, z2, pos_weights, neg_weights, temperature, engine):
+        want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        loss, dz1, dz2 = run_step_dense(z1, z2, pos_weights, neg_weights, temperature, engine, want)
+        if want:
+            ctx.save_for_backward(dz1, dz2)
+        return loss
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        dz1, dz2 = ctx.saved_tensors
+        g1 = grad_out * dz1 if ctx.needs_input_grad[0] else None
+        g2 = grad_out * dz2 if ctx.needs_input_grad[1] else None
+        return g1, g2, None, None, None, None
 
 
 class _WeightedNTXentFn(torch.autograd.Function):
@@ -276,23 +365,31 @@ def vanila_weights_contrastive_loss(z1: torch.Tensor, z2: torch.Tensor, pos_weig
         if src.joints1.shape[0] != z1.shape[0]:
             raise ValueError(f"weights were built for batch {src.joints1.shape[0]}, z1 has {z1.shape[0]}")
         return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine)
-    raise NotImplementedError(
-        "simhand_b200.vanila_weights_contrastive_loss: dense weight tensors are not accepted yet; pass the "
-        "handles returned by simhand_b200.get_weights_linear (fused path)")
+    if isinstance(pos_weights, LazyWeights):
+        pos_weights = pos_weights.materialize()
+    if isinstance(neg_weights, LazyWeights):
+        neg_weights = neg_weights.materialize()
+    # real tensors (any values): the materialised-weights path
+    return _DenseWeightedNTXentFn.apply(z1, z2, pos_weights, neg_weights, float(temperature), engine)
 
 
-def _source_of(weights, kind: str) -> _WeightSource:
-    if not isinstance(weights, LazyWeights) or weights.kind != kind:
-        raise NotImplementedError(
-            f"simhand_b200: expected the {kind}-weights handle returned by simhand_b200.get_weights_linear "
-            "(dense weight tensors are not accepted yet)")
-    return weights._source
+def _source_of(weights, kind: str):
+    """The joints behind a lazy handle of the right kind, or None for a real tensor."""
+    if isinstance(weights, LazyWeights):
+        if weights.kind != kind:
+            raise ValueError(f"simhand_b200: expected the {kind}-weights handle, got the {weights.kind} one")
+        return weights._source
+    if not isinstance(weights, torch.Tensor):
+        raise TypeError(f"simhand_b200: {kind}_weights must be a tensor or a handle from get_weights_linear")
+    return None
 
 
 def vanila_pos_weights_contrastive_loss(z1, z2, pos_weights, temperature: float = 0.5,
                                         engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
     """Drop-in for `src/models/utils.py:430` (`pos_neg == "pos"`): only the positive logits are weighted."""
     src = _source_of(pos_weights, "pos")
+    if src is None:
+        return _DenseWeightedNTXentFn.apply(z1, z2, pos_weights, None, float(temperature), engine)
     return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, True, False)
 
 
@@ -300,6 +397,8 @@ def vanila_neg_weights_contrastive_loss(z1, z2, neg_weights, temperature: float 
                                         engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
     """Drop-in for `src/models/utils.py:468` (`pos_neg == "neg"`): only the negative logits are weighted."""
     src = _source_of(neg_weights, "neg")
+    if src is None:
+        return _DenseWeightedNTXentFn.apply(z1, z2, None, neg_weights, float(temperature), engine)
     return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, False, True)
 
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_sizes_match_header():
-    assert ctypes.sizeof(_lib.Dims) == 20
+    assert ctypes.sizeof(_lib.Dims) == 24
     assert ctypes.sizeof(_lib.Stats) == 32
     assert ctypes.sizeof(_lib.Exchange) == 8 + 3 * 8 * 8
     assert ctypes.sizeof(_lib.Layout) == 15 * 8 + 6 * 4
@@ -96,6 +96,43 @@ def test_plan_covers_every_ordered_pair_once(n, world):
     assert (cover[live] == 1).all() and (cover[~live] == 0).all()
     if tp >= 2 * world:
         assert max(per_rank) - min(per_rank) <= tp + 1      # balanced over ranks
+
+
+@pytest.mark.parametrize("n", [3, 96, 200, 1024])
+def test_dense_plans_visit_every_tile(n):
+    """Materialised-weights path: every (I, J) tile is stored; the forward list visits each 128 x 64 piece once
+    (direct), the backward list once direct and once through the transposed read of the mirror tile."""
+    m = 2 * n
+    tp = (m + 127) // 128
+    lay_f, (hf, tiles_f, tasks_f, _) = L.build_plan(n, 128, 1, 0, 0, _lib.DIMS_DENSE_WEIGHTS)
+    lay_b, (hb, tiles_b, tasks_b, strips_b) = L.build_plan(n, 128, 1, 0, 0,
+                                                           _lib.DIMS_DENSE_WEIGHTS | _lib.DIMS_DENSE_BACKWARD)
+    assert lay_f.ws_bytes == lay_b.ws_bytes and lay_f.off_dist == lay_b.off_dist
+    assert (tiles_f == tiles_b).all() and len(tiles_f) == tp * tp
+    assert [tuple(t) for t in tiles_f] == [(i, j) for i in range(tp) for j in range(tp)]
+    live = np.array([[cj * 64 < m for cj in range(2 * tp)]] * tp)
+    for tasks, want_t in ((tasks_f, 0), (tasks_b, 1)):
+        direct = np.zeros((tp, 2 * tp), np.int32)
+        trans = np.zeros((tp, 2 * tp), np.int32)
+        for row, cj, lt, flags in tasks:
+            I, J = tiles_f[lt]
+            if flags & L.TASK_TRANSPOSED:
+                assert (I, J) == (cj // 2, row)
+                trans[row, cj] += 1
+            else:
+                assert (I, J) == (row, cj // 2)
+                direct[row, cj] += 1
+            assert bool(flags & L.TASK_DIAGONAL) == (row == cj // 2)
+        assert (direct[live] == 1).all() and (direct[~live] == 0).all()
+        assert (trans[live] == want_t).all() and (trans[~live] == 0).all()
+    for a, b in strips_b:
+        assert len(set(tasks_b[a:b, 0])) == 1
+    # dims validation of the path
+    lib = _lib.load()
+    lay = _lib.Layout()
+    assert lib.smh_layout(ctypes.byref(_lib.Dims(n, 128, 1, 0, 0, _lib.DIMS_DENSE_BACKWARD)), ctypes.byref(lay)) == -1
+    if n % 2 == 0:
+        assert lib.smh_layout(ctypes.byref(_lib.Dims(n, 128, 2, 0, 0, _lib.DIMS_DENSE_WEIGHTS)), ctypes.byref(lay)) == -2
 
 
 def test_layout_indices_are_bijections():
