@@ -218,6 +218,22 @@ int smh_l2norm_fwd(const float *x_dev, float *y_dev, float *norm_dev, int64_t ro
 int smh_l2norm_bwd(const float *y_dev, const float *norm_dev, const float *dy_dev, float *dx_dev,
                    int64_t rows, int32_t d, float eps, void *stream);
 
+/* K4: fused projection-space transform of HandCLR_W / PeCLR_W.get_transformed_projections
+ * (src/models/unsupervised/simhand_w_model.py:55-94, peclr_w_model.py:52-91): every row of x [rows, d] (d even, <= 128)
+ * is d/2 2-D points; out = normalize(rotate(translate(normalize(x)))), i.e. F.normalize, translate_encodings
+ * (utils.py:661-684: shift by tx/ty times the detached per-row extent), rotate_encoding (utils.py:636-658: rotation by
+ * `angle_deg` about the detached per-row centroid, matrix of get_rotation_2D_matrix :606-633 built on the device),
+ * F.normalize.  tx_dev/ty_dev (both or neither) and angle_deg_dev may be NULL (that stage is skipped, as when "crop" /
+ * "rotate" is not in config.augmentation).  save_dev [rows][4] receives (||x||, ||rotated||, cos, sin) for the backward.
+ * Strides are in elements. */
+int smh_transform_fwd(const float *x_dev, int64_t x_row_stride, const float *tx_dev, const float *ty_dev,
+                      const float *angle_deg_dev, float *out_dev, int64_t out_row_stride, float *save_dev,
+                      int64_t rows, int32_t d, float eps, void *stream);
+/* backward of smh_transform_fwd: dx = J^T dout (normalise-bwd o rotation^T o normalise-bwd; extents/centroid detached) */
+int smh_transform_bwd(const float *x_dev, int64_t x_row_stride, const float *out_dev, int64_t out_row_stride,
+                      const float *save_dev, const float *dout_dev, int64_t dout_row_stride, float *dx_dev,
+                      int64_t dx_row_stride, int64_t rows, int32_t d, float eps, void *stream);
+
 /* device self-tests used by tests/ (exhaustive exact-sqrt / exact-division checks, tcgen05 tile
  * checks).  out_dev receives test-specific counters. */
 int smh_selftest(int which, uint64_t *out_dev, int64_t out_words, void *stream);

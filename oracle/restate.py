@@ -237,3 +237,32 @@ def grad_metrics(g, ref):
     cos = float(g @ ref / (np.linalg.norm(g) * np.linalg.norm(ref) + 1e-300))
     maxabs = float(np.abs(g - ref).max() / (np.abs(ref).max() + 1e-300))
     return cos, maxabs
+
+
+# --------------------------------------------------------------------------------------
+# projection-space transform: restatement of get_transformed_projections
+# (src/models/unsupervised/simhand_w_model.py:55-94) with translate_encodings (utils.py:661-684)
+# and rotate_encoding / get_rotation_2D_matrix (utils.py:606-658), out-of-place and differentiable
+# --------------------------------------------------------------------------------------
+def port_transform(projections, translate_x=None, translate_y=None, angle=None, eps: float = 1e-12):
+    """projections [rows, d] -> normalize(rotate(translate(normalize(projections)))); d/2 2-D points per row.
+    translate_* / angle are the values the reference passes to its helpers (the models pass -jitter, -angles)."""
+    rows, d = projections.shape
+    y = torch.nn.functional.normalize(projections, dim=1, eps=eps).view(rows, d // 2, 2)
+    px, py = y[..., 0], y[..., 1]
+    if translate_x is not None:
+        yd = y.detach()
+        ext = yd.max(dim=1).values - yd.min(dim=1).values                 # utils.py:673-674
+        px = px + (translate_x * ext[:, 0]).view(-1, 1)                   # :676-678
+        py = py + (translate_y * ext[:, 1]).view(-1, 1)                   # :679-681
+    if angle is not None:
+        cx, cy = px.detach().mean(dim=1), py.detach().mean(dim=1)         # :649
+        rad = angle * np.pi / 180                                         # :622
+        al, be = torch.cos(rad), torch.sin(rad)                           # :623-624 (scale = 1)
+        ox = (1 - al) * cx - be * cy                                      # :627
+        oy = (1 - al) * cy + be * cx                                      # :630
+        qx = px * al.view(-1, 1) + py * be.view(-1, 1) + ox.view(-1, 1)   # [x, y, 1] @ rot_mat[:, :, 0]
+        qy = -px * be.view(-1, 1) + py * al.view(-1, 1) + oy.view(-1, 1)  # [x, y, 1] @ rot_mat[:, :, 1]
+        px, py = qx, qy
+    out = torch.stack([px, py], dim=-1).reshape(rows, d)
+    return torch.nn.functional.normalize(out, dim=1, eps=eps)

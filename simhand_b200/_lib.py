@@ -71,7 +71,7 @@ class Stats(ctypes.Structure):
 EXPORTS = ("smh_version", "smh_last_error", "smh_layout", "smh_plan_build", "smh_prep", "smh_mpjpe",
            "smh_forward", "smh_backward", "smh_finalize", "smh_weights_dense", "smh_l2norm_fwd",
            "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params", "smh_push_inputs",
-           "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz", "smh_import_weights")
+           "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz", "smh_import_weights", "smh_transform_fwd", "smh_transform_bwd")
 
 _lib = None
 
@@ -106,6 +106,8 @@ def load() -> ctypes.CDLL:
     lib.smh_import_weights.argtypes = [pd, vp, vp, vp, i64, vp, vp]
     lib.smh_l2norm_fwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     lib.smh_l2norm_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]
+    lib.smh_transform_fwd.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i64, i32, f32, vp]
+    lib.smh_transform_bwd.argtypes = [vp, i64, vp, i64, vp, vp, i64, vp, i64, i64, i32, f32, vp]
     lib.smh_selftest.argtypes = [ctypes.c_int, vp, i64, vp]
     lib.smh_tc_probe.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), vp, vp, vp, vp, vp]
     lib.smh_tc_default_params.argtypes = [ctypes.POINTER(ctypes.c_uint32)]

@@ -573,6 +573,34 @@ int smh_l2norm_bwd(const float *y_dev, const float *norm_dev, const float *dy_de
     return launch_l2norm_bwd(y_dev, norm_dev, dy_dev, dx_dev, rows, d, eps, (cudaStream_t)stream);
 }
 
+int smh_transform_fwd(const float *x_dev, int64_t x_row_stride, const float *tx_dev, const float *ty_dev,
+                      const float *angle_deg_dev, float *out_dev, int64_t out_row_stride, float *save_dev,
+                      int64_t rows, int32_t d, float eps, void *stream)
+{
+    if (!x_dev || !out_dev || !save_dev) return set_error(SMH_E_ARG, "transform_fwd: x/out/save is null");
+    if ((tx_dev == nullptr) != (ty_dev == nullptr)) return set_error(SMH_E_ARG, "transform_fwd: tx and ty go together");
+    if (rows <= 0) return set_error(SMH_E_ARG, "rows must be positive");
+    if (d <= 0 || d > SMH_MAX_DIM || (d & 1)) return set_error(SMH_E_DIM, "d must be even and in 2..%d (got %d)", SMH_MAX_DIM, d);
+    if (x_row_stride < d || out_row_stride < d) return set_error(SMH_E_ARG, "row stride < d");
+    if (((uintptr_t)save_dev) % 16) return set_error(SMH_E_ALIGN, "save must be 16-byte aligned");
+    return launch_transform_fwd(x_dev, x_row_stride, tx_dev, ty_dev, angle_deg_dev, out_dev, out_row_stride, save_dev,
+                                rows, d, eps, (cudaStream_t)stream);
+}
+
+int smh_transform_bwd(const float *x_dev, int64_t x_row_stride, const float *out_dev, int64_t out_row_stride,
+                      const float *save_dev, const float *dout_dev, int64_t dout_row_stride, float *dx_dev,
+                      int64_t dx_row_stride, int64_t rows, int32_t d, float eps, void *stream)
+{
+    if (!x_dev || !out_dev || !save_dev || !dout_dev || !dx_dev) return set_error(SMH_E_ARG, "transform_bwd: null pointer");
+    if (rows <= 0) return set_error(SMH_E_ARG, "rows must be positive");
+    if (d <= 0 || d > SMH_MAX_DIM || (d & 1)) return set_error(SMH_E_DIM, "d must be even and in 2..%d (got %d)", SMH_MAX_DIM, d);
+    if (x_row_stride < d || out_row_stride < d || dout_row_stride < d || dx_row_stride < d)
+        return set_error(SMH_E_ARG, "row stride < d");
+    if (((uintptr_t)save_dev) % 16) return set_error(SMH_E_ALIGN, "save must be 16-byte aligned");
+    return launch_transform_bwd(x_dev, x_row_stride, out_dev, out_row_stride, save_dev, dout_dev, dout_row_stride, dx_dev,
+                                dx_row_stride, rows, d, eps, (cudaStream_t)stream);
+}
+
 int smh_selftest(int which, uint64_t *out_dev, int64_t out_words, void *stream)
 {
     if (!out_dev || out_words < 8) return set_error(SMH_E_ARG, "out buffer needs >= 8 words");

@@ -60,6 +60,12 @@ int launch_weights_dense(const smh_dims_t &dims, const smh_layout_t &lay, const 
 int launch_l2norm_fwd(const float *x, float *y, float *norm, int64_t rows, int d, float eps, cudaStream_t stream);
 int launch_l2norm_bwd(const float *y, const float *norm, const float *dy, float *dx, int64_t rows, int d,
                       float eps, cudaStream_t stream);
+int launch_transform_fwd(const float *x, int64_t x_stride, const float *tx, const float *ty, const float *angle,
+                         float *out, int64_t out_stride, float *save, int64_t rows, int d, float eps,
+                         cudaStream_t stream);
+int launch_transform_bwd(const float *x, int64_t x_stride, const float *p, int64_t p_stride, const float *save,
+                         const float *dp, int64_t dp_stride, float *dx, int64_t dx_stride, int64_t rows, int d,
+                         float eps, cudaStream_t stream);
 int launch_selftest(int which, uint64_t *out, int64_t out_words, cudaStream_t stream);
 
 }  // namespace smh

@@ -458,3 +458,65 @@ class _L2NormFn(torch.autograd.Function):
 def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     """`torch.nn.functional.normalize(x, dim=1)` for `[B, d]` fp32 (simhand_w_model.py:56-58, 91-93)."""
     return _L2NormFn.apply(x, float(eps))
+
+
+# ----------------------------------------------------------------------------------------------------
+# K4: fused projection-space transform (SURVEY.md 8f #1)
+# ----------------------------------------------------------------------------------------------------
+class _TransformFn(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, tx, ty, angle, eps):
+        _require_cuda(x, "projections")
+        lib = _lib.load()
+        rows, d = x.shape
+        xc = x.contiguous()
+        vec = lambda t, nm: None if t is None else _vec_on(t, rows, x.device, nm)        # noqa: E731
+        txc, tyc, anc = vec(tx, "translate_x"), vec(ty, "translate_y"), vec(angle, "angle")
+        out = torch.empty_like(xc)
+        save = torch.empty((rows, 4), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.smh_transform_fwd(xc.data_ptr(), d, txc.data_ptr() if txc is not None else None,
+                                        tyc.data_ptr() if tyc is not None else None,
+                                        anc.data_ptr() if anc is not None else None, out.data_ptr(), d,
+                                        save.data_ptr(), rows, d, eps, _stream_ptr(x.device)), "smh_transform_fwd")
+        ctx.save_for_backward(xc, out, save)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        xc, out, save = ctx.saved_tensors
+        lib = _lib.load()
+        rows, d = xc.shape
+        gc = g.contiguous().float()
+        dx = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            check(lib.smh_transform_bwd(xc.data_ptr(), d, out.data_ptr(), d, save.data_ptr(), gc.data_ptr(), d,
+                                        dx.data_ptr(), d, rows, d, ctx.eps, _stream_ptr(xc.device)),
+                  "smh_transform_bwd")
+        return dx, None, None, None, None
+
+
+def _vec_on(t: torch.Tensor, rows: int, device, name: str) -> torch.Tensor:
+    t = torch.as_tensor(t)
+    if t.numel() != rows:
+        raise ValueError(f"{name} must have one value per projection row ({rows}), got {tuple(t.shape)}")
+    return t.detach().to(device=device, dtype=torch.float32).reshape(rows).contiguous()
+
+
+def get_transformed_projections(projections: torch.Tensor, translate_x=None, translate_y=None, angle=None,
+                                eps: float = 1e-12) -> torch.Tensor:
+    """The projection-space equivariance step of HandCLR_W / PeCLR_W (`simhand_w_model.py:55-94`,
+    `peclr_w_model.py:52-91`) in one kernel each way:
+        normalize -> translate_encodings(., translate_x, translate_y) -> rotate_encoding(., angle) -> normalize
+    on `[2B, d]` raw projections seen as d/2 2-D points per row (`utils.py:636-684`).  `translate_*` / `angle` are the
+    values the reference hands to its helpers (the models pass `-jitter / image_size` and `-angles`); None skips that
+    stage ("crop" / "rotate" not in `config.augmentation`).  The per-row extent and centroid are detached, as in the
+    reference.  Returns `[2B, d]`; split it in halves for (projection1, projection2)."""
+    if projections.dim() != 2 or projections.shape[1] % 2 or projections.shape[1] > 128:
+        raise ValueError(f"projections must be [rows, d] with even d <= 128, got {tuple(projections.shape)}")
+    if (translate_x is None) != (translate_y is None):
+        raise ValueError("translate_x and translate_y go together")
+    return _TransformFn.apply(projections, translate_x, translate_y, angle, float(eps))
