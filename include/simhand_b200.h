@@ -76,7 +76,20 @@ typedef struct smh_dims {
     int32_t rank;                /* this rank, 0..world-1 */
     int32_t strip_len;           /* sweep tasks per strip (<= 0: library default) */
     int32_t flags;               /* SMH_DIMS_*; 0 = fused path (weights from the joints) */
+    int32_t diff_type;           /* SMH_DIFF_*: which joint distance feeds the weights (utils.py:219-231, :241-253) */
+    int32_t weight_type;         /* SMH_WEIGHT_*: linear (utils.py:218) or non_linear (utils.py:304) */
+    float lambda_pos;            /* non_linear: Wp = 1 / (1 + exp(lambda_pos (D - mean D)))   (utils.py:323-325) */
+    float lambda_neg;            /* non_linear: Wn = 1 / (1 + exp(lambda_neg (D - mean D)))   (utils.py:343-346) */
 } smh_dims_t;
+
+/* smh_dims_t.diff_type: distance between two samples' 21 x 2 joints a, b */
+#define SMH_DIFF_MPJPE 0    /* mean_k ||a_k - b_k||                                   (bit-exact with torch-CPU) */
+#define SMH_DIFF_W_ABS 1    /* negatives: || ((|dx_k| + |dy_k|) / 2)_k ||; positives: || mean_k (|dx_k|, |dy_k|) || */
+#define SMH_DIFF_W_O_ABS 2  /* negatives: || ((dx_k + dy_k) / 2)_k ||;     positives: || mean_k (dx_k, dy_k) ||
+                             * (the reference reduces over different axes for the two, utils.py:219-227 vs :241-249) */
+/* smh_dims_t.weight_type */
+#define SMH_WEIGHT_LINEAR 0     /* W = (max D - D) / (max D - min D) */
+#define SMH_WEIGHT_NONLINEAR 1  /* W = 1 / (1 + exp(lambda (D - mean D))); single rank */
 
 /* byte offsets into the workspace blob (all 256-byte aligned) and table sizes */
 typedef struct smh_layout {
@@ -114,6 +127,7 @@ typedef struct smh_stats {
     uint32_t counter;            /* internal: last-block-done ticket */
     uint32_t fail_site;          /* != 0: a bounded pipeline wait timed out (result invalid) */
     uint32_t ticket2;            /* internal: last-block-done ticket of the MPJPE kernel (peer exchange) */
+    double dsum;                 /* non_linear weights: sum_ij D_ij over all ordered pairs (mean = dsum / M^2, utils.py:345) */
 } smh_stats_t;
 
 #define SMH_FLAG_SLOW_DOMAIN 1u  /* joints outside the fast exact-sqrt domain: IEEE slow path used */

@@ -266,3 +266,34 @@ def port_transform(projections, translate_x=None, translate_y=None, angle=None, 
         px, py = qx, qy
     out = torch.stack([px, py], dim=-1).reshape(rows, d)
     return torch.nn.functional.normalize(out, dim=1, eps=eps)
+
+
+# --------------------------------------------------------------------------------------
+# the other weightings of the reference: diff_type w_abs / w_o_abs and weight_type non_linear,
+# restated from get_weights_linear (utils.py:218-261) and get_weights_nonlinear (utils.py:304-346)
+# --------------------------------------------------------------------------------------
+def port_distances(joints1, joints2, diff_type: str):
+    """(positive distances [N], all-pairs distances [2N, 2N]) for one diff_type; dense, small sizes only."""
+    bj = torch.cat((joints1, joints2), dim=0)
+    if diff_type == "mpjpe":
+        pos = torch.norm(joints1 - joints2, dim=-1).mean(dim=1)                               # :229-231
+        neg = torch.norm(bj.unsqueeze(1) - bj.unsqueeze(0), dim=-1).mean(dim=2)               # :251-253
+    elif diff_type in ("w_abs", "w_o_abs"):
+        fn = torch.abs if diff_type == "w_abs" else (lambda t: t)
+        pos = torch.norm(fn(joints1 - joints2).mean(dim=1), dim=1)                            # :219-227: mean over joints
+        neg = torch.norm(torch.mean(fn(bj.unsqueeze(1) - bj.unsqueeze(0)), dim=-1), dim=2)    # :241-249: mean over x, y
+    else:
+        raise ValueError(diff_type)
+    return pos, neg
+
+
+def port_get_weights(joints1, joints2, weight_type: str = "linear", diff_type: str = "mpjpe",
+                     lambda_pos: float = 0.0, lambda_neg: float = 0.0):
+    pos, neg = port_distances(joints1, joints2, diff_type)
+    if weight_type == "linear":
+        pos_w = (pos.max() - pos) / (pos.max() - pos.min())                                   # :233-235
+        neg_w = (neg.max() - neg) / (neg.max() - neg.min())                                   # :255-259
+    else:
+        pos_w = 1 / (1 + torch.exp(lambda_pos * (pos - pos.mean())))                          # :323-325
+        neg_w = 1 / (1 + torch.exp(lambda_neg * (neg - neg.mean())))                          # :343-346
+    return pos_w, neg_w

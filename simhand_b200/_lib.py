@@ -24,13 +24,17 @@ UNIT_POS_WEIGHTS = 0x800
 DENSE_WEIGHTS = 0x2000
 DIMS_DENSE_WEIGHTS = 1
 DIMS_DENSE_BACKWARD = 2
+DIFF_TYPES = {"mpjpe": 0, "w_abs": 1, "w_o_abs": 2}
+WEIGHT_TYPES = {"linear": 0, "non_linear": 1}
 FLAG_SLOW_DOMAIN = 1
 FLAG_NONFINITE = 2
 
 
 class Dims(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int32), ("d", ctypes.c_int32), ("world", ctypes.c_int32),
-                ("rank", ctypes.c_int32), ("strip_len", ctypes.c_int32), ("flags", ctypes.c_int32)]
+                ("rank", ctypes.c_int32), ("strip_len", ctypes.c_int32), ("flags", ctypes.c_int32),
+                ("diff_type", ctypes.c_int32), ("weight_type", ctypes.c_int32),
+                ("lambda_pos", ctypes.c_float), ("lambda_neg", ctypes.c_float)]
 
 
 class Layout(ctypes.Structure):
@@ -64,7 +68,7 @@ class Exchange(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("dmax_bits", ctypes.c_uint32), ("pmax_bits", ctypes.c_uint32), ("pmin_inv", ctypes.c_uint32),
                 ("flags", ctypes.c_uint32), ("loss", ctypes.c_float), ("counter", ctypes.c_uint32),
-                ("fail_site", ctypes.c_uint32), ("ticket2", ctypes.c_uint32)]
+                ("fail_site", ctypes.c_uint32), ("ticket2", ctypes.c_uint32), ("dsum", ctypes.c_double)]
 
 
 # every symbol include/simhand_b200.h declares (tests check that the library exports all of them)

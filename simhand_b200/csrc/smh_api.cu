@@ -50,6 +50,14 @@ static int validate_dims(const smh_dims_t *dims)
         return set_error(SMH_E_ARG, "SMH_DIMS_DENSE_BACKWARD needs SMH_DIMS_DENSE_WEIGHTS");
     if ((dims->flags & SMH_DIMS_DENSE_WEIGHTS) && dims->world != 1)
         return set_error(SMH_E_DIM, "the materialised-weights path is single-rank (world == 1)");
+    if (dims->diff_type < SMH_DIFF_MPJPE || dims->diff_type > SMH_DIFF_W_O_ABS)
+        return set_error(SMH_E_MODE, "unknown diff_type %d", dims->diff_type);
+    if (dims->weight_type != SMH_WEIGHT_LINEAR && dims->weight_type != SMH_WEIGHT_NONLINEAR)
+        return set_error(SMH_E_MODE, "unknown weight_type %d", dims->weight_type);
+    if (dims->weight_type == SMH_WEIGHT_NONLINEAR && dims->world != 1)
+        return set_error(SMH_E_DIM, "non_linear weights need the global mean distance: single rank only (world == 1)");
+    if (dims->weight_type == SMH_WEIGHT_NONLINEAR && !(dims->lambda_pos == dims->lambda_pos && dims->lambda_neg == dims->lambda_neg))
+        return set_error(SMH_E_ARG, "non_linear weights: lambda is NaN");
     return 0;
 }
 
@@ -301,7 +309,8 @@ static int check_inputs(const smh_dims_t &dims, const smh_inputs_t *in)
     return 0;
 }
 
-// 0: weights from the stored MPJPE tiles, 1: unit weights, 2: the tiles hold the materialised weights
+// 0: linear weights from the stored distance tiles, 1: unit weights, 2: the tiles hold the materialised weights,
+// 3: non_linear (sigmoid) weights from the stored distance tiles
 static int weight_mode(const smh_dims_t &dims, int engine, bool backward, int *out)
 {
     const bool dense_dims = dims.flags & SMH_DIMS_DENSE_WEIGHTS;
@@ -318,7 +327,7 @@ static int weight_mode(const smh_dims_t &dims, int engine, bool backward, int *o
         return 0;
     }
     if (dense_dims) return set_error(SMH_E_MODE, "dense dims need SMH_DENSE_WEIGHTS or SMH_UNIT_NEG_WEIGHTS in engine");
-    *out = 0;
+    *out = dims.weight_type == SMH_WEIGHT_NONLINEAR ? 3 : 0;
     return 0;
 }
 
@@ -405,7 +414,7 @@ int smh_prep(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, int e
         cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)(lay.off_posd - lay.off_stats), st);
         if (e != cudaSuccess) return set_error((int)e, "prep memset: %s", cudaGetErrorString(e));
     }
-    return launch_prep(*dims, lay, *in, ws, engine == SMH_ENGINE_TC_TF32, st);
+    return launch_prep(*dims, lay, *in, ws, engine == SMH_ENGINE_TC_TF32, st);      // dims carries diff_type
 }
 
 int smh_prep_zero(const smh_dims_t *dims, void *ws_dev, void *stream)
@@ -502,7 +511,8 @@ int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, c
         local_block = true;
         n_parts = dims->world;
     }
-    const int pos_mode = (flags & SMH_UNIT_POS_WEIGHTS) ? 1 : ((flags & SMH_DENSE_WEIGHTS) ? 2 : 0);
+    const int pos_mode = (flags & SMH_UNIT_POS_WEIGHTS) ? 1
+                         : ((flags & SMH_DENSE_WEIGHTS) ? 2 : (dims->weight_type == SMH_WEIGHT_NONLINEAR ? 3 : 0));
     return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, local_block, n_parts, pos_mode,
                            temperature, grad_scale, loss_dev, dz1_dev, dz2_dev, dz_row_stride, st);
 }

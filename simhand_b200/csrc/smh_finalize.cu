@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256)
 finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict__ neg,
                 const float *__restrict__ posd, float *__restrict__ rowloss, Stats *__restrict__ stats,
                 const float *__restrict__ dzacc_src, int64_t src_row_offset, int n_parts, int64_t part_stride,
-                int pos_mode, float inv_tau, float grad_scale,
+                int pos_mode, float lambda_pos, float inv_tau, float grad_scale,
                 float *__restrict__ loss_out, float *__restrict__ dz1, float *__restrict__ dz2,
                 int64_t dz_row_stride)
 {
@@ -58,6 +58,22 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
     const int n_local = in.n_local;
     const int k_lo = rank * n_local, k_hi = k_lo + n_local;
     const float gs = grad_scale * inv_tau / (float)m;
+    __shared__ float pos_mean_s;
+    if (pos_mode == 3) {
+        // non_linear positives (utils.py:323-325): mean_k D_{k,k+N}, summed in the same fixed order by every block
+        __shared__ float red[256];
+        float a = 0.f;
+        for (int i = threadIdx.x; i < n; i += 256) a += posd[i];
+        red[threadIdx.x] = a;
+        __syncthreads();
+        for (int s2 = 128; s2 > 0; s2 >>= 1) {
+            if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) pos_mean_s = red[0] / (float)n;
+        __syncthreads();
+    }
+    const float pos_mean = pos_mode == 3 ? pos_mean_s : 0.f;
 
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < m; row += gridDim.x * warps_per_block) {
         const int v = row >= n ? 1 : 0;
@@ -68,7 +84,8 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
         for (int c = lane; c < d; c += 32) dot = fmaf(zi[c], zp[c], dot);
         dot = warp_sum(dot);
         // utils.py:235; 1: unit weights; 2: posd holds the caller's materialised Wp (smh_import_weights)
-        const float wp = pos_mode == 1 ? 1.0f : (pos_mode == 2 ? posd[k] : __fdiv_rn(__fsub_rn(pmax, posd[k]), pden));
+        float wp = pos_mode == 1 ? 1.0f : (pos_mode == 2 ? posd[k] : __fdiv_rn(__fsub_rn(pmax, posd[k]), pden));
+        if (pos_mode == 3) wp = __fdiv_rn(1.0f, 1.0f + expf(lambda_pos * (posd[k] - pos_mean)));
         if (lane == 0) rowloss[row] = logf(neg[row]) - dot * wp * inv_tau;      // utils.py:420-426
         if (dz1 != nullptr && k >= k_lo && k < k_hi) {
             const float *src = dzacc_src + (dz_out_row(row, n, n_local) - src_row_offset) * kD;
@@ -124,7 +141,7 @@ int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_i
     inp.n_local = in.n_local;
     finalize_kernel<<<blocks, 256, 0, stream>>>(inp, dims.n, dims.d, dims.rank, ws.neg, ws.posd, ws.rowloss,
                                                 (Stats *)ws.stats, dzacc_src, src_off, n_parts,
-                                                (int64_t)2 * n_local * kD, pos_mode, 1.0f / temperature, grad_scale, loss, dz1,
+                                                (int64_t)2 * n_local * kD, pos_mode, dims.lambda_pos, 1.0f / temperature, grad_scale, loss, dz1,
                                                 dz2, dz_row_stride);
     return check_launch("finalize_kernel");
 }
@@ -173,8 +190,9 @@ int launch_import_weights(const smh_dims_t &dims, const smh_layout_t &lay, const
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 weights_dense_kernel(const int2 *__restrict__ tiles, const float *__restrict__ dist, const Stats *__restrict__ stats,
-                     float *__restrict__ neg_w, int m)
+                     float *__restrict__ neg_w, int m, bool nonlinear, float lambda_neg)
 {
+    const float mu = nonlinear ? (float)(stats->dsum / ((double)m * (double)m)) : 0.f;
     const int2 ij = tiles[blockIdx.x];
     const float *tile = dist + (int64_t)blockIdx.x * kTileFloats;
     const float dmax = __uint_as_float(stats->dmax_bits);
@@ -187,7 +205,9 @@ weights_dense_kernel(const int2 *__restrict__ tiles, const float *__restrict__ d
         if (gi < m && gj < m) {
             float dv = tile[dist_index(r, c)];
             float num = __fsub_rn(dmax, dv);
-            neg_w[(int64_t)gi * m + gj] = slow ? __fdiv_rn(num, dmax) : div_fast(num, divw);
+            float w = slow ? __fdiv_rn(num, dmax) : div_fast(num, divw);
+            if (nonlinear) w = __fdiv_rn(1.0f, 1.0f + expf(lambda_neg * (dv - mu)));        // utils.py:346
+            neg_w[(int64_t)gi * m + gj] = w;
         }
         if (ij.x != ij.y) {
             // mirrored orientation: element (c', r') of the stored tile lands at row J*128 + c', col I*128 + r'
@@ -196,16 +216,33 @@ weights_dense_kernel(const int2 *__restrict__ tiles, const float *__restrict__ d
             if (gi2 < m && gj2 < m) {
                 float dv = tile[dist_index(rr, cc)];
                 float num = __fsub_rn(dmax, dv);
-                neg_w[(int64_t)gi2 * m + gj2] = slow ? __fdiv_rn(num, dmax) : div_fast(num, divw);
+                float w = slow ? __fdiv_rn(num, dmax) : div_fast(num, divw);
+                if (nonlinear) w = __fdiv_rn(1.0f, 1.0f + expf(lambda_neg * (dv - mu)));
+                neg_w[(int64_t)gi2 * m + gj2] = w;
             }
         }
     }
 }
 
-__global__ void pos_weights_kernel(const float *__restrict__ posd, const Stats *__restrict__ stats,
-                                   float *__restrict__ pos_w, int n)
+__global__ void __launch_bounds__(256)
+pos_weights_kernel(const float *__restrict__ posd, const Stats *__restrict__ stats, float *__restrict__ pos_w, int n,
+                   bool nonlinear, float lambda_pos)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nonlinear) {
+        __shared__ float red[256];
+        float a = 0.f;
+        for (int i = threadIdx.x; i < n; i += 256) a += posd[i];
+        red[threadIdx.x] = a;
+        __syncthreads();
+        for (int s2 = 128; s2 > 0; s2 >>= 1) {
+            if (threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+            __syncthreads();
+        }
+        const float mean = red[0] / (float)n;
+        if (k < n) pos_w[k] = __fdiv_rn(1.0f, 1.0f + expf(lambda_pos * (posd[k] - mean)));        // utils.py:325
+        return;
+    }
     if (k >= n) return;
     const float pmax = __uint_as_float(stats->pmax_bits);
     const float pmin = __uint_as_float(0x7fffffffu - stats->pmin_inv);
@@ -216,13 +253,16 @@ int launch_weights_dense(const smh_dims_t &dims, const smh_layout_t &lay, const 
                          float *pos_w, float *neg_w, cudaStream_t stream)
 {
     if (pos_w) {
-        pos_weights_kernel<<<(dims.n + 255) / 256, 256, 0, stream>>>(ws.posd, (const Stats *)ws.stats, pos_w, dims.n);
+        pos_weights_kernel<<<(dims.n + 255) / 256, 256, 0, stream>>>(ws.posd, (const Stats *)ws.stats, pos_w, dims.n,
+                                                                      dims.weight_type == SMH_WEIGHT_NONLINEAR, dims.lambda_pos);
         int rc = check_launch("pos_weights_kernel");
         if (rc) return rc;
     }
     if (neg_w && lay.n_stored_tiles > 0) {
         weights_dense_kernel<<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.dist, (const Stats *)ws.stats,
-                                                                    neg_w, lay.m);
+                                                                    neg_w, lay.m,
+                                                                    dims.weight_type == SMH_WEIGHT_NONLINEAR,
+                                                                    dims.lambda_neg);
         return check_launch("weights_dense_kernel");
     }
     return 0;

@@ -173,18 +173,133 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// diff_type w_abs / w_o_abs (utils.py:241-249): D_ij = || ((dx_k + dy_k) / 2)_k ||_2 over the 21 joints, with |.| on
+// dx, dy for w_abs.  One sqrt per pair: a light kernel (same tiles, same layout, same max reduction).  Symmetric with
+// a zero diagonal like the MPJPE, so the upper triangle is enough.  IEEE sqrt: no input-domain restriction.
+// ----------------------------------------------------------------------------------------------
+template <bool ABS>
+__global__ void __launch_bounds__(256, 2)
+altdist_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float *__restrict__ dist, int m,
+               Stats *__restrict__ stats)
+{
+    __shared__ __align__(16) float cs[kTile * kJP];
+    __shared__ uint32_t wmax[8];
+    const int2 ij = tiles[blockIdx.x];
+    float *tile_out = dist + (int64_t)blockIdx.x * kTileFloats;
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(jp + (int64_t)ij.y * kTile * kJP);
+        float4 *dst = reinterpret_cast<float4 *>(cs);
+        for (int i = threadIdx.x; i < kTile * kJP / 4; i += 256) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int r = threadIdx.x & 127, col0 = (threadIdx.x >> 7) * 64;
+    float a[kJP];
+    {
+        const float4 *rowp = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.x * kTile + r) * kJP);
+#pragma unroll
+        for (int p = 0; p < 11; ++p) {
+            const float4 v = rowp[p];
+            a[4 * p] = v.x; a[4 * p + 1] = v.y; a[4 * p + 2] = v.z; a[4 * p + 3] = v.w;
+        }
+    }
+    const bool row_ok = (ij.x * kTile + r) < m;
+    const int col_limit = m - ij.y * kTile;
+    uint32_t vmax_bits = 0u;
+#pragma unroll 1
+    for (int c0 = col0; c0 < col0 + 64; c0 += 4) {
+        float dv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float *b = cs + (c0 + u) * kJP;
+            float acc = 0.f;
+#pragma unroll
+            for (int p = 0; p < 10; ++p) {          // packed (x_2p, x_2p+1, y_2p, y_2p+1)
+                float dx0 = a[4 * p] - b[4 * p], dx1 = a[4 * p + 1] - b[4 * p + 1];
+                float dy0 = a[4 * p + 2] - b[4 * p + 2], dy1 = a[4 * p + 3] - b[4 * p + 3];
+                if (ABS) { dx0 = fabsf(dx0); dx1 = fabsf(dx1); dy0 = fabsf(dy0); dy1 = fabsf(dy1); }
+                const float t0 = 0.5f * (dx0 + dy0), t1 = 0.5f * (dx1 + dy1);
+                acc = fmaf(t0, t0, acc);
+                acc = fmaf(t1, t1, acc);
+            }
+            float dx = a[40] - b[40], dy = a[41] - b[41];
+            if (ABS) { dx = fabsf(dx); dy = fabsf(dy); }
+            const float t = 0.5f * (dx + dy);
+            acc = fmaf(t, t, acc);
+            dv[u] = __fsqrt_rn(acc);
+            if (row_ok && (c0 + u) < col_limit) vmax_bits = max(vmax_bits, __float_as_uint(dv[u]));
+        }
+        *reinterpret_cast<float4 *>(tile_out + dist_index(r, c0)) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax_bits = max(vmax_bits, __shfl_xor_sync(0xffffffffu, vmax_bits, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = vmax_bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t v = wmax[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) v = max(v, wmax[w]);
+        if (v > 0x7f800000u)
+            atomicOr(&stats->flags, SMH_FLAG_NONFINITE);
+        else
+            atomicMax(&stats->dmax_bits, v);
+    }
+}
+
+// non_linear weights (utils.py:343-346) need mean_ij D_ij over all M^2 ordered pairs: one pass over the stored tiles
+// (an off-diagonal tile stands for both (I, J) and (J, I)), summed in double.
+__global__ void __launch_bounds__(256)
+tile_sum_kernel(const int2 *__restrict__ tiles, const float *__restrict__ dist, int m, Stats *__restrict__ stats)
+{
+    __shared__ double part[8];
+    const int2 ij = tiles[blockIdx.x];
+    const float *tile = dist + (int64_t)blockIdx.x * kTileFloats;
+    float acc = 0.f;
+    for (int idx = threadIdx.x; idx < kTileFloats / 4; idx += 256) {
+        const int r = idx >> 5, c4 = idx & 31;
+        const float4 v = *reinterpret_cast<const float4 *>(tile + dist_index(r, 4 * c4));
+        const int gi = ij.x * kTile + r, gj = ij.y * kTile + 4 * c4;
+        if (gi < m) {
+            if (gj < m) acc += v.x;
+            if (gj + 1 < m) acc += v.y;
+            if (gj + 2 < m) acc += v.z;
+            if (gj + 3 < m) acc += v.w;
+        }
+    }
+    double d = (double)acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = d;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w];
+        atomicAdd(&stats->dsum, ij.x == ij.y ? t : 2.0 * t);
+    }
+}
+
 int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
                  const Peers &peers, cudaStream_t stream)
 {
-    (void)dims;
     if (lay.n_stored_tiles == 0) return 0;
     Stats *st = (Stats *)ws.stats;
-    // fewer than ~8 waves of whole tiles (2 CTAs x 148 SMs per wave): cut the tiles in halves
-    if (lay.n_stored_tiles < 8 * 2 * kNumCtas)
+    if (dims.diff_type != SMH_DIFF_MPJPE) {
+        if (peers.world > 1) return set_error(SMH_E_DIM, "diff_type w_abs / w_o_abs: single rank only");
+        if (dims.diff_type == SMH_DIFF_W_ABS)
+            altdist_kernel<true><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st);
+        else
+            altdist_kernel<false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st);
+    } else if (lay.n_stored_tiles < 8 * 2 * kNumCtas) {
+        // fewer than ~8 waves of whole tiles (2 CTAs x 148 SMs per wave): cut the tiles in halves
         mpjpe_kernel<true><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
-    else
+    } else {
         mpjpe_kernel<false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
-    return check_launch("mpjpe_kernel");
+    }
+    int rc = check_launch(dims.diff_type != SMH_DIFF_MPJPE ? "altdist_kernel" : "mpjpe_kernel");
+    if (rc || dims.weight_type != SMH_WEIGHT_NONLINEAR) return rc;
+    tile_sum_kernel<<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.dist, lay.m, st);
+    return check_launch("tile_sum_kernel");
 }
 
 }  // namespace smh

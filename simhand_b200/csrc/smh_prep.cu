@@ -22,7 +22,7 @@ __device__ __forceinline__ const float *sample_ptr(const float *base, int k, int
     return base + (int64_t)(k / n_local) * rank_stride + (int64_t)(k % n_local) * row_stride;
 }
 
-__global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d, int mp, bool round_tf32,
+__global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d, int mp, bool round_tf32, int diff,
                                                    float *__restrict__ zt, uint16_t *__restrict__ zb,
                                                    uint16_t *__restrict__ zh,
                                                    float *__restrict__ jp, float *__restrict__ posd,
@@ -101,22 +101,33 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
 
         // positive pair (k, k + N): utils.py:229-231, IEEE sqrt/div (any domain), ATen summation order
         if (has_joints && row < n) {
-            float nk = 0.f;
+            float dx = 0.f, dy = 0.f;
             if (lane < kJ) {
                 const float *pb = sample_ptr(in.j2_dev, k, in.n_local, in.j_rank_stride, in.j_sample_stride) +
                                   (int64_t)lane * in.j_joint_stride;
-                float dx = __fsub_rn(jx, pb[0]);
-                float dy = __fsub_rn(jy, pb[in.j_coord_stride]);
-                nk = __fsqrt_rn(__fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                dx = __fsub_rn(jx, pb[0]);
+                dy = __fsub_rn(jy, pb[in.j_coord_stride]);
             }
-            float s = __shfl_sync(0xffffffffu, nk, 16);
+            float dk;
+            if (diff == SMH_DIFF_MPJPE) {
+                const float nk = lane < kJ ? __fsqrt_rn(__fmaf_rn(dy, dy, __fmul_rn(dx, dx))) : 0.f;
+                float s = __shfl_sync(0xffffffffu, nk, 16);
 #pragma unroll
-            for (int q = 17; q <= 20; ++q) s = __fadd_rn(s, __shfl_sync(0xffffffffu, nk, q));
+                for (int q = 17; q <= 20; ++q) s = __fadd_rn(s, __shfl_sync(0xffffffffu, nk, q));
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                s = __fadd_rn(s, __fadd_rn(__shfl_sync(0xffffffffu, nk, q), __shfl_sync(0xffffffffu, nk, q + 8)));
+                for (int q = 0; q < 8; ++q)
+                    s = __fadd_rn(s, __fadd_rn(__shfl_sync(0xffffffffu, nk, q), __shfl_sync(0xffffffffu, nk, q + 8)));
+                dk = __fdiv_rn(s, 21.0f);
+            } else {
+                // w_abs / w_o_abs (utils.py:219-227): per-coordinate mean over the joints, then the 2-norm
+                if (diff == SMH_DIFF_W_ABS) {
+                    dx = fabsf(dx);
+                    dy = fabsf(dy);
+                }
+                const float mx = __fdiv_rn(warp_sum(dx), 21.0f), my = __fdiv_rn(warp_sum(dy), 21.0f);
+                dk = __fsqrt_rn(__fmaf_rn(my, my, __fmul_rn(mx, mx)));
+            }
             if (lane == 0) {
-                float dk = __fdiv_rn(s, 21.0f);
                 posd[k] = dk;
                 uint32_t b = __float_as_uint(dk);
                 if (b <= 0x7f800000u) {     // non-negative, not NaN
@@ -135,7 +146,7 @@ int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_input
 {
     const int mp = lay.tiles_per_side * kTile;
     const int blocks = (mp + 7) / 8;
-    prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, ws.zt, ws.zb, ws.zh, ws.jp, ws.posd, (Stats *)ws.stats);
+    prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, dims.diff_type, ws.zt, ws.zb, ws.zh, ws.jp, ws.posd, (Stats *)ws.stats);
     return check_launch("prep_kernel");
 }
 

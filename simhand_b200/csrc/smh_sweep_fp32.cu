@@ -21,7 +21,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(256, 1)
 sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                   const float *__restrict__ zt, const float *__restrict__ dist, const float *__restrict__ rn,
-                  Peers peers, const Stats *__restrict__ stats, int m, int n, int n_local, float k2, int wmode)
+                  Peers peers, const Stats *__restrict__ stats, int m, int n, int n_local, float k2, int wmode, float lambda_neg)
 {
     extern __shared__ __align__(16) float smem[];
     float *As = smem;                         // [128][129]  row block of z
@@ -33,6 +33,7 @@ sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strip
     const int s_begin = cta_ptr[blockIdx.x], s_end = cta_ptr[blockIdx.x + 1];      // this CTA's strips
     const float dmax = __uint_as_float(stats->dmax_bits);
     const DivConst divw = make_div(dmax);     // Dmax - Dmin with Dmin = +0 (diagonal)
+    const float mu = wmode == 3 ? (float)(stats->dsum / ((double)m * (double)m)) : 0.f;     // non_linear: mean D
 
     for (int s = s_begin; s < s_end; ++s) {
         const int2 strip = strips[s];
@@ -96,7 +97,8 @@ sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strip
                     const int cc = (cj & 1) * 64 + jl;            // column inside the 128-wide stored tile
                     // wmode 1: unit weights, the tile is never read; 2: the tile holds the materialised W
                     const float dv = wmode == 1 ? 0.f : (transposed ? tile[dist_index(cc, r)] : tile[dist_index(r, cc)]);
-                    const float w = wmode == 1 ? 1.0f : (wmode == 2 ? dv : div_fast(__fsub_rn(dmax, dv), divw));
+                    float w = wmode == 1 ? 1.0f : (wmode == 2 ? dv : div_fast(__fsub_rn(dmax, dv), divw));
+                    if (wmode == 3) w = __fdiv_rn(1.0f, 1.0f + expf(lambda_neg * (dv - mu)));     // utils.py:346
                     float e = ex2_approx(acc[p][q] * w * k2);
                     const bool valid = (gi < m) && (gj < m) && !(diagonal && gi == gj);
                     e = valid ? e : 0.f;
@@ -171,13 +173,13 @@ int launch_sweep_fp32(bool backward, int wmode, const smh_dims_t &dims, const sm
         if (e != cudaSuccess) return set_error((int)e, "fp32 sweep smem attr: %s", cudaGetErrorString(e));
         sweep_fp32_kernel<true><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt,
                                                                  ws.dist, ws.rn, peers,
-                                                                 (const Stats *)ws.stats, lay.m, dims.n, n_local, k2, wmode);
+                                                                 (const Stats *)ws.stats, lay.m, dims.n, n_local, k2, wmode, dims.lambda_neg);
     } else {
         e = cudaFuncSetAttribute(sweep_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32Smem);
         if (e != cudaSuccess) return set_error((int)e, "fp32 sweep smem attr: %s", cudaGetErrorString(e));
         sweep_fp32_kernel<false><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt,
                                                                   ws.dist, ws.rn, peers,
-                                                                  (const Stats *)ws.stats, lay.m, dims.n, n_local, k2, wmode);
+                                                                  (const Stats *)ws.stats, lay.m, dims.n, n_local, k2, wmode, dims.lambda_neg);
     }
     return check_launch("sweep_fp32_kernel");
 }

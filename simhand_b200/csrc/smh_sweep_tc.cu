@@ -85,8 +85,8 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 template <bool BWD, bool TRANSPOSED, bool MASKED>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], uint32_t dstage_s, int r,
                                                int chunk, int gi, int gj0, int m, bool diagonal, f2 negc2, f2 k2c2,
-                                               float rni, f2 cs2, bool no_tile, const float *__restrict__ rn,
-                                               f2 (&rowsum)[2])
+                                               float rni, f2 cs2, bool no_tile, bool sigmoid, float k2,
+                                               const float *__restrict__ rn, f2 (&rowsum)[2])
 {
     uint32_t ta[8];                                   // transposed reads: one address per (row & 7) XOR pattern
     uint32_t dbase = 0, rx = 0;
@@ -120,7 +120,18 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
             rs01 = fma2(pack2(rnj.x, rnj.y), cs2, rni2);        // cs = 1: 1/neg_i + 1/neg_j (exact, as an add)
             rs23 = fma2(pack2(rnj.z, rnj.w), cs2, rni2);
         }
-        const f2 wk01 = fma2(d01, negc2, k2c2), wk23 = fma2(d23, negc2, k2c2);
+        f2 wk01 = fma2(d01, negc2, k2c2), wk23 = fma2(d23, negc2, k2c2);
+        if (sigmoid) {
+            // non_linear weights (utils.py:346): W = 1 / (1 + exp(lambda (D - mean D))); the fma above produced
+            // lambda log2(e) (D - mean D)
+            float t[4];
+            unpack2(wk01, t[0], t[1]);
+            unpack2(wk23, t[2], t[3]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = k2 * rcp_approx(1.0f + ex2_approx(t[u]));
+            wk01 = pack2(t[0], t[1]);
+            wk23 = pack2(t[2], t[3]);
+        }
         const f2 a01 = mul2(pack2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), wk01);
         const f2 a23 = mul2(pack2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), wk23);
         float a[4], e[4];
@@ -164,7 +175,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
                 const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
-                float k2, float inv_k2, int wmode, uint32_t idesc1)
+                float k2, float inv_k2, int wmode, float lambda_neg, uint32_t idesc1)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
     using Cfg = TcCfg<SBF16>;
@@ -424,9 +435,16 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16);
         const float dmax = __uint_as_float(stats->dmax_bits);
         // wk = W * k2 = k2 - D * (k2 / Dmax)  (Dmin = +0, the diagonal); unit weights: wk = k2
-        const bool no_tile = wmode == 1, dense = wmode == 2;
-        const float negc = no_tile ? 0.f : (dense ? k2 : -__fdiv_rn(k2, dmax));
-        const f2 negc2 = pack2(negc, negc), k2c2 = dense ? pack2(0.f, 0.f) : pack2(k2, k2);
+        const bool no_tile = wmode == 1, dense = wmode == 2, sigmoid = wmode == 3;
+        float negc = no_tile ? 0.f : (dense ? k2 : -__fdiv_rn(k2, dmax));
+        float addc = dense ? 0.f : k2;
+        if (sigmoid) {
+            // exponent of the sigmoid in base 2: lambda log2(e) (D - mean D), mean over all M^2 ordered pairs
+            const float mu = (float)(stats->dsum / ((double)m * (double)m));
+            negc = lambda_neg * 1.4426950408889634f;
+            addc = -mu * negc;
+        }
+        const f2 negc2 = pack2(negc, negc), k2c2 = pack2(addc, addc);
         const uint32_t sD_s = smem_u32(sD);
         uint32_t seq = 0, dz_ph = 0;
         f2 rowsum[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
@@ -462,14 +480,14 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 tc_wait_ld();
                 if (masked) {
                     if (transposed)
-                        epilogue_chunk<BWD, true, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, rn, rowsum);
+                        epilogue_chunk<BWD, true, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, sigmoid, k2, rn, rowsum);
                     else
-                        epilogue_chunk<BWD, false, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, rn, rowsum);
+                        epilogue_chunk<BWD, false, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, sigmoid, k2, rn, rowsum);
                 } else {
                     if (transposed)
-                        epilogue_chunk<BWD, true, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, rn, rowsum);
+                        epilogue_chunk<BWD, true, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, sigmoid, k2, rn, rowsum);
                     else
-                        epilogue_chunk<BWD, false, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, rn, rowsum);
+                        epilogue_chunk<BWD, false, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, sigmoid, k2, rn, rowsum);
                 }
                 if (BWD) {
                     // G' as packed bf16x2 over the first half of this warp's own S columns
@@ -546,7 +564,7 @@ static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, co
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
     sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
                                                                    ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
-                                                                   dims.n, n_local, k2, inv_k2, wmode, idesc1);
+                                                                   dims.n, n_local, k2, inv_k2, wmode, dims.lambda_neg, idesc1);
     return check_launch("sweep_tc_kernel");
 }
 

@@ -45,9 +45,12 @@ _ctx_cache = {}
 class _Context:
     """Layout + device copy of the task plan for one (n, d, world, rank, strip_len, device)."""
 
-    def __init__(self, n: int, d: int, world: int, rank: int, strip_len: int, device: torch.device, flags: int = 0):
+    def __init__(self, n: int, d: int, world: int, rank: int, strip_len: int, device: torch.device, flags: int = 0,
+                 weighting=None):
         lib = _lib.load()
-        self.dims = Dims(n, d, world, rank, strip_len, flags)
+        diff, wtype, lam_p, lam_n = weighting or DEFAULT_WEIGHTING
+        self.dims = Dims(n, d, world, rank, strip_len, flags, _lib.DIFF_TYPES[diff], _lib.WEIGHT_TYPES[wtype],
+                         float(lam_p), float(lam_n))
         self.layout = Layout()
         check(lib.smh_layout(ctypes.byref(self.dims), ctypes.byref(self.layout)), "smh_layout")
         host = torch.empty(int(self.layout.plan_bytes), dtype=torch.uint8).pin_memory() \
@@ -62,13 +65,31 @@ class _Context:
         return ws[off:off + nbytes].view(dtype)
 
 
-def get_context(n: int, d: int, world: int, rank: int, device, strip_len: int = 0, flags: int = 0) -> _Context:
+def make_weighting(weight_type: str = "linear", diff_type: str = "mpjpe", lambda_pos: float = 0.0,
+                   lambda_neg: float = 0.0):
+    """(diff_type, weight_type, lambda_pos, lambda_neg) as the reference's config names them
+    (`config.weight_type`, `config.diff_type`, `config.non_linear_lambda_pos/neg`, simhand_w_model.py:106-118)."""
+    if diff_type not in _lib.DIFF_TYPES:
+        raise ValueError(f"diff_type must be one of {sorted(_lib.DIFF_TYPES)}, got {diff_type!r}")
+    if weight_type not in _lib.WEIGHT_TYPES:
+        raise ValueError(f"weight_type must be one of {sorted(_lib.WEIGHT_TYPES)}, got {weight_type!r}")
+    if weight_type == "linear":
+        lambda_pos = lambda_neg = 0.0
+    return (diff_type, weight_type, float(lambda_pos), float(lambda_neg))
+
+
+DEFAULT_WEIGHTING = ("mpjpe", "linear", 0.0, 0.0)
+
+
+def get_context(n: int, d: int, world: int, rank: int, device, strip_len: int = 0, flags: int = 0,
+                weighting=None) -> _Context:
     device = torch.device(device)
-    key = (n, d, world, rank, strip_len, device.type, device.index, flags)
+    weighting = tuple(weighting or DEFAULT_WEIGHTING)
+    key = (n, d, world, rank, strip_len, device.type, device.index, flags, weighting)
     with _ctx_lock:
         ctx = _ctx_cache.get(key)
         if ctx is None:
-            ctx = _Context(n, d, world, rank, strip_len, device, flags)
+            ctx = _Context(n, d, world, rank, strip_len, device, flags, weighting)
             _ctx_cache[key] = ctx
     return ctx
 
@@ -112,10 +133,11 @@ def _stream_ptr(device) -> int:
 
 def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _DEFAULT_ENGINE,
              want_grad: bool = True, grad_scale: float = 1.0, strip_len: int = 0, return_aux: bool = False,
-             pos_weighted: bool = True, neg_weighted: bool = True):
+             pos_weighted: bool = True, neg_weighted: bool = True, weighting=None):
     """One fused fwd(+bwd) step on a single GPU.  Returns (loss[()], dz1, dz2[, aux]).
     pos_weighted / neg_weighted = False give the reference's neg-only / pos-only / unweighted losses
-    (utils.py:468, :430, :157): the corresponding weight is 1."""
+    (utils.py:468, :430, :157): the corresponding weight is 1.  weighting = make_weighting(...) selects
+    weight_type linear / non_linear and diff_type mpjpe / w_abs / w_o_abs (utils.py:218-261, :304-346)."""
     for t, nm in ((z1, "z1"), (z2, "z2"), (joints1, "joints1"), (joints2, "joints2")):
         _require_cuda(t, nm)
     lib = _lib.load()
@@ -123,7 +145,7 @@ def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _
     n, d = z1.shape
     eng = _lib.ENGINES[resolve_engine(engine, n)]
     with torch.cuda.device(dev):
-        ctx = get_context(n, d, 1, 0, dev, strip_len)
+        ctx = get_context(n, d, 1, 0, dev, strip_len, 0, weighting)
         lay, dims = ctx.layout, ctx.dims
         inp, keep = make_inputs(z1, z2, joints1, joints2)
         ws = torch.empty(int(lay.ws_bytes), dtype=torch.uint8, device=dev)
@@ -248,14 +270,15 @@ class _WeightedNTXentFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, z1, z2, joints1, joints2, temperature, engine, group, pos_weighted=True, neg_weighted=True):
+    def forward(ctx, z1, z2, joints1, joints2, temperature, engine, group, pos_weighted=True, neg_weighted=True,
+                weighting=None):
         want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         if group is None:
             loss, dz1, dz2 = run_step(z1, z2, joints1, joints2, temperature, engine, want,
-                                      pos_weighted=pos_weighted, neg_weighted=neg_weighted)
+                                      pos_weighted=pos_weighted, neg_weighted=neg_weighted, weighting=weighting)
         else:
-            if not (pos_weighted and neg_weighted):
-                raise NotImplementedError("the sharded path implements the pos_neg weighting only")
+            if not (pos_weighted and neg_weighted) or tuple(weighting or DEFAULT_WEIGHTING) != DEFAULT_WEIGHTING:
+                raise NotImplementedError("the sharded path implements linear / mpjpe / pos_neg weighting only")
             from .dist import run_step_sharded
             loss, dz1, dz2 = run_step_sharded(z1, z2, joints1, joints2, temperature, engine, want, group)
         if want:
@@ -268,31 +291,32 @@ class _WeightedNTXentFn(torch.autograd.Function):
         dz1, dz2 = ctx.saved_tensors
         g1 = grad_out * dz1 if ctx.needs_input_grad[0] else None
         g2 = grad_out * dz2 if ctx.needs_input_grad[1] else None
-        return g1, g2, None, None, None, None, None, None, None
+        return g1, g2, None, None, None, None, None, None, None, None
 
 
 def weighted_ntxent(z1: torch.Tensor, z2: torch.Tensor, joints1: torch.Tensor, joints2: torch.Tensor,
                     temperature: float = 0.5, group=None, engine: str = _DEFAULT_ENGINE,
-                    pos_weighted: bool = True, neg_weighted: bool = True) -> torch.Tensor:
+                    pos_weighted: bool = True, neg_weighted: bool = True, weighting=None) -> torch.Tensor:
     """Fused similarity-weighted NT-Xent (weight_type linear, diff_type mpjpe, pos_neg): equals
     `vanila_weights_contrastive_loss(z1, z2, *get_weights_linear(joints1, joints2, 'mpjpe'), temperature)`
     of the reference.  With `group` (a torch.distributed process group) the batch is the concatenation of
     every rank's local batch and the work is sharded over the ranks."""
     return _WeightedNTXentFn.apply(z1, z2, joints1, joints2, float(temperature), engine, group,
-                                   bool(pos_weighted), bool(neg_weighted))
+                                   bool(pos_weighted), bool(neg_weighted), weighting)
 
 
 # ----------------------------------------------------------------------------------------------------
 # the reference's two-call API
 # ----------------------------------------------------------------------------------------------------
 class _WeightSource:
-    def __init__(self, joints1, joints2):
+    def __init__(self, joints1, joints2, weighting=None):
         self.joints1, self.joints2 = joints1, joints2
+        self.weighting = tuple(weighting or DEFAULT_WEIGHTING)
         self._dense = None
 
     def dense(self):
         if self._dense is None:
-            self._dense = mpjpe_weights(self.joints1, self.joints2)
+            self._dense = mpjpe_weights(self.joints1, self.joints2, weighting=self.weighting)
         return self._dense
 
 
@@ -319,16 +343,17 @@ class LazyWeights:
         return f"LazyWeights(kind={self.kind!r}, shape={tuple(self.shape)})"
 
 
-def mpjpe_weights(joints1: torch.Tensor, joints2: torch.Tensor, strip_len: int = 0):
+def mpjpe_weights(joints1: torch.Tensor, joints2: torch.Tensor, strip_len: int = 0, weighting=None):
     """Materialised (pos_w [N], neg_w [2N, 2N]) exactly as `get_weights_linear(j1, j2, 'mpjpe')` returns
-    them, from the CUDA kernels (prep -> MPJPE tiles -> dense expansion)."""
+    them, from the CUDA kernels (prep -> MPJPE tiles -> dense expansion); `weighting` selects the other
+    diff_type / weight_type combinations of the reference."""
     _require_cuda(joints1, "joints1")
     _require_cuda(joints2, "joints2")
     lib = _lib.load()
     dev = joints1.device
     n = joints1.shape[0]
     with torch.cuda.device(dev):
-        ctx = get_context(n, 1, 1, 0, dev, strip_len)
+        ctx = get_context(n, 1, 1, 0, dev, strip_len, 0, weighting)
         zero = torch.zeros((n, 1), dtype=torch.float32, device=dev)
         inp, keep = make_inputs(zero, zero, joints1, joints2)
         ws = torch.empty(int(ctx.layout.ws_bytes), dtype=torch.uint8, device=dev)
@@ -345,13 +370,17 @@ def mpjpe_weights(joints1: torch.Tensor, joints2: torch.Tensor, strip_len: int =
 
 
 def get_weights_linear(joints1: torch.Tensor, joints2: torch.Tensor, diff_type: str):
-    """Drop-in for `src/models/utils.py:218` (`diff_type == 'mpjpe'`, the configuration of the hot path).
+    """Drop-in for `src/models/utils.py:218`: `diff_type` 'mpjpe' (the hot path; bit-exact weights), 'w_abs' or
+    'w_o_abs'.  Returns `(pos_weights, neg_weights)` as lazy handles."""
+    src = _WeightSource(joints1, joints2, make_weighting("linear", diff_type))
+    return LazyWeights(src, "pos"), LazyWeights(src, "neg")
+
+
+def get_weights_nonlinear(joints1: torch.Tensor, joints2: torch.Tensor, lambda_pos: float, lambda_neg: float,
+                          diff_type: str):
+    """Drop-in for `src/models/utils.py:304` (`weight_type == 'non_linear'`): W = 1 / (1 + exp(lambda (D - mean D))).
     Returns `(pos_weights, neg_weights)` as lazy handles."""
-    if diff_type != "mpjpe":
-        raise NotImplementedError(
-            f"simhand_b200.get_weights_linear: diff_type {diff_type!r} is outside the accelerated path "
-            "(only 'mpjpe'); keep the reference function for it")
-    src = _WeightSource(joints1, joints2)
+    src = _WeightSource(joints1, joints2, make_weighting("non_linear", diff_type, lambda_pos, lambda_neg))
     return LazyWeights(src, "pos"), LazyWeights(src, "neg")
 
 
@@ -364,7 +393,7 @@ def vanila_weights_contrastive_loss(z1: torch.Tensor, z2: torch.Tensor, pos_weig
         src = pos_weights._source
         if src.joints1.shape[0] != z1.shape[0]:
             raise ValueError(f"weights were built for batch {src.joints1.shape[0]}, z1 has {z1.shape[0]}")
-        return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine)
+        return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, weighting=src.weighting)
     if isinstance(pos_weights, LazyWeights):
         pos_weights = pos_weights.materialize()
     if isinstance(neg_weights, LazyWeights):
@@ -390,7 +419,7 @@ def vanila_pos_weights_contrastive_loss(z1, z2, pos_weights, temperature: float 
     src = _source_of(pos_weights, "pos")
     if src is None:
         return _DenseWeightedNTXentFn.apply(z1, z2, pos_weights, None, float(temperature), engine)
-    return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, True, False)
+    return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, True, False, src.weighting)
 
 
 def vanila_neg_weights_contrastive_loss(z1, z2, neg_weights, temperature: float = 0.5,
@@ -399,7 +428,7 @@ def vanila_neg_weights_contrastive_loss(z1, z2, neg_weights, temperature: float 
     src = _source_of(neg_weights, "neg")
     if src is None:
         return _DenseWeightedNTXentFn.apply(z1, z2, None, neg_weights, float(temperature), engine)
-    return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, False, True)
+    return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, False, True, src.weighting)
 
 
 def vanila_contrastive_loss(z1, z2, temperature: float = 0.5, engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
@@ -408,7 +437,7 @@ def vanila_contrastive_loss(z1, z2, temperature: float = 0.5, engine: str = _DEF
     return weighted_ntxent(z1, z2, zero, zero, temperature, None, engine, False, False)
 
 
-_DROP_INS = ("get_weights_linear", "vanila_weights_contrastive_loss", "vanila_pos_weights_contrastive_loss",
+_DROP_INS = ("get_weights_linear", "get_weights_nonlinear", "vanila_weights_contrastive_loss", "vanila_pos_weights_contrastive_loss",
              "vanila_neg_weights_contrastive_loss", "vanila_contrastive_loss")
 
 
