@@ -287,7 +287,7 @@ def run_ours(args):
                          h2d_bytes_per_step=int(hz1.numel() * 8 + hj1.numel() * 8), d2h_bytes_per_step=4,
                          loss=loss_e2e, api="simhand_b200.HostPipeline (double-buffered H2D, graph replay, loss D2H)"),
                 loss=loss_dev,
-                gpu_launches=(6 if world == 1 else 13) * args.steps)
+                gpu_launches=(6 if world == 1 else 14) * args.steps)
     if kernels is not None:
         f_clk = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
         xu_peak = NUM_SMS * MUFU_LANES_PER_SM * f_clk * 1e6 / 1e9          # G special-function ops / s

@@ -61,6 +61,14 @@ extern "C" {
 #define SMH_DENSE_WEIGHTS 0x2000 /* OR into smh_forward/backward's engine and smh_finalize's flags: the weights are the
                                   * materialised tensors handed to smh_import_weights (dims.flags has SMH_DIMS_DENSE_WEIGHTS) */
 
+/* Sharded finalize (peer exchange; OR into smh_finalize's flags): every rank evaluates the loss terms of its OWN rows only.
+ * LOSS_PART (after smh_backward, before the barrier that follows smh_exchange_dz): row terms of the local rows, their sum
+ * stored into slot `rank` of every peer's partial-loss array.  GRAD (after that barrier): gradients of the local rows and
+ * loss = rank-ordered sum of the partials / M.  Nothing reads the gathered inputs of other ranks after smh_prep, so the step
+ * needs no closing barrier. */
+#define SMH_FINALIZE_LOSS_PART 0x4000
+#define SMH_FINALIZE_GRAD 0x8000
+
 /* smh_dims_t.flags */
 #define SMH_DIMS_DENSE_WEIGHTS 1  /* materialised-weights path (the reference's two-call API with real tensors,
                                    * utils.py:391): every (I, J) tile is stored, nothing is assumed symmetric; world == 1 */

@@ -22,6 +22,8 @@ BACKWARD_RN_ONLY = 0x200
 UNIT_NEG_WEIGHTS = 0x400
 UNIT_POS_WEIGHTS = 0x800
 DENSE_WEIGHTS = 0x2000
+FINALIZE_LOSS_PART = 0x4000
+FINALIZE_GRAD = 0x8000
 DIMS_DENSE_WEIGHTS = 1
 DIMS_DENSE_BACKWARD = 2
 DIFF_TYPES = {"mpjpe": 0, "w_abs": 1, "w_o_abs": 2}

@@ -209,7 +209,8 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     lay->off_zh = take(mp * kD * 2);
     lay->off_jp = take(mp * kJP * 4);
     // partial buffers of the peer exchange (unused, and not allocated, on a single rank)
-    lay->off_negparts = take(dims.world > 1 ? (int64_t)dims.world * mp * 4 : 0);
+    // + 64 B tail: one partial loss per rank (sharded finalize)
+    lay->off_negparts = take(dims.world > 1 ? (int64_t)dims.world * mp * 4 + 64 : 0);
     lay->off_dzparts = take(dims.world > 1 ? (int64_t)m * kD * 4 : 0);
     lay->off_dist = take((int64_t)lay->n_stored_tiles * kTileFloats * 4);
     lay->ws_bytes = off;
@@ -266,6 +267,7 @@ static int make_peers(const smh_dims_t &dims, const smh_layout_t &lay, void *ws_
     out->off_dzacc = lay.off_dzacc;
     out->off_negparts = lay.off_negparts;
     out->off_dzparts = lay.off_dzparts;
+    out->off_lossparts = lay.off_negparts + (int64_t)dims.world * lay.tiles_per_side * kTile * 4;
     if (!exch) {
         out->world = 1;
         out->rank = 0;
@@ -505,6 +507,15 @@ int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, c
     bool local_block = dzacc_src_dev != nullptr;
     int n_parts = 1;
     if (!dzacc_src_dev) dzacc_src_dev = ws.dzacc;
+    Peers peers;
+    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
+    int phase = 0;
+    if (flags & (SMH_FINALIZE_LOSS_PART | SMH_FINALIZE_GRAD)) {
+        if (!exch) return set_error(SMH_E_ARG, "sharded finalize phases need the peer exchange");
+        if ((flags & SMH_FINALIZE_LOSS_PART) && (flags & SMH_FINALIZE_GRAD))
+            return set_error(SMH_E_ARG, "finalize: one phase per call");
+        phase = (flags & SMH_FINALIZE_LOSS_PART) ? 1 : 2;
+    }
     if (exch) {
         if (exch->world != dims->world) return set_error(SMH_E_DIM, "exchange world does not match dims");
         dzacc_src_dev = ws.dzparts;           // [world][2 n_local][128], summed in rank order
@@ -514,7 +525,7 @@ int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, c
     const int pos_mode = (flags & SMH_UNIT_POS_WEIGHTS) ? 1
                          : ((flags & SMH_DENSE_WEIGHTS) ? 2 : (dims->weight_type == SMH_WEIGHT_NONLINEAR ? 3 : 0));
     return launch_finalize(*dims, lay, *in, ws, dzacc_src_dev, local_block, n_parts, pos_mode,
-                           temperature, grad_scale, loss_dev, dz1_dev, dz2_dev, dz_row_stride, st);
+                           temperature, grad_scale, loss_dev, dz1_dev, dz2_dev, dz_row_stride, phase, peers, st);
 }
 
 int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float *pos_w_dev,

@@ -41,13 +41,16 @@ __device__ __forceinline__ const float *sample_ptr_f(const float *base, int k, i
     return base + (int64_t)(k / n_local) * rank_stride + (int64_t)(k % n_local) * row_stride;
 }
 
+// phase 0: every row (single rank, NCCL transport).  Sharded finalize of the peer exchange: phase 1 evaluates the loss
+// terms of this rank's own rows and stores their sum into slot `rank` of every peer's partial-loss array; phase 2 (after
+// the barrier) writes the gradients of the own rows and combines the partial losses in rank order.
 __global__ void __launch_bounds__(256)
 finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict__ neg,
                 const float *__restrict__ posd, float *__restrict__ rowloss, Stats *__restrict__ stats,
                 const float *__restrict__ dzacc_src, int64_t src_row_offset, int n_parts, int64_t part_stride,
                 int pos_mode, float lambda_pos, float inv_tau, float grad_scale,
                 float *__restrict__ loss_out, float *__restrict__ dz1, float *__restrict__ dz2,
-                int64_t dz_row_stride)
+                int64_t dz_row_stride, int phase, Peers peers)
 {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
@@ -74,20 +77,35 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
         __syncthreads();
     }
     const float pos_mean = pos_mode == 3 ? pos_mean_s : 0.f;
+    // rows this launch walks: all M, or the 2 * n_local rows of this rank (idx -> view v, sample k)
+    const int rows = phase == 0 ? m : 2 * n_local;
+    auto row_of = [&](int idx) { return phase == 0 ? idx : (idx / n_local) * n + k_lo + idx % n_local; };
 
-    for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < m; row += gridDim.x * warps_per_block) {
+    if (phase == 2 && blockIdx.x == 0 && threadIdx.x == 0) {
+        float total = 0.f;
+        for (int p = 0; p < peers.world; ++p) total += __ldcg(peers.lossparts(peers.rank) + p);       // rank order
+        float loss = total / (float)m;
+        if ((stats->flags & SMH_FLAG_NONFINITE) || stats->fail_site != 0u) loss = CUDART_NAN_F;
+        stats->loss = loss;
+        if (loss_out) *loss_out = loss;
+    }
+
+    for (int idx = blockIdx.x * warps_per_block + (threadIdx.x >> 5); idx < rows; idx += gridDim.x * warps_per_block) {
+        const int row = row_of(idx);
         const int v = row >= n ? 1 : 0;
         const int k = row - v * n;
         const float *zi = sample_ptr_f(v ? in.z2_dev : in.z1_dev, k, n_local, in.z_rank_stride, in.z_row_stride);
         const float *zp = sample_ptr_f(v ? in.z1_dev : in.z2_dev, k, n_local, in.z_rank_stride, in.z_row_stride);
-        float dot = 0.f;
-        for (int c = lane; c < d; c += 32) dot = fmaf(zi[c], zp[c], dot);
-        dot = warp_sum(dot);
         // utils.py:235; 1: unit weights; 2: posd holds the caller's materialised Wp (smh_import_weights)
         float wp = pos_mode == 1 ? 1.0f : (pos_mode == 2 ? posd[k] : __fdiv_rn(__fsub_rn(pmax, posd[k]), pden));
         if (pos_mode == 3) wp = __fdiv_rn(1.0f, 1.0f + expf(lambda_pos * (posd[k] - pos_mean)));
-        if (lane == 0) rowloss[row] = logf(neg[row]) - dot * wp * inv_tau;      // utils.py:420-426
-        if (dz1 != nullptr && k >= k_lo && k < k_hi) {
+        if (phase != 2) {
+            float dot = 0.f;
+            for (int c = lane; c < d; c += 32) dot = fmaf(zi[c], zp[c], dot);
+            dot = warp_sum(dot);
+            if (lane == 0) rowloss[row] = logf(neg[row]) - dot * wp * inv_tau;      // utils.py:420-426
+        }
+        if (phase != 1 && dz1 != nullptr && k >= k_lo && k < k_hi) {
             const float *src = dzacc_src + (dz_out_row(row, n, n_local) - src_row_offset) * kD;
             float *dst = (v ? dz2 : dz1) + (int64_t)(k - k_lo) * dz_row_stride;
             const float two_wp = 2.f * wp;
@@ -98,6 +116,7 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
             }
         }
     }
+    if (phase == 2) return;
 
     // last block reduces the per-row terms in a fixed order (deterministic loss)
     __shared__ bool is_last;
@@ -112,7 +131,7 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
     if (!is_last) return;
     __threadfence();
     float acc = 0.f;
-    for (int i = threadIdx.x; i < m; i += 256) acc += __ldcg(rowloss + i);
+    for (int i = threadIdx.x; i < rows; i += 256) acc += __ldcg(rowloss + row_of(i));
     part[threadIdx.x] = acc;
     __syncthreads();
     for (int s2 = 128; s2 > 0; s2 >>= 1) {
@@ -120,10 +139,16 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
         __syncthreads();
     }
     if (threadIdx.x == 0) {
+        stats->counter = 0u;
+        if (phase == 1) {
+            // all-gather of the partial sums: one 4-byte store per peer
+            for (int p = 0; p < peers.world; ++p) peers.lossparts(p)[peers.rank] = part[0];
+            __threadfence_system();
+            return;
+        }
         float loss = part[0] / (float)m;
         if ((stats->flags & SMH_FLAG_NONFINITE) || stats->fail_site != 0u) loss = CUDART_NAN_F;
         stats->loss = loss;
-        stats->counter = 0u;
         if (loss_out) *loss_out = loss;
     }
 }
@@ -131,10 +156,12 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
                     const float *dzacc_src, bool local_block, int n_parts, int pos_mode, float temperature,
                     float grad_scale,
-                    float *loss, float *dz1, float *dz2, int64_t dz_row_stride, cudaStream_t stream)
+                    float *loss, float *dz1, float *dz2, int64_t dz_row_stride, int phase, const Peers &peers,
+                    cudaStream_t stream)
 {
-    const int blocks = (lay.m + 7) / 8 < 1184 ? (lay.m + 7) / 8 : 1184;
     const int n_local = dims.n / dims.world;
+    const int rows = phase == 0 ? lay.m : 2 * n_local;
+    const int blocks = (rows + 7) / 8 < 1184 ? (rows + 7) / 8 : 1184;
     // a rank-local block (reduce-scattered buffer or peer-exchange accumulator) starts at this rank's first row
     const int64_t src_off = local_block ? (int64_t)dims.rank * 2 * n_local : 0;
     smh_inputs_t inp = in;
@@ -142,7 +169,7 @@ int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_i
     finalize_kernel<<<blocks, 256, 0, stream>>>(inp, dims.n, dims.d, dims.rank, ws.neg, ws.posd, ws.rowloss,
                                                 (Stats *)ws.stats, dzacc_src, src_off, n_parts,
                                                 (int64_t)2 * n_local * kD, pos_mode, dims.lambda_pos, 1.0f / temperature, grad_scale, loss, dz1,
-                                                dz2, dz_row_stride);
+                                                dz2, dz_row_stride, phase, peers);
     return check_launch("finalize_kernel");
 }
 

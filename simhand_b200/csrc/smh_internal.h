@@ -54,7 +54,8 @@ int launch_import_weights(const smh_dims_t &dims, const smh_layout_t &lay, const
 int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
                     const float *dzacc_src, bool local_block, int n_parts, int pos_mode /* 0 fused, 1 unit, 2 given */, float temperature, float grad_scale, float *loss,
                     float *dz1,
-                    float *dz2, int64_t dz_row_stride, cudaStream_t stream);
+                    float *dz2, int64_t dz_row_stride, int phase /* 0 whole, 1 local loss part, 2 local grad + loss */,
+                    const Peers &peers, cudaStream_t stream);
 int launch_weights_dense(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
                          float *pos_w, float *neg_w, cudaStream_t stream);
 int launch_l2norm_fwd(const float *x, float *y, float *norm, int64_t rows, int d, float eps, cudaStream_t stream);

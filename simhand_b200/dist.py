@@ -148,20 +148,26 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
         check(lib.smh_barrier(px, st), "smh_barrier")
         loss = torch.empty((), dtype=torch.float32, device=dev)
         dz1 = dz2 = None
+        fin = lambda flags: check(lib.smh_finalize(pd, pi, ws.data_ptr(), None, temperature, grad_scale,      # noqa: E731
+                                                   loss.data_ptr(), dz1.data_ptr() if want_grad else None,
+                                                   dz2.data_ptr() if want_grad else None, d, flags, px, st),
+                                  "smh_finalize")
         if want_grad:
-            check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng, px, st), "smh_backward")
-            check(lib.smh_exchange_dz(pd, ws.data_ptr(), px, st), "smh_exchange_dz")
-            check(lib.smh_barrier(px, st), "smh_barrier")
             dz1 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
             dz2 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
+            check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng, px, st), "smh_backward")
+            # sharded finalize, first half: loss terms of the own rows, partial sum stored into every peer
+            fin(_lib.FINALIZE_LOSS_PART)
+            check(lib.smh_exchange_dz(pd, ws.data_ptr(), px, st), "smh_exchange_dz")
         else:
             # the loss needs the summed row sums: same reduction the backward's first kernel would do
             check(lib.smh_backward(pd, plan, ws.data_ptr(), temperature, eng | _lib.BACKWARD_RN_ONLY, px, st), "smh_rn")
-        check(lib.smh_finalize(pd, pi, ws.data_ptr(), None, temperature, grad_scale,
-                               loss.data_ptr(), dz1.data_ptr() if want_grad else None,
-                               dz2.data_ptr() if want_grad else None, d, 0, px, st), "smh_finalize")
-        # the next step's push may overwrite xin while a slow peer still reads it in finalize: close the step
+            fin(_lib.FINALIZE_LOSS_PART)
         check(lib.smh_barrier(px, st), "smh_barrier")
+        # second half: gradients of the own rows, loss = rank-ordered sum of the partials.  No closing barrier: after
+        # smh_prep nothing reads another rank's slot of the gathered inputs, and every cross-rank store of this step
+        # precedes the barrier above, so the next step's push cannot race with this one.
+        fin(_lib.FINALIZE_GRAD)
     return loss, dz1, dz2
 
 

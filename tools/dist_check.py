@@ -38,6 +38,33 @@ def main():
     ok = e_loss < 2e-6 and e1 < 1e-4 and e2 < 1e-4
     print(f"rank {rank}/{world}: n={n} transport={transport} sharded loss {float(loss):.7f} single {float(full_loss):.7f} rel {e_loss:.1e} "
           f"grad err {e1:.1e} {e2:.1e} -> {'OK' if ok else 'MISMATCH'}", flush=True)
+    # Back-to-back steps on alternating batches with rank-dependent delays between them: the step has no closing barrier,
+    # so a fast rank starts pushing batch k+1 while a slow one still finishes batch k.  Every step must still equal the
+    # single-GPU result of ITS batch, and the loss-only path must agree with the loss of the gradient path.
+    if transport != "nccl":
+        y1, y2, k1, k2 = synth.make_batch(n, 128, 29, "uniform")
+        batches = [(z1, z2, j1, j2), (y1, y2, k1, k2)]
+        refs = [ops.run_step(p.to(dev), q.to(dev), r.to(dev)[:, :, :2], s_.to(dev)[:, :, :2], 0.5, "tf32", True)
+                for p, q, r, s_ in batches]
+        local = [(p[sl].to(dev), q[sl].to(dev), r[sl].to(dev)[:, :, :2], s_[sl].to(dev)[:, :, :2]) for p, q, r, s_ in batches]
+        outs = []
+        for step in range(24):
+            if (step + rank) % 3 == 0:
+                torch.cuda._sleep(2_000_000 * (1 + (step * 7 + rank * 3) % 4))      # ~1-4 ms of skew on this rank
+            outs.append(run_step_sharded(*local[step % 2], 0.5, "tf32", True, dist.group.WORLD, transport=transport))
+        loss_only, _, _ = run_step_sharded(*local[1], 0.5, "tf32", False, dist.group.WORLD, transport=transport)
+        torch.cuda.synchronize()
+        worst = 0.0
+        for step, (l, g1, g2) in enumerate(outs):
+            rl, r1, r2 = refs[step % 2]
+            sc = float(r1.abs().max())
+            worst = max(worst, abs(float(l) - float(rl)) / abs(float(rl)), float((g1 - r1[sl]).abs().max()) / sc * 1e-2,
+                        float((g2 - r2[sl]).abs().max()) / sc * 1e-2)
+        worst = max(worst, abs(float(loss_only) - float(refs[1][0])) / abs(float(refs[1][0])))
+        ok2 = worst < 2e-6
+        print(f"rank {rank}/{world}: 24 skewed back-to-back steps + loss-only step: worst scaled error {worst:.1e} -> "
+              f"{'PASS' if ok2 else 'MISMATCH'}", flush=True)
+        ok = ok and ok2
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
