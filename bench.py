@@ -145,7 +145,7 @@ def run_reference(args):
                                   sample=base["sample"]),
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -312,7 +312,7 @@ def run_ours(args):
         line["kernels_ms"] = kernels
         line["peaks"] = peaks
         line["cpu_baseline"] = cpu_port_sample(rows=128, repeats=3, warmup=1)
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -354,7 +354,25 @@ def time_kernels(ops, _lib, z1, z2, j1, j2, engine, iters):
     return {k: v / iters for k, v in acc.items()}
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Native libraries (NCCL's version banner) write to fd 1: route everything but the one JSON line to stderr."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    sys.stdout.flush()
+    payload = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, payload)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
