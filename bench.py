@@ -35,6 +35,27 @@ MUFU_LANES_PER_SM = 16
 NUM_SMS = 148
 
 
+def _ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` per launch, from the newest committed ncu summary under
+    profiles/ (tools/ncu_summary.py output of a `ncu --set full` capture of this same command); None if absent."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_summary*.txt")), key=os.path.getmtime)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in reversed(files):
+        total, inside, found = 0.0, False, 0
+        for ln in open(path, errors="replace"):
+            if ln.startswith("----"):
+                inside = kernel in ln
+            m = re.match(r"\s+dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", ln)
+            if inside and m and m.group(3) in scale:
+                total += float(m.group(2)) * scale[m.group(3)]
+                found += 1
+        if found >= 2:
+            return dict(bytes=total, source=os.path.relpath(path, ROOT))
+    return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -293,11 +314,13 @@ def run_ours(args):
         xu_peak = NUM_SMS * MUFU_LANES_PER_SM * f_clk * 1e6 / 1e9          # G special-function ops / s
         t_mpjpe = kernels["mpjpe_kernel"] * 1e-3
         tiles = (m // 128) * (m // 128 + 1) // 2                          # stored (upper-triangular) MPJPE tiles
+        traffic = _ncu_traffic("mpjpe_kernel")
         executed = 21.0 * tiles * 128 * 128 / t_mpjpe / 1e9              # sqrt the launch evaluates / its duration
         line["roofline"] = dict(
             kernel="mpjpe_kernel", bound="xu (MUFU pipe; neither HBM nor tensor binds this path, SURVEY.md 8d)",
             achieved=executed, peak=xu_peak, unit="Gop/s (correctly rounded sqrt: 21 per pair the launch evaluates)",
-            frac=executed / xu_peak, traffic=None,
+            frac=executed / xu_peak, traffic=(traffic or {}).get("bytes"),
+            traffic_source=(traffic or {}).get("source"),
             peak_source=f"148 SMs x 16 MUFU lanes/clk x {f_clk:.0f} MHz (median SM clock under load)",
             units_per_launch=f"{tiles} tiles x 16384 unordered pairs (symmetry: D_ij == D_ji bitwise)",
             algorithmic_frac=(21.0 * m * m / t_mpjpe / 1e9) / xu_peak,
