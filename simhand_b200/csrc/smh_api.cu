@@ -416,7 +416,7 @@ int smh_prep(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, int e
         cudaError_t e = cudaMemsetAsync(ws.stats, 0, (size_t)(lay.off_posd - lay.off_stats), st);
         if (e != cudaSuccess) return set_error((int)e, "prep memset: %s", cudaGetErrorString(e));
     }
-    return launch_prep(*dims, lay, *in, ws, engine == SMH_ENGINE_TC_TF32, st);      // dims carries diff_type
+    return launch_prep(*dims, lay, *in, ws, engine, st);      // dims carries diff_type
 }
 
 int smh_prep_zero(const smh_dims_t *dims, void *ws_dev, void *stream)

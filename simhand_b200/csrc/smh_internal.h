@@ -37,7 +37,7 @@ int check_launch(const char *what);
 
 // kernel launchers (one per translation unit)
 int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
-                bool round_tf32, cudaStream_t stream);
+                int engine, cudaStream_t stream);
 int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
                  const Peers &peers, cudaStream_t stream);
 int launch_sweep_fp32(bool backward, int wmode /* 0 fused, 1 unit, 2 materialised */, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,

@@ -22,7 +22,7 @@ __device__ __forceinline__ const float *sample_ptr(const float *base, int k, int
     return base + (int64_t)(k / n_local) * rank_stride + (int64_t)(k % n_local) * row_stride;
 }
 
-__global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d, int mp, bool round_tf32, int diff,
+__global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d, int mp, bool round_tf32, int diff, int images,
                                                    float *__restrict__ zt, uint16_t *__restrict__ zb,
                                                    uint16_t *__restrict__ zh,
                                                    float *__restrict__ jp, float *__restrict__ posd,
@@ -63,11 +63,14 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
                 jy = jb[in.j_coord_stride];
             }
         }
-        *reinterpret_cast<float4 *>(zt + zt_index(row, 4 * lane)) = zv;
+        // only the images the selected engine stages are written (bit 0: fp32/tf32, 1: bf16, 2: fp16)
+        if (images & 1) *reinterpret_cast<float4 *>(zt + zt_index(row, 4 * lane)) = zv;
         // bf16 copy (value operand of dz += G z): 4 consecutive columns = 8 bytes inside one 16-byte chunk
-        *reinterpret_cast<uint2 *>(zb + zb_index(row, 4 * lane)) = make_uint2(pack_bf16x2(zv.x, zv.y), pack_bf16x2(zv.z, zv.w));
+        if (images & 2)
+            *reinterpret_cast<uint2 *>(zb + zb_index(row, 4 * lane)) = make_uint2(pack_bf16x2(zv.x, zv.y), pack_bf16x2(zv.z, zv.w));
         // fp16 copy, same layout: 11-bit significand = the precision of tf32 for |z| <= 1 (forward logit operand)
-        *reinterpret_cast<uint2 *>(zh + zb_index(row, 4 * lane)) = make_uint2(pack_f16x2(zv.x, zv.y), pack_f16x2(zv.z, zv.w));
+        if (images & 4)
+            *reinterpret_cast<uint2 *>(zh + zb_index(row, 4 * lane)) = make_uint2(pack_f16x2(zv.x, zv.y), pack_f16x2(zv.z, zv.w));
 
         // packed joints
         float *jrow = jp + (int64_t)row * kJP;
@@ -142,11 +145,15 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
 }
 
 int launch_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
-                bool round_tf32, cudaStream_t stream)
+                int engine, cudaStream_t stream)
 {
+    const bool round_tf32 = engine == SMH_ENGINE_TC_TF32;
+    // fp32 engine: the fp32 image only; tensor-core engines: bf16 (backward, and the bf16 forward) + their forward image
+    const int images = engine == SMH_ENGINE_FP32 ? 1 : (2 | (engine == SMH_ENGINE_TC_TF32 ? 1 : 0) |
+                                                         (engine == SMH_ENGINE_TC_FP16 ? 4 : 0));
     const int mp = lay.tiles_per_side * kTile;
     const int blocks = (mp + 7) / 8;
-    prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, dims.diff_type, ws.zt, ws.zb, ws.zh, ws.jp, ws.posd, (Stats *)ws.stats);
+    prep_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, mp, round_tf32, dims.diff_type, images, ws.zt, ws.zb, ws.zh, ws.jp, ws.posd, (Stats *)ws.stats);
     return check_launch("prep_kernel");
 }
 
