@@ -41,7 +41,7 @@ def main():
     pd, pi, plan = ctypes.byref(dims), ctypes.byref(inp), ctx.plan_dev.data_ptr()
     loss = torch.empty((), device=dev)
     g1, g2 = torch.empty((n_local, 128), device=dev), torch.empty((n_local, 128), device=dev)
-    eng = 0
+    eng = _lib.ENGINES["fp16"]
     dz_src = ws.data_ptr() + int(lay.off_dzacc)
     calls = [
         ("push", lambda: lib.smh_push_inputs(px, ctypes.byref(local_in), n_local, 128, st)),
@@ -54,11 +54,12 @@ def main():
         ("xneg", lambda: lib.smh_exchange_neg(pd, ws.data_ptr(), px, st)),
         ("barrier3", lambda: lib.smh_barrier(px, st)),
         ("bwd", lambda: lib.smh_backward(pd, plan, ws.data_ptr(), 0.5, eng, px, st)),
+        ("fin_loss", lambda: lib.smh_finalize(pd, pi, ws.data_ptr(), None, 0.5, 1.0, loss.data_ptr(), g1.data_ptr(),
+                                              g2.data_ptr(), 128, _lib.FINALIZE_LOSS_PART, px, st)),
         ("xdz", lambda: lib.smh_exchange_dz(pd, ws.data_ptr(), px, st)),
         ("barrier4", lambda: lib.smh_barrier(px, st)),
-        ("finalize", lambda: lib.smh_finalize(pd, pi, ws.data_ptr(), None, 0.5, 1.0, loss.data_ptr(), g1.data_ptr(),
-                                              g2.data_ptr(), 128, 0, px, st)),
-        ("barrier5", lambda: lib.smh_barrier(px, st)),
+        ("fin_grad", lambda: lib.smh_finalize(pd, pi, ws.data_ptr(), None, 0.5, 1.0, loss.data_ptr(), g1.data_ptr(),
+                                              g2.data_ptr(), 128, _lib.FINALIZE_GRAD, px, st)),
     ]
     iters = 20
     acc = {k: 0.0 for k, _ in calls}
