@@ -305,7 +305,8 @@ def run_ours(args):
                                "no explicit flush"),
                 clocks=clocks,
                 e2e=dict(value=1e3 / (ms_e2e / args.steps), unit=UNIT,
-                         h2d_bytes_per_step=int(hz1.numel() * 8 + hj1.numel() * 8), d2h_bytes_per_step=4,
+                         h2d_bytes_per_step=int(hz1.numel() * 8 + hj1.numel() * 8) * world, d2h_bytes_per_step=4 * world,
+                         bytes_scope="whole job (sum over ranks; every rank copies its own shard and reads the loss)",
                          loss=loss_e2e, api="simhand_b200.HostPipeline (double-buffered H2D, graph replay, loss D2H)"),
                 loss=loss_dev,
                 gpu_launches=(6 if world == 1 else 14) * args.steps)
