@@ -330,7 +330,8 @@ def run_ours(args):
                  "reference evaluates them) over the same launch time and step_frac is SURVEY 8d's figure, "
                  "(21 sqrt + 1 exp) M^2 / whole step time over the MUFU peak: both exceed frac because symmetry "
                  "halves the executed count.  The FMA pipe is co-critical (ncu: fma 66 %, xu 65 % busy).")
-        hbm_bytes = 8256 * 65536.0 * 2          # each stored tile is read direct + transposed
+        tile_bytes = 32768.0 if ops.step_flags(engine) else 65536.0      # 16-bit image of the tiles, or fp32
+        hbm_bytes = 8256 * tile_bytes * 2          # each stored tile is read direct + transposed
         for k in ("sweep_fwd", "sweep_bwd"):
             kernels[k + "_hbm_frac"] = hbm_bytes / (kernels[k] * 1e-3) / 1e9 / peaks["hbm_gbs"]
         line["kernels_ms"] = kernels
@@ -348,7 +349,7 @@ def time_kernels(ops, _lib, z1, z2, j1, j2, engine, iters):
     eng = _lib.ENGINES[engine]
     dev = z1.device
     n, d = z1.shape
-    ctx = ops.get_context(n, d, 1, 0, dev)
+    ctx = ops.get_context(n, d, 1, 0, dev, 0, ops.step_flags(engine))
     inp, keep = ops.make_inputs(z1, z2, j1[:, :, :2], j2[:, :, :2])
     ws = torch.empty(int(ctx.layout.ws_bytes), dtype=torch.uint8, device=dev)
     loss = torch.empty((), device=dev)

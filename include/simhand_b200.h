@@ -72,6 +72,11 @@ extern "C" {
 /* smh_dims_t.flags */
 #define SMH_DIMS_DENSE_WEIGHTS 1  /* materialised-weights path (the reference's two-call API with real tensors,
                                    * utils.py:391): every (I, J) tile is stored, nothing is assumed symmetric; world == 1 */
+#define SMH_DIMS_Q16_TILES 4      /* tensor-core engines, linear / mpjpe weighting: the distance tiles are stored as 16-bit
+                                   * fixed point q = round(D * 65000 / Dbound), Dbound = 2 max_i D(i, 0) >= Dmax (triangle
+                                   * inequality), which halves the bytes the sweeps stage per tile.  |W error| <= 1.6e-5, far
+                                   * below the 2^-11 operand rounding of the logits.  Dmax itself stays exact.  The fp32
+                                   * engine, smh_weights_dense and the other weightings need the fp32 tiles (flag clear). */
 #define SMH_DIMS_DENSE_BACKWARD 2 /* with SMH_DIMS_DENSE_WEIGHTS: the task list of the backward sweep, which visits every
                                    * tile twice (W_ij for the row term, W_ji read transposed for the column term).  Same
                                    * layout as the forward list: one workspace, two plans. */
@@ -136,6 +141,8 @@ typedef struct smh_stats {
     uint32_t fail_site;          /* != 0: a bounded pipeline wait timed out (result invalid) */
     uint32_t ticket2;            /* internal: last-block-done ticket of the MPJPE kernel (peer exchange) */
     double dsum;                 /* non_linear weights: sum_ij D_ij over all ordered pairs (mean = dsum / M^2, utils.py:345) */
+    uint32_t dbound_bits;        /* float bits of max_i D(i, 0): 2x this bounds every D_ij (SMH_DIMS_Q16_TILES scale) */
+    uint32_t reserved;
 } smh_stats_t;
 
 #define SMH_FLAG_SLOW_DOMAIN 1u  /* joints outside the fast exact-sqrt domain: IEEE slow path used */

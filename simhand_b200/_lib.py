@@ -26,6 +26,7 @@ FINALIZE_LOSS_PART = 0x4000
 FINALIZE_GRAD = 0x8000
 DIMS_DENSE_WEIGHTS = 1
 DIMS_DENSE_BACKWARD = 2
+DIMS_Q16_TILES = 4
 DIFF_TYPES = {"mpjpe": 0, "w_abs": 1, "w_o_abs": 2}
 WEIGHT_TYPES = {"linear": 0, "non_linear": 1}
 FLAG_SLOW_DOMAIN = 1
@@ -70,7 +71,8 @@ class Exchange(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("dmax_bits", ctypes.c_uint32), ("pmax_bits", ctypes.c_uint32), ("pmin_inv", ctypes.c_uint32),
                 ("flags", ctypes.c_uint32), ("loss", ctypes.c_float), ("counter", ctypes.c_uint32),
-                ("fail_site", ctypes.c_uint32), ("ticket2", ctypes.c_uint32), ("dsum", ctypes.c_double)]
+                ("fail_site", ctypes.c_uint32), ("ticket2", ctypes.c_uint32), ("dsum", ctypes.c_double),
+                ("dbound_bits", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 # every symbol include/simhand_b200.h declares (tests check that the library exports all of them)

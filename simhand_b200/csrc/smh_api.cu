@@ -44,12 +44,15 @@ static int validate_dims(const smh_dims_t *dims)
     if (dims->n % dims->world != 0)
         return set_error(SMH_E_DIM, "n (%d) must be a multiple of world (%d)", dims->n, dims->world);
     if ((int64_t)dims->n * 2 > (1 << 22)) return set_error(SMH_E_DIM, "2N too large (%d)", dims->n * 2);
-    if (dims->flags & ~(SMH_DIMS_DENSE_WEIGHTS | SMH_DIMS_DENSE_BACKWARD))
+    if (dims->flags & ~(SMH_DIMS_DENSE_WEIGHTS | SMH_DIMS_DENSE_BACKWARD | SMH_DIMS_Q16_TILES))
         return set_error(SMH_E_ARG, "unknown dims.flags 0x%x", dims->flags);
     if ((dims->flags & SMH_DIMS_DENSE_BACKWARD) && !(dims->flags & SMH_DIMS_DENSE_WEIGHTS))
         return set_error(SMH_E_ARG, "SMH_DIMS_DENSE_BACKWARD needs SMH_DIMS_DENSE_WEIGHTS");
     if ((dims->flags & SMH_DIMS_DENSE_WEIGHTS) && dims->world != 1)
         return set_error(SMH_E_DIM, "the materialised-weights path is single-rank (world == 1)");
+    if ((dims->flags & SMH_DIMS_Q16_TILES) &&
+        ((dims->flags & SMH_DIMS_DENSE_WEIGHTS) || dims->diff_type != SMH_DIFF_MPJPE || dims->weight_type != SMH_WEIGHT_LINEAR))
+        return set_error(SMH_E_MODE, "SMH_DIMS_Q16_TILES: only with linear / mpjpe weights built from the joints");
     if (dims->diff_type < SMH_DIFF_MPJPE || dims->diff_type > SMH_DIFF_W_O_ABS)
         return set_error(SMH_E_MODE, "unknown diff_type %d", dims->diff_type);
     if (dims->weight_type != SMH_WEIGHT_LINEAR && dims->weight_type != SMH_WEIGHT_NONLINEAR)
@@ -127,11 +130,11 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
     // maximal run of tasks with the same row block (the accumulators are flushed at its end).  When all stored tiles
     // of the rank fit in L2 anyway (sharded runs), plain (row block, column) order gives the longest strips.
     {
-        // super-block edge: a rank's share of one super-tile pair (2 sbk^2 / world tiles of 64 KiB) stays ~32 MB
+        // super-block edge: a rank's share of one super-tile pair (2 sbk^2 / world tiles) stays ~32 MB
+        const long long tile_bytes = (long long)kTileFloats * ((dims.flags & SMH_DIMS_Q16_TILES) ? 2 : 4);
         int sbk = 16;
-        if (dims.world == 2) sbk = 22;
-        if (dims.world >= 3) sbk = 32;
-        if ((long long)tiles.size() * kTileFloats * 4 <= (96ll << 20)) sbk = 4096;
+        while ((long long)2 * (sbk + 1) * (sbk + 1) * tile_bytes <= (32ll << 20) * dims.world) ++sbk;
+        if ((long long)tiles.size() * tile_bytes <= (96ll << 20)) sbk = 4096;
         if (dense) sbk = 4096;                 // every tile is read once per visit type: longest strips
         auto key = [&](const int4 &t) {
             long long a = t.x / sbk, b = (t.y / 2) / sbk;
@@ -212,7 +215,7 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     // + 64 B tail: one partial loss per rank (sharded finalize)
     lay->off_negparts = take(dims.world > 1 ? (int64_t)dims.world * mp * 4 + 64 : 0);
     lay->off_dzparts = take(dims.world > 1 ? (int64_t)m * kD * 4 : 0);
-    lay->off_dist = take((int64_t)lay->n_stored_tiles * kTileFloats * 4);
+    lay->off_dist = take((int64_t)lay->n_stored_tiles * kTileFloats * ((dims.flags & SMH_DIMS_Q16_TILES) ? 2 : 4));
     lay->ws_bytes = off;
     lay->plan_bytes = align_up((int64_t)sizeof(PlanHeader), 16) + align_up((int64_t)lay->n_stored_tiles * 8, 16) +
                       (int64_t)lay->n_tasks * 16 + align_up((int64_t)lay->n_strips * 8, 16) +
@@ -468,6 +471,8 @@ int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, floa
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16 || engine == SMH_ENGINE_TC_FP16)
         return launch_sweep_tc(false, engine == SMH_ENGINE_TC_TF32 ? 0 : (engine == SMH_ENGINE_TC_BF16 ? 1 : 2), wmode,
                                *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_FP32 && (dims->flags & SMH_DIMS_Q16_TILES))
+        return set_error(SMH_E_MODE, "the fp32 engine reads fp32 distance tiles (clear SMH_DIMS_Q16_TILES)");
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, wmode, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
@@ -488,6 +493,8 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
     engine &= 0xff;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16 || engine == SMH_ENGINE_TC_FP16)
         return launch_sweep_tc(true, 1, wmode, *dims, lay, pv, ws, peers, temperature, st);
+    if (engine == SMH_ENGINE_FP32 && (dims->flags & SMH_DIMS_Q16_TILES))
+        return set_error(SMH_E_MODE, "the fp32 engine reads fp32 distance tiles (clear SMH_DIMS_Q16_TILES)");
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, wmode, *dims, lay, pv, ws, peers, temperature, st);
     return set_error(SMH_E_MODE, "unknown engine %d", engine);
 }
@@ -533,6 +540,7 @@ int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev
 {
     SMH_COMMON_PROLOGUE(true)
     if (dims->world != 1) return set_error(SMH_E_DIM, "smh_weights_dense needs world == 1");
+    if (dims->flags & SMH_DIMS_Q16_TILES) return set_error(SMH_E_MODE, "smh_weights_dense needs the fp32 tiles");
     if (!pos_w_dev && !neg_w_dev) return set_error(SMH_E_ARG, "no output requested");
     return launch_weights_dense(*dims, lay, carve_plan(plan_dev, lay), ws, pos_w_dev, neg_w_dev, st);
 }

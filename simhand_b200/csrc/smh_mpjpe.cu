@@ -64,10 +64,12 @@ __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10
 // MODE as in joint_pair.  vmax_bits: running maximum of the integer image of D (D >= 0; NaN is larger than any finite).
 // NCOLS: columns per thread (64: one CTA per stored tile; 32: one CTA per 64-column half).  col0: first column (inside
 // the tile) of this thread's run; cs holds the staged columns starting at tile column cs0.
-template <int MODE, int UN, int NCOLS>
-__device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, float *__restrict__ tile_out, int I,
+// Q16: the tile is stored as 16-bit fixed point q = round(D * qscale) (SMH_DIMS_Q16_TILES); the maximum is still taken on
+// the exact fp32 D.  The rounding to integer rides on the FMA pipe: fma(D, qscale, 2^23) has q in its low mantissa bits.
+template <int MODE, int UN, int NCOLS, bool Q16>
+__device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, void *__restrict__ tile_out, int I,
                                                 int J, int m, const float *cs, int cs0, int col0,
-                                                uint32_t &vmax_bits)
+                                                uint32_t &vmax_bits, float qscale)
 {
     const int r = threadIdx.x & 127;
     // this thread's row sample in registers
@@ -98,17 +100,28 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, fl
             if (row_ok && (c0 + u) < col_limit) vmax_bits = max(vmax_bits, __float_as_uint(dv[u]));
         }
 #pragma unroll
-        for (int u = 0; u < UN; u += 4)
-            *reinterpret_cast<float4 *>(tile_out + dist_index(r, c0 + u)) = make_float4(dv[u], dv[u + 1], dv[u + 2], dv[u + 3]);
+        for (int u = 0; u < UN; u += 4) {
+            if (Q16) {
+                uint32_t q[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) q[t] = __float_as_uint(__fmaf_rn(dv[u + t], qscale, 8388608.0f));
+                // low 16 bits of each: (q0 | q1 << 16, q2 | q3 << 16)
+                const uint2 pk = make_uint2(__byte_perm(q[0], q[1], 0x5410), __byte_perm(q[2], q[3], 0x5410));
+                *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(tile_out) + distq_index(r, c0 + u)) = pk;
+            } else {
+                *reinterpret_cast<float4 *>(reinterpret_cast<float *>(tile_out) + dist_index(r, c0 + u)) =
+                    make_float4(dv[u], dv[u + 1], dv[u + 2], dv[u + 3]);
+            }
+        }
     }
 }
 
 // HALF = false: one CTA per stored tile (thread = row x 64 columns).  HALF = true: one CTA per 64-column half of a
 // stored tile (thread = row x 32 columns) -- twice as many, half as long CTAs, used when a rank has few tiles (sharded
 // runs) so that the last wave of the 2-CTAs-per-SM grid is not mostly empty (1032 tiles = 3.5 waves -> 7.0 waves).
-template <bool HALF>
+template <bool HALF, bool Q16>
 __global__ void __launch_bounds__(256, 2)
-mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float *__restrict__ dist, int m,
+mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m,
              Stats *__restrict__ stats, Peers peers)
 {
     constexpr int kCols = HALF ? 64 : 128;            // columns staged per CTA
@@ -119,7 +132,8 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float
     const int cs0 = HALF ? (blockIdx.x & 1) * 64 : 0;
     const int col0 = cs0 + (threadIdx.x >> 7) * kPerThread;
     const int2 ij = tiles[tile_id];
-    float *tile_out = dist + (int64_t)tile_id * kTileFloats;
+    void *tile_out = reinterpret_cast<unsigned char *>(dist) + (int64_t)tile_id * kTileFloats * (Q16 ? 2 : 4);
+    const float qscale = Q16 ? q16_scale(__uint_as_float(stats->dbound_bits)) : 0.f;
     {
         const float4 *src = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.y * kTile + cs0) * kJP);
         float4 *dst = reinterpret_cast<float4 *>(cs);
@@ -130,11 +144,11 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float
     const bool slow = flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE);
     uint32_t vmax_bits = 0u;
     if (slow)
-        mpjpe_tile_body<0, 4, kPerThread>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits);
+        mpjpe_tile_body<0, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
     else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
-        mpjpe_tile_body<1, 4, kPerThread>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits);   // zero distances
+        mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);   // zero distances
     else
-        mpjpe_tile_body<2, 4, kPerThread>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits);
+        mpjpe_tile_body<2, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
     auto block_max = [&](uint32_t v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -150,7 +164,7 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float
     if (!slow && bmax > 0x7f800000u) {
         // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo it guarded
         vmax_bits = 0u;
-        mpjpe_tile_body<1, 4, kPerThread>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits);
+        mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
         bmax = block_max(vmax_bits);
     }
     if (threadIdx.x == 0) {
@@ -292,9 +306,15 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
             altdist_kernel<false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st);
     } else if (lay.n_stored_tiles < 8 * 2 * kNumCtas) {
         // fewer than ~8 waves of whole tiles (2 CTAs x 148 SMs per wave): cut the tiles in halves
-        mpjpe_kernel<true><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
+        if (dims.flags & SMH_DIMS_Q16_TILES)
+            mpjpe_kernel<true, true><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
+        else
+            mpjpe_kernel<true, false><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
     } else {
-        mpjpe_kernel<false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
+        if (dims.flags & SMH_DIMS_Q16_TILES)
+            mpjpe_kernel<false, true><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
+        else
+            mpjpe_kernel<false, false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
     }
     int rc = check_launch(dims.diff_type != SMH_DIFF_MPJPE ? "altdist_kernel" : "mpjpe_kernel");
     if (rc || dims.weight_type != SMH_WEIGHT_NONLINEAR) return rc;

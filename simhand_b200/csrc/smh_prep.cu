@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
     const int warps_per_block = blockDim.x >> 5;
     const int m = 2 * n;
     const bool has_joints = in.j1_dev != nullptr;         // optional on the materialised-weights path
+    uint32_t bound_bits = 0u;                             // running max of D(row, sample 0) over this warp's rows
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < mp; row += gridDim.x * warps_per_block) {
         float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
         float jx = 0.f, jy = 0.f;
@@ -102,6 +103,20 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
         bad |= __shfl_xor_sync(0xffffffffu, bad, 1);
         if (bad && lane == 0) atomicOr(&stats->flags, bad);
 
+        // D(row, sample 0): by the triangle inequality D_ij <= D_i0 + D_0j, so 2 max_i D_i0 bounds the whole matrix
+        // (scale of the 16-bit tile image, SMH_DIMS_Q16_TILES; any summation order will do)
+        if (has_joints && live) {
+            float nk = 0.f;
+            if (lane < kJ) {
+                const float *rb = sample_ptr(in.j1_dev, 0, in.n_local, in.j_rank_stride, in.j_sample_stride) +
+                                  (int64_t)lane * in.j_joint_stride;
+                const float ex = jx - rb[0], ey = jy - rb[in.j_coord_stride];
+                nk = sqrtf(fmaf(ey, ey, ex * ex));
+            }
+            const float d0 = warp_sum(nk) * (1.0f / 21.0f) * 1.0001f;        // + margin for the rounding of this sum
+            if (d0 >= 0.f && d0 <= 3.0e38f) bound_bits = max(bound_bits, __float_as_uint(d0));
+        }
+
         // positive pair (k, k + N): utils.py:229-231, IEEE sqrt/div (any domain), ATen summation order
         if (has_joints && row < n) {
             float dx = 0.f, dy = 0.f;
@@ -141,6 +156,15 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
                 }
             }
         }
+    }
+    // one atomic per block for the distance bound
+    __shared__ uint32_t wb[8];
+    if (lane == 0) wb[threadIdx.x >> 5] = bound_bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t v = wb[0];
+        for (int w = 1; w < warps_per_block; ++w) v = max(v, wb[w]);
+        if (v != 0u) atomicMax(&stats->dbound_bits, v);
     }
 }
 

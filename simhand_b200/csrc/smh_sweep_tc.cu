@@ -33,17 +33,18 @@ constexpr int kEpiWarps = kEpiGroups * kGroupWarps;      // 16
 constexpr int kTcThreads = 64 + 32 * kEpiWarps + 32;     // 608: tile producer, MMA, 16 epilogue, operand producer
 constexpr int kSBufs = 4;                                // S / G buffers in TMEM (64 columns each)
 constexpr int kMaxBStages = 4;                           // z blocks come from L2
-constexpr int kMaxDStages = 4;                           // MPJPE tile pieces come from HBM: deeper prefetch
-constexpr int kDBytes = 32768;                           // the half of a stored tile a task needs
-constexpr int kNumBars = 40;
+constexpr int kMaxDStages = 8;                           // MPJPE tile pieces come from HBM: deeper prefetch
+constexpr int kNumBars = 56;
 constexpr int kCtlBytes = kNumBars * 8 + kMaxDStages * 16 + 16;   // barriers, staged task records, TMEM base
 
-template <bool SBF16>
+// Q16: the distance tiles are the 16-bit image (SMH_DIMS_Q16_TILES): half the bytes per task, twice the stages in flight
+template <bool SBF16, bool Q16>
 struct TcCfg {
     static constexpr int kABytes = SBF16 ? kTile * kD * 2 : kTile * kD * 4;        // row block of z
     static constexpr int kBBytes = SBF16 ? kTaskN * kD * 2 : kTaskN * kD * 4;      // column block of z
     static constexpr int kBStages = SBF16 ? 4 : 2;
-    static constexpr int kDStages = SBF16 ? 4 : 3;
+    static constexpr int kDBytes = Q16 ? 16384 : 32768;                            // the half of a stored tile a task needs
+    static constexpr int kDStages = Q16 ? (SBF16 ? 8 : 4) : (SBF16 ? 4 : 3);
     static constexpr int kSmem = 1024 /*align slack*/ + kABytes + kBStages * kBBytes + kDStages * kDBytes + kCtlBytes;
     static_assert(kSmem <= 232448, "sweep exceeds the 227 KB shared-memory limit");
 };
@@ -66,6 +67,13 @@ __device__ __forceinline__ void lds_f2x2(uint32_t addr, f2 &a, f2 &b)
 {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
+// one 16-bit fixed-point distance as the float 2^23 + q (the caller subtracts 2^23)
+__device__ __forceinline__ float lds_q16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return __uint_as_float(v | 0x4B000000u);
+}
 __device__ __forceinline__ float lds_f32(uint32_t addr)
 {
     float v;
@@ -82,48 +90,86 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 // (the tile holds W itself): negc2 = k2, k2c2 = 0, and, W not being symmetric in general, the backward visits a tile
 // once for the row term (cs2 = 0: G = W_ij E_ij / neg_i) and once transposed for the column term (rni = 0, cs2 = 1:
 // G = W_ji E_ji / neg_j).
-template <bool BWD, bool TRANSPOSED, bool MASKED>
+// The 32 columns [chunk * 32, chunk * 32 + 32) of one task for one row; v[] holds S on entry.
+//   forward : rowsum += E,  E = 2^(S * wk),  wk = W * k2 = k2 - D * (k2 / Dmax)      (one FFMA per weight)
+//   backward: pk[] = bf16x2 of G' = wk * E * (1/neg_i + 1/neg_j) = k2 * G; the strip flush multiplies by 1 / k2
+// The tensor-core engines do not need the correctly rounded W of the fp32 engine (the logits carry 2^-11 operand
+// rounding): the fused form is within 1 ulp of k2 in absolute terms.  Packed f32x2 arithmetic throughout.
+// negc2 / k2c2: slope and offset of wk in the staged value.  Unit weights: slope 0 and the tile is not read.
+// Materialised weights (the tile holds W itself): slope k2, offset 0, and, W not being symmetric in general, the
+// backward visits a tile once for the row term (cs2 = 0: G = W_ij E_ij / neg_i) and once transposed for the column
+// term (rni = 0, cs2 = 1: G = W_ji E_ji / neg_j).  Q16: the staged tile is the 16-bit image (SMH_DIMS_Q16_TILES).
+// SIG: non_linear weights (utils.py:346), W = 1 / (1 + exp(lambda (D - mean D))).  A template parameter, not a run-time
+// flag: as a flag ptxas predicated the two extra MUFU per element into the linear path (backward sweep XU pipe 21 % ->
+// 70 % busy), and an out-of-line helper cost more in register traffic than it saved.
+// (Tried and not faster: computing all 32 weights before the wait on the S buffer -- the two-phase form overlaps the MMA
+// wait with the tile reads but gains nothing and spills in the backward sweep.)
+template <bool BWD, bool TRANSPOSED, bool MASKED, bool Q16, bool SIG>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t (&pk)[16], uint32_t dstage_s, int r,
                                                int chunk, int gi, int gj0, int m, bool diagonal, f2 negc2, f2 k2c2,
-                                               float rni, f2 cs2, bool no_tile, bool sigmoid, float k2,
+                                               float rni, f2 cs2, bool no_tile, float k2,
                                                const float *__restrict__ rn, f2 (&rowsum)[2])
 {
     uint32_t ta[8];                                   // transposed reads: one address per (row & 7) XOR pattern
     uint32_t dbase = 0, rx = 0;
     if (TRANSPOSED) {
-        const uint32_t c4 = (uint32_t)r >> 2, x = c4 & 7u;
-        const uint32_t base = dstage_s + c4 * 1024u + ((uint32_t)r & 3u) * 4u + (uint32_t)chunk * 512u;
+        // thread = stored column r: 16-byte slot (c, stored row ^ (c & 7)) with c = r / 4 (fp32) or r / 8 (16-bit image)
+        const uint32_t c = (uint32_t)r >> (Q16 ? 3 : 2), x = c & 7u;
+        const uint32_t sub = Q16 ? ((uint32_t)r & 7u) * 2u : ((uint32_t)r & 3u) * 4u;
+        const uint32_t base = dstage_s + c * 1024u + sub + (uint32_t)chunk * 512u;
 #pragma unroll
         for (uint32_t k = 0; k < 8; ++k) ta[k] = base + ((k ^ x) << 4);
     } else {
-        dbase = dstage_s + ((uint32_t)r >> 6) * 16384u + (uint32_t)chunk * 8192u;
+        // thread = row r; per 64-row half the staged piece holds 16 (fp32: 4 columns each) or 8 (16-bit: 8 columns each)
+        // column groups of 1 KiB; a 32-column chunk is 8 resp. 4 of them
+        dbase = dstage_s + ((uint32_t)r >> 6) * (Q16 ? 8192u : 16384u) + (uint32_t)chunk * (Q16 ? 4096u : 8192u);
         rx = ((uint32_t)r & 63u) << 4;
     }
     const f2 rni2 = pack2(rni, rni);
+    const f2 magic2 = pack2(8388608.0f, 8388608.0f);
+    f2 dnext01 = 0, dnext23 = 0;                      // 16-bit image: one 16-byte read serves two q steps
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const int jl = chunk * 32 + q * 4;                       // first of 4 columns inside the task
         f2 d01 = 0, d23 = 0;                                     // unit weights: the tile is never read (0.0f x2)
         if (no_tile) {
         } else if (!TRANSPOSED) {
-            // column group c4 = chunk * 8 + q of the staged half: its low 3 bits (q) drive the XOR
-            lds_f2x2(dbase + (uint32_t)q * 1024u + (rx ^ ((uint32_t)q << 4)), d01, d23);
+            if (!Q16) {
+                // column group c4 = chunk * 8 + q of the staged half: its low 3 bits (q) drive the XOR
+                lds_f2x2(dbase + (uint32_t)q * 1024u + (rx ^ ((uint32_t)q << 4)), d01, d23);
+            } else if ((q & 1) == 0) {
+                // column group c8 = chunk * 4 + q / 2: eight 16-bit values; 0x4B000000 | q is the float 2^23 + q
+                const uint32_t g = (uint32_t)(q >> 1), c8l = (uint32_t)chunk * 4u + g;
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                             : "r"(dbase + g * 1024u + (rx ^ ((c8l & 7u) << 4))));
+                d01 = sub2(pack2(__uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7610)),
+                                 __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7632))), magic2);
+                d23 = sub2(pack2(__uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7610)),
+                                 __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7632))), magic2);
+                dnext01 = sub2(pack2(__uint_as_float(__byte_perm(w2, 0x4B000000u, 0x7610)),
+                                     __uint_as_float(__byte_perm(w2, 0x4B000000u, 0x7632))), magic2);
+                dnext23 = sub2(pack2(__uint_as_float(__byte_perm(w3, 0x4B000000u, 0x7610)),
+                                     __uint_as_float(__byte_perm(w3, 0x4B000000u, 0x7632))), magic2);
+            } else {
+                d01 = dnext01;
+                d23 = dnext23;
+            }
         } else {
             const uint32_t off = (uint32_t)(q >> 1) * 128u;      // stored rows jl .. jl + 3: bits 3.. of the row index
             const int k0 = (q & 1) * 4;
-            d01 = pack2(lds_f32(ta[k0] + off), lds_f32(ta[k0 + 1] + off));
-            d23 = pack2(lds_f32(ta[k0 + 2] + off), lds_f32(ta[k0 + 3] + off));
-        }
-        f2 rs01 = 0, rs23 = 0;
-        if (BWD) {
-            const float4 rnj = __ldg(reinterpret_cast<const float4 *>(rn + gj0 + jl));
-            rs01 = fma2(pack2(rnj.x, rnj.y), cs2, rni2);        // cs = 1: 1/neg_i + 1/neg_j (exact, as an add)
-            rs23 = fma2(pack2(rnj.z, rnj.w), cs2, rni2);
+            if (!Q16) {
+                d01 = pack2(lds_f32(ta[k0] + off), lds_f32(ta[k0 + 1] + off));
+                d23 = pack2(lds_f32(ta[k0 + 2] + off), lds_f32(ta[k0 + 3] + off));
+            } else {
+                d01 = sub2(pack2(lds_q16(ta[k0] + off), lds_q16(ta[k0 + 1] + off)), magic2);
+                d23 = sub2(pack2(lds_q16(ta[k0 + 2] + off), lds_q16(ta[k0 + 3] + off)), magic2);
+            }
         }
         f2 wk01 = fma2(d01, negc2, k2c2), wk23 = fma2(d23, negc2, k2c2);
-        if (sigmoid) {
-            // non_linear weights (utils.py:346): W = 1 / (1 + exp(lambda (D - mean D))); the fma above produced
-            // lambda log2(e) (D - mean D)
+        if (SIG) {
+            // the fma above produced lambda log2(e) (D - mean D)
             float t[4];
             unpack2(wk01, t[0], t[1]);
             unpack2(wk23, t[2], t[3]);
@@ -131,6 +177,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
             for (int u = 0; u < 4; ++u) t[u] = k2 * rcp_approx(1.0f + ex2_approx(t[u]));
             wk01 = pack2(t[0], t[1]);
             wk23 = pack2(t[2], t[3]);
+        }
+        f2 rs01 = 0, rs23 = 0;
+        if (BWD) {
+            const float4 rnj = __ldg(reinterpret_cast<const float4 *>(rn + gj0 + jl));
+            rs01 = fma2(pack2(rnj.x, rnj.y), cs2, rni2);        // cs = 1: 1/neg_i + 1/neg_j (exact, as an add)
+            rs23 = fma2(pack2(rnj.z, rnj.w), cs2, rni2);
         }
         const f2 a01 = mul2(pack2(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1])), wk01);
         const f2 a23 = mul2(pack2(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])), wk23);
@@ -170,16 +222,17 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
 // BWD: backward sweep (always reads the bf16 image).  SBF16: logits from a 16-bit image `zb` (bf16, or fp16 in the
 // forward sweep of the fp16 engine: the caller passes that image and the matching instruction descriptor idesc1),
 // else from the tf32 image `zt`.
-template <bool BWD, bool SBF16>
+template <bool BWD, bool SBF16, bool Q16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
-                const float *__restrict__ zt, const uint16_t *__restrict__ zb, const float *__restrict__ dist,
+                const float *__restrict__ zt, const uint16_t *__restrict__ zb, const void *__restrict__ dist,
                 const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
                 float k2, float inv_k2, int wmode, float lambda_neg, uint32_t idesc1)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
-    using Cfg = TcCfg<SBF16>;
+    using Cfg = TcCfg<SBF16, Q16>;
     constexpr int kABytes = Cfg::kABytes, kBBytes = Cfg::kBBytes, kDStages = Cfg::kDStages, kBStages = Cfg::kBStages;
+    constexpr int kDBytes = Cfg::kDBytes;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *sm = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sA = sm;
@@ -241,15 +294,18 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                     mbar_wait(&bars->empty_d[dst], dph ^ 1u, fail, 3);
                     task_slot[dst] = task;
                     mbar_arrive_expect_tx(full, kDBytes);
-                    const float *tile = dist + (int64_t)task.z * kTileFloats;
+                    // fp32 tile: 64 KiB, 1 KiB per (row half, 4-column group); 16-bit image: 32 KiB, 1 KiB per (row half,
+                    // 8-column group).  Either way a task needs one half of it:
+                    const unsigned char *tile = reinterpret_cast<const unsigned char *>(dist) +
+                                                (int64_t)task.z * (2 * kDBytes);
                     const int half = task.y & 1;
                     if (task.w & kTaskTransposed) {
-                        // stored rows half*64 .. +63, all 128 stored columns: one contiguous 32 KiB slab
-                        bulk_g2s(sD + dst * kDBytes, tile + half * 8192, 32768, full);
+                        // stored rows half*64 .. +63, all 128 stored columns: one contiguous slab
+                        bulk_g2s(sD + dst * kDBytes, tile + half * kDBytes, kDBytes, full);
                     } else {
-                        // stored columns half*64 .. +63: one 16 KiB slab per 64-row half
-                        bulk_g2s(sD + dst * kDBytes, tile + (half * 16) * 256, 16384, full);
-                        bulk_g2s(sD + dst * kDBytes + 16384, tile + (32 + half * 16) * 256, 16384, full);
+                        // stored columns half*64 .. +63: one slab per 64-row half
+                        bulk_g2s(sD + dst * kDBytes, tile + half * (kDBytes / 2), kDBytes / 2, full);
+                        bulk_g2s(sD + dst * kDBytes + kDBytes / 2, tile + kDBytes + half * (kDBytes / 2), kDBytes / 2, full);
                     }
                 }
                 task = next;
@@ -444,6 +500,11 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             negc = lambda_neg * 1.4426950408889634f;
             addc = -mu * negc;
         }
+        if (Q16 && !no_tile) {
+            // the staged value is q = D * qscale: fold 1 / qscale into the slope (wk = k2 - q k2 / (Dmax qscale))
+            const float qs = q16_scale(__uint_as_float(stats->dbound_bits));
+            negc = qs > 0.f ? __fdiv_rn(negc, qs) : negc;
+        }
         const f2 negc2 = pack2(negc, negc), k2c2 = pack2(addc, addc);
         const uint32_t sD_s = smem_u32(sD);
         uint32_t seq = 0, dz_ph = 0;
@@ -478,17 +539,20 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 uint32_t v[32], pk[16];
                 tc_ld32(lane_addr + sb * kTaskN + half * 32, v);
                 tc_wait_ld();
-                if (masked) {
-                    if (transposed)
-                        epilogue_chunk<BWD, true, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, sigmoid, k2, rn, rowsum);
-                    else
-                        epilogue_chunk<BWD, false, true>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, sigmoid, k2, rn, rowsum);
+#define SMH_EPI(T, M, S)                                                                                              \
+    epilogue_chunk<BWD, T, M, Q16, S>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, k2, \
+                                      rn, rowsum)
+                if (sigmoid) {                       // non_linear weights: the masked form serves every task
+                    if (transposed) SMH_EPI(true, true, true);
+                    else SMH_EPI(false, true, true);
+                } else if (masked) {
+                    if (transposed) SMH_EPI(true, true, false);
+                    else SMH_EPI(false, true, false);
                 } else {
-                    if (transposed)
-                        epilogue_chunk<BWD, true, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, sigmoid, k2, rn, rowsum);
-                    else
-                        epilogue_chunk<BWD, false, false>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, sigmoid, k2, rn, rowsum);
+                    if (transposed) SMH_EPI(true, false, false);
+                    else SMH_EPI(false, false, false);
                 }
+#undef SMH_EPI
                 if (BWD) {
                     // G' as packed bf16x2 over the first half of this warp's own S columns
                     tc_st16(lane_addr + sb * kTaskN + half * 32, pk);
@@ -546,7 +610,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     if (warp == 2) tc_dealloc(tmem_base, kTmemCols);
 }
 
-template <bool BWD, bool SBF16>
+template <bool BWD, bool SBF16, bool Q16>
 static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, const smh_dims_t &dims,
                       const smh_layout_t &lay, const PlanView &plan, const WsView &ws, const Peers &peers,
                       float temperature, cudaStream_t stream)
@@ -559,10 +623,10 @@ static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, co
     const float k2 = 1.4426950408889634f / temperature;
     const float inv_k2 = (float)(0.6931471805599453 * (double)temperature);
     const int n_local = dims.n / dims.world;
-    constexpr int smem = TcCfg<SBF16>::kSmem;
-    cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    constexpr int smem = TcCfg<SBF16, Q16>::kSmem;
+    cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16, Q16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-    sweep_tc_kernel<BWD, SBF16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
+    sweep_tc_kernel<BWD, SBF16, Q16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
                                                                    ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
                                                                    dims.n, n_local, k2, inv_k2, wmode, dims.lambda_neg, idesc1);
     return check_launch("sweep_tc_kernel");
@@ -574,12 +638,16 @@ int launch_sweep_tc(bool backward, int logit_format, int wmode, const smh_dims_t
     if (lay.n_strips == 0) return 0;
     const uint32_t id_bf16 = umma_idesc_bf16(kTile, kTaskN, 0, 0), id_f16 = umma_idesc_f16(kTile, kTaskN, 0, 0),
                    id_tf32 = umma_idesc_tf32(kTile, kTaskN, 0, 0);
-    if (backward) return launch_one<true, true>(wmode, ws.zb, id_bf16, dims, lay, plan, ws, peers, temperature, stream);
-    if (logit_format == 1)
-        return launch_one<false, true>(wmode, ws.zb, id_bf16, dims, lay, plan, ws, peers, temperature, stream);
-    if (logit_format == 2)
-        return launch_one<false, true>(wmode, ws.zh, id_f16, dims, lay, plan, ws, peers, temperature, stream);
-    return launch_one<false, false>(wmode, ws.zb, id_tf32, dims, lay, plan, ws, peers, temperature, stream);
+    const bool q16 = dims.flags & SMH_DIMS_Q16_TILES;
+    if (q16 && wmode != 0) return set_error(SMH_E_MODE, "SMH_DIMS_Q16_TILES: linear weights from the joints only");
+#define SMH_SWEEP(B, S, IMG, ID)                                                                                      \
+    (q16 ? launch_one<B, S, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, temperature, stream)                    \
+         : launch_one<B, S, false>(wmode, IMG, ID, dims, lay, plan, ws, peers, temperature, stream))
+    if (backward) return SMH_SWEEP(true, true, ws.zb, id_bf16);
+    if (logit_format == 1) return SMH_SWEEP(false, true, ws.zb, id_bf16);
+    if (logit_format == 2) return SMH_SWEEP(false, true, ws.zh, id_f16);
+    return SMH_SWEEP(false, false, ws.zb, id_tf32);
+#undef SMH_SWEEP
 }
 
 }  // namespace smh

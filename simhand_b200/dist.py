@@ -24,7 +24,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check
-from .ops import _as_f32, _stream_ptr, get_context, make_inputs, resolve_engine
+from .ops import _as_f32, _stream_ptr, get_context, make_inputs, resolve_engine, step_flags
 
 
 def pack_local(z1, z2, joints1, joints2) -> torch.Tensor:
@@ -119,9 +119,10 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
     dev = z1.device
     n_local, d = z1.shape
     n = n_local * world
-    eng = _lib.ENGINES[resolve_engine(engine, n)]
+    engine_name = resolve_engine(engine, n)
+    eng = _lib.ENGINES[engine_name]
     with torch.cuda.device(dev):
-        ctx = get_context(n, d, world, rank, dev, strip_len)
+        ctx = get_context(n, d, world, rank, dev, strip_len, step_flags(engine_name))
         lay, dims = ctx.layout, ctx.dims
         chunk = 2 * n_local * (d + 42)
         ex = get_exchange(ctx, group, chunk)
@@ -185,9 +186,10 @@ def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, 
     dev = z1.device
     n_local, d = z1.shape
     n = n_local * world
-    eng = _lib.ENGINES[resolve_engine(engine, n)]
+    engine_name = resolve_engine(engine, n)
+    eng = _lib.ENGINES[engine_name]
     with torch.cuda.device(dev):
-        ctx = get_context(n, d, world, rank, dev, strip_len)
+        ctx = get_context(n, d, world, rank, dev, strip_len, step_flags(engine_name))
         lay, dims = ctx.layout, ctx.dims
         local = pack_local(z1, z2, joints1, joints2)
         gathered = torch.empty(world * local.numel(), dtype=torch.float32, device=dev)

@@ -88,3 +88,37 @@ def staged_read(stage: np.ndarray, task, r: int, jl: int) -> float:
         return stage[(c4 * 64 + (jl ^ (c4 & 7))) * 4 + (r & 3)]
     c4l = jl >> 2
     return stage[(((r >> 6) * 16 + c4l) * 64 + ((r & 63) ^ (c4l & 7))) * 4 + (jl & 3)]
+
+
+# ----------------------------------------------------------------------------------------------------
+# 16-bit image of the distance tiles (SMH_DIMS_Q16_TILES): mirrors of smh_common.cuh / smh_sweep_tc.cu
+# ----------------------------------------------------------------------------------------------------
+STAGE_Q16 = 8192                 # u16 elements staged per task (16 KiB)
+Q16_LEVELS = 65000.0
+
+
+def distq_index(row, col):
+    """u16 index of q[row, col] inside a stored tile: [row/64][col/8][(row%64) ^ (col/8 % 8)][col%8]."""
+    row, col = np.asarray(row), np.asarray(col)
+    c8 = col >> 3
+    return ((((row >> 6) * 16 + c8) * 64) + ((row & 63) ^ (c8 & 7))) * 8 + (col & 7)
+
+
+def stage_task_q16(tile: np.ndarray, task) -> np.ndarray:
+    """The 16 KiB the tile producer stages for a task from the 16-bit image: direct -> two 8 KiB column-half slabs,
+    transposed -> the 16 KiB row-half slab."""
+    half = task[1] & 1
+    if task[3] & TASK_TRANSPOSED:
+        return tile[half * 8192:(half + 1) * 8192].copy()
+    lo = tile[half * 4096:(half + 1) * 4096]
+    hi = tile[8192 + half * 4096:8192 + (half + 1) * 4096]
+    return np.concatenate([lo, hi])
+
+
+def staged_read_q16(stage: np.ndarray, task, r: int, jl: int):
+    """The value the epilogue thread of row r reads for task column jl from the staged 8192 u16."""
+    if task[3] & TASK_TRANSPOSED:
+        c8 = r >> 3
+        return stage[(c8 * 64 + (jl ^ (c8 & 7))) * 8 + (r & 7)]
+    c8l = jl >> 3
+    return stage[(((r >> 6) * 8 + c8l) * 64 + ((r & 63) ^ (c8l & 7))) * 8 + (jl & 7)]

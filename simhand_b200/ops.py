@@ -16,6 +16,7 @@ There is no CPU or eager-PyTorch fallback: inputs must live on a CUDA (sm_100) d
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 from typing import Optional, Tuple
 
@@ -94,6 +95,18 @@ def get_context(n: int, d: int, world: int, rank: int, device, strip_len: int = 
     return ctx
 
 
+def step_flags(engine_name: str, weighting=None, neg_weighted: bool = True) -> int:
+    """smh_dims_t.flags of the fused step.  With SMH_Q16=1 in the environment the tensor-core engines stage the 16-bit
+    image of the distance tiles (SMH_DIMS_Q16_TILES: half the workspace and half the tile traffic of the sweeps, W within
+    1.6e-5) when the weights are the linear / mpjpe ones built from the joints.  Off by default: measured speed is the same
+    (DESIGN.md section 5), so the default keeps the exact fp32 distances."""
+    if os.environ.get("SMH_Q16", "0") != "1" or engine_name == "fp32" or not neg_weighted:
+        return 0
+    if tuple(weighting or DEFAULT_WEIGHTING) != DEFAULT_WEIGHTING:
+        return 0
+    return _lib.DIMS_Q16_TILES
+
+
 def _require_cuda(t: torch.Tensor, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(
@@ -143,9 +156,10 @@ def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _
     lib = _lib.load()
     dev = z1.device
     n, d = z1.shape
-    eng = _lib.ENGINES[resolve_engine(engine, n)]
+    engine_name = resolve_engine(engine, n)
+    eng = _lib.ENGINES[engine_name]
     with torch.cuda.device(dev):
-        ctx = get_context(n, d, 1, 0, dev, strip_len, 0, weighting)
+        ctx = get_context(n, d, 1, 0, dev, strip_len, step_flags(engine_name, weighting, neg_weighted), weighting)
         lay, dims = ctx.layout, ctx.dims
         inp, keep = make_inputs(z1, z2, joints1, joints2)
         ws = torch.empty(int(lay.ws_bytes), dtype=torch.uint8, device=dev)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.Dims) == 40
-    assert ctypes.sizeof(_lib.Stats) == 40
+    assert ctypes.sizeof(_lib.Stats) == 48
     assert ctypes.sizeof(_lib.Exchange) == 8 + 3 * 8 * 8
     assert ctypes.sizeof(_lib.Layout) == 15 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.Inputs) == 88
@@ -179,3 +179,46 @@ def test_staged_reads_are_bank_conflict_free():
             slot = ((rows >> 6) * 16 + c4l) * 64 + ((rows & 63) ^ (c4l & 7))
             for q in range(4):
                 assert len(set(slot[8 * q:8 * q + 8] % 8)) == 8
+
+
+def test_q16_tile_layout_mirrors():
+    """16-bit tile image: index bijection, producer piece mapping + epilogue reads reproduce q[gi, gj] for every task,
+    and both read patterns are free of shared-memory bank conflicts."""
+    r, c = np.meshgrid(np.arange(128), np.arange(128), indexing="ij")
+    assert sorted(L.distq_index(r, c).ravel()) == list(range(128 * 128))
+    n = 200
+    rng = np.random.default_rng(1)
+    qfull = rng.integers(0, 65000, (512, 512)).astype(np.uint16)
+    qfull = np.triu(qfull) + np.triu(qfull, 1).T
+    lay, (h, tiles, tasks, strips) = L.build_plan(n, 128, 1, 0, 0, _lib.DIMS_Q16_TILES)
+    lay32, _ = L.build_plan(n)
+    assert lay.ws_bytes - lay.off_dist == (lay32.ws_bytes - lay32.off_dist) // 2          # half the tile bytes
+    store = np.zeros((len(tiles), 128 * 128), np.uint16)
+    for lt, (I, J) in enumerate(tiles):
+        store[lt, L.distq_index(r, c)] = qfull[I * 128:(I + 1) * 128, J * 128:(J + 1) * 128]
+    for task in tasks:
+        row, cj, lt, flags = task
+        stage = L.stage_task_q16(store[lt], task)
+        assert stage.size == L.STAGE_Q16
+        for rr in (0, 1, 7, 8, 63, 64, 77, 127):
+            for jl in (0, 3, 4, 7, 8, 31, 32, 63):
+                assert L.staged_read_q16(stage, task, rr, jl) == qfull[row * 128 + rr, cj * 64 + jl]
+    for w4 in range(4):
+        rows = np.arange(32) + 32 * w4
+        for jl in range(64):
+            # transposed: 2-byte reads; lanes may share a 32-bit word (broadcast) but never a bank with another word
+            c8 = rows >> 3
+            byte = (c8 * 64 + (jl ^ (c8 & 7))) * 16 + (rows & 7) * 2
+            words = byte // 4
+            assert len(set(words % 32)) == len(set(words))
+        for c8l in range(8):
+            # direct: 16-byte reads, conflict-free within every quarter warp
+            slot = (rows & 63) ^ (c8l & 7)
+            for qw in range(4):
+                assert len(set((slot[8 * qw:8 * qw + 8] * 4) % 32)) == 8
+    # the flag is rejected where the fp32 tiles are required
+    lib = _lib.load()
+    lo = _lib.Layout()
+    assert lib.smh_layout(ctypes.byref(_lib.Dims(64, 128, 1, 0, 0, _lib.DIMS_Q16_TILES, 1)), ctypes.byref(lo)) == -6
+    assert lib.smh_layout(ctypes.byref(_lib.Dims(64, 128, 1, 0, 0, _lib.DIMS_Q16_TILES | _lib.DIMS_DENSE_WEIGHTS)),
+                          ctypes.byref(lo)) == -6
