@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsimhand_b200.so")
+LIB_PATH = os.environ.get("SMH_LIB") or os.path.join(_HERE, "lib", "libsimhand_b200.so")      # SMH_LIB: development builds
 
 ENGINE_TC_TF32 = 0
 ENGINE_FP32 = 1

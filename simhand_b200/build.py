@@ -34,7 +34,14 @@ def _newer(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True: development build with -DSMH_TRACE (per-role cycle counters in the sweeps, tools/trace_sweeps.py)
+    into lib/libsimhand_b200_trace.so; the product library is never built with it."""
+    global OBJDIR, LIB
+    flags = list(FLAGS)
+    if trace:
+        OBJDIR, LIB = os.path.join(HERE, "build_trace"), os.path.join(LIBDIR, "libsimhand_b200_trace.so")
+        flags.append("-DSMH_TRACE")
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
@@ -47,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        r = subprocess.run([NVCC, *FLAGS, "-c", s, "-o", o], capture_output=True, text=True)
+        r = subprocess.run([NVCC, *flags, "-c", s, "-o", o], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {s}:\n{r.stdout}\n{r.stderr}")
         return s, r.stderr
@@ -69,5 +76,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose=True)
+    path = build(force="--force" in sys.argv, verbose=True, trace="--trace" in sys.argv)
     print(path)

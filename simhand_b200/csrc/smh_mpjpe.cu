@@ -34,7 +34,9 @@ __device__ __forceinline__ f2 joint_pair(const f2 ax, const f2 ay, const float *
 
 // Joints are evaluated in the order the ATen summation consumes them (16..20 first, then k and k+8 together), so only
 // two pair results are live at a time.
-template <int MODE>
+// SUM: return the 21-term sum s instead of D = s / 21 (the 16-bit tile image scales s directly, and max_ij D_ij =
+// (max_ij s_ij) / 21 because the correctly rounded division is monotonic: one division per tile instead of one per pair).
+template <int MODE, bool SUM>
 __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10], float ax20, float ay20,
                                            const float *__restrict__ col, const DivConst &div21)
 {
@@ -58,14 +60,16 @@ __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10
         s = __fadd_rn(s, a);
         s = __fadd_rn(s, b);
     }
+    if (SUM) return s;
     return FAST ? div_fast(s, div21) : __fdiv_rn(s, 21.0f);
 }
 
 // MODE as in joint_pair.  vmax_bits: running maximum of the integer image of D (D >= 0; NaN is larger than any finite).
 // NCOLS: columns per thread (64: one CTA per stored tile; 32: one CTA per 64-column half).  col0: first column (inside
 // the tile) of this thread's run; cs holds the staged columns starting at tile column cs0.
-// Q16: the tile is stored as 16-bit fixed point q = round(D * qscale) (SMH_DIMS_Q16_TILES); the maximum is still taken on
-// the exact fp32 D.  The rounding to integer rides on the FMA pipe: fma(D, qscale, 2^23) has q in its low mantissa bits.
+// Q16: the tile is stored as 16-bit fixed point q = round(D * qscale) = round(s * qscale / 21) (SMH_DIMS_Q16_TILES) and
+// vmax_bits tracks the exact fp32 sum s (the caller divides the tile maximum by 21).  The rounding to integer rides on
+// the FMA pipe: fma(s, qscale / 21, 2^23) has q in its low mantissa bits.
 template <int MODE, int UN, int NCOLS, bool Q16>
 __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, void *__restrict__ tile_out, int I,
                                                 int J, int m, const float *cs, int cs0, int col0,
@@ -90,13 +94,14 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
     const DivConst div21 = make_div(21.0f);
     const bool row_ok = (I * kTile + r) < m;
     const int col_limit = m - J * kTile;          // columns >= col_limit are padding
+    uint2 qprev = make_uint2(0u, 0u);             // 16-bit image: two 4-column steps share one 16-byte store
 #pragma unroll 1
     for (int cq = 0; cq < NCOLS / UN; ++cq) {
         const int c0 = col0 + cq * UN;
         float dv[UN];
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
-            dv[u] = mpjpe_one<MODE>(ax, ay, ax20, ay20, cs + (c0 - cs0 + u) * kJP, div21);
+            dv[u] = mpjpe_one<MODE, Q16>(ax, ay, ax20, ay20, cs + (c0 - cs0 + u) * kJP, div21);
             if (row_ok && (c0 + u) < col_limit) vmax_bits = max(vmax_bits, __float_as_uint(dv[u]));
         }
 #pragma unroll
@@ -107,7 +112,11 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
                 for (int t = 0; t < 4; ++t) q[t] = __float_as_uint(__fmaf_rn(dv[u + t], qscale, 8388608.0f));
                 // low 16 bits of each: (q0 | q1 << 16, q2 | q3 << 16)
                 const uint2 pk = make_uint2(__byte_perm(q[0], q[1], 0x5410), __byte_perm(q[2], q[3], 0x5410));
-                *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(tile_out) + distq_index(r, c0 + u)) = pk;
+                static_assert(!Q16 || UN == 4, "the 16-bit store pairs consecutive 4-column steps");
+                if (cq & 1)
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(tile_out) + distq_index(r, c0 - 4)) =
+                        make_uint4(qprev.x, qprev.y, pk.x, pk.y);
+                qprev = pk;
             } else {
                 *reinterpret_cast<float4 *>(reinterpret_cast<float *>(tile_out) + dist_index(r, c0 + u)) =
                     make_float4(dv[u], dv[u + 1], dv[u + 2], dv[u + 3]);
@@ -133,7 +142,7 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
     const int col0 = cs0 + (threadIdx.x >> 7) * kPerThread;
     const int2 ij = tiles[tile_id];
     void *tile_out = reinterpret_cast<unsigned char *>(dist) + (int64_t)tile_id * kTileFloats * (Q16 ? 2 : 4);
-    const float qscale = Q16 ? q16_scale(__uint_as_float(stats->dbound_bits)) : 0.f;
+    const float qscale = Q16 ? q16_scale(__uint_as_float(stats->dbound_bits)) * (1.0f / 21.0f) : 0.f;    // applied to the sum
     {
         const float4 *src = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.y * kTile + cs0) * kJP);
         float4 *dst = reinterpret_cast<float4 *>(cs);
@@ -171,7 +180,7 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
         if (bmax > 0x7f800000u)
             atomicOr(&stats->flags, SMH_FLAG_NONFINITE);      // non-finite inputs (IEEE path): the loss is NaN
         else
-            atomicMax(&stats->dmax_bits, bmax);
+            atomicMax(&stats->dmax_bits, Q16 ? __float_as_uint(__fdiv_rn(__uint_as_float(bmax), 21.0f)) : bmax);
         if (peers.world > 1) {
             // fused all-reduce(MAX): the last CTA of this rank pushes the rank's maximum into every peer's stats
             __threadfence();

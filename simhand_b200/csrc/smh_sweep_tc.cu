@@ -27,6 +27,21 @@
 
 namespace smh {
 
+// Development aid (python -m simhand_b200.build --trace): per-role cycle counters of every sweep CTA, written to the
+// rowloss region of the workspace (unused until finalize) and read by tools/trace_sweeps.py.  Compiled out otherwise.
+#ifdef SMH_TRACE
+#define TR_DECL(n) long long tr_[n] = {}; long long tr_t_ = clock64(); const long long tr_t0_ = tr_t_
+#define TR_LAP(i) do { const long long now_ = clock64(); tr_[i] += now_ - tr_t_; tr_t_ = now_; } while (0)
+#define TR_COUNT(i) (++tr_[i])
+#define TR_STORE(slot, n) do { for (int i_ = 0; i_ < (n); ++i_) trace[(blockIdx.x * 4 + (slot)) * 8 + i_] = tr_[i_]; \
+                               trace[(blockIdx.x * 4 + (slot)) * 8 + 7] = clock64() - tr_t0_; } while (0)
+#else
+#define TR_DECL(n)
+#define TR_LAP(i)
+#define TR_COUNT(i)
+#define TR_STORE(slot, n)
+#endif
+
 constexpr int kEpiGroups = 2;                            // epilogue groups take alternate tasks
 constexpr int kGroupWarps = 8;                           // 4 TMEM lane quadrants x 2 column halves
 constexpr int kEpiWarps = kEpiGroups * kGroupWarps;      // 16
@@ -227,7 +242,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const void *__restrict__ dist,
                 const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
-                float k2, float inv_k2, int wmode, float lambda_neg, uint32_t idesc1)
+                float k2, float inv_k2, int wmode, float lambda_neg, uint32_t idesc1, long long *trace)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
     using Cfg = TcCfg<SBF16, Q16>;
@@ -284,14 +299,17 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         // ------------------------------------------------------------------ tile producer (MPJPE pieces, HBM)
         int dst = 0;
         uint32_t dph = 0, seq = 0;
+        TR_DECL(7);
         for (int s = s_begin; s < s_end; ++s) {
             const int2 strip = strips[s];
             int4 task = tasks[strip.x];
             for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
                 const int4 next = (ti + 1 < strip.y) ? tasks[ti + 1] : task;      // prefetch the next record
-                if (lane == 0) {
-                    uint64_t *full = &bars->full_d[dst][seq & 1u];                  // the group that takes task `seq`
-                    mbar_wait(&bars->empty_d[dst], dph ^ 1u, fail, 3);
+                uint64_t *full = &bars->full_d[dst][seq & 1u];                      // the group that takes task `seq`
+                TR_LAP(0);
+                mbar_wait(&bars->empty_d[dst], dph ^ 1u, fail, 3);                  // all lanes: warp-uniform control flow
+                TR_LAP(1);                                                          // [1] waiting for a free tile stage
+                if (elect_one()) {
                     task_slot[dst] = task;
                     mbar_arrive_expect_tx(full, kDBytes);
                     // fp32 tile: 64 KiB, 1 KiB per (row half, 4-column group); 16-bit image: 32 KiB, 1 KiB per (row half,
@@ -312,16 +330,21 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 if (++dst == kDStages) { dst = 0; dph ^= 1u; }
             }
         }
+        if (lane == 0) TR_STORE(0, 7);
     } else if (warp == 2 + kEpiWarps) {
         // ------------------------------------------------------------------ operand producer (z blocks, L2)
-        if (lane == 0) {
+        {
             int bst = 0;
             uint32_t bph = 0, a_ph = 0;
+            TR_DECL(7);
             for (int s = s_begin; s < s_end; ++s) {
                 const int2 strip = strips[s];
                 int4 task = tasks[strip.x];
                 const int I = task.x;
+                TR_LAP(0);
                 mbar_wait(&bars->a_empty, a_ph ^ 1u, fail, 1);
+                TR_LAP(1);                                                          // [1] waiting for the A buffer
+                if (elect_one()) {
                 mbar_arrive_expect_tx(&bars->a_full, kABytes);
                 if (SBF16) {
                     // two 64-row bf16 blocks -> two 64-column boxes of [128 rows][128 B]
@@ -339,33 +362,42 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                                  &bars->a_full);
                     }
                 }
+                }
                 a_ph ^= 1u;
                 for (int ti = strip.x; ti < strip.y; ++ti) {
                     const int4 next = (ti + 1 < strip.y) ? tasks[ti + 1] : task;
+                    TR_LAP(0);
                     mbar_wait(&bars->empty_b[bst], bph ^ 1u, fail, 2);
-                    mbar_arrive_expect_tx(&bars->full_b[bst], kBBytes);
-                    if (SBF16)
-                        bulk_g2s(sB + bst * kBBytes, zb + (int64_t)task.y * kBlockFloats, kBBytes, &bars->full_b[bst]);
-                    else
-                        bulk_g2s(sB + bst * kBBytes, zt + (int64_t)task.y * kBlockFloats, kBBytes, &bars->full_b[bst]);
+                    TR_LAP(2);                                                      // [2] waiting for a free z-block stage
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&bars->full_b[bst], kBBytes);
+                        if (SBF16)
+                            bulk_g2s(sB + bst * kBBytes, zb + (int64_t)task.y * kBlockFloats, kBBytes, &bars->full_b[bst]);
+                        else
+                            bulk_g2s(sB + bst * kBBytes, zt + (int64_t)task.y * kBlockFloats, kBBytes, &bars->full_b[bst]);
+                    }
                     task = next;
                     if (++bst == kBStages) { bst = 0; bph ^= 1u; }
                 }
             }
+            if (lane == 0) TR_STORE(1, 7);
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (one elected lane issues; the
+        // control flow and every operand stay warp-uniform, see elect_one)
+        {
             constexpr uint32_t idesc2 = umma_idesc_bf16(kTile, kD, 0, 1);
             const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
             uint32_t a_ph = 0, dz_ph = 0;
             uint32_t seq = 0;                       // logit MMAs issued so far by this CTA
             uint32_t done2 = 0;                     // value MMAs issued so far (backward)
             uint32_t first_mask = 0, last_mask = 0; // per pending task (bit = seq % 32): first / last of its strip
+            TR_DECL(7);
             // logit contraction of task `seq` into S buffer seq % kSBufs (operands and buffer are known to be ready)
             auto mma1 = [&](bool last_of_strip) {
                 const uint32_t sb = seq % kSBufs, bst = seq % kBStages;
                 tc_fence_after();
+                if (elect_one()) {
                 if (SBF16) {
                     // K-major 16-bit: 64 columns (128 B) per box, 16 columns (32 B) per K step
 #pragma unroll
@@ -392,12 +424,15 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 tc_commit(&bars->sg_full[sb]);
                 if (!BWD) tc_commit(&bars->empty_b[bst]);
                 if (last_of_strip) tc_commit(&bars->a_empty);           // every logit MMA of the strip has read sA
+                }
+                __syncwarp();
             };
             // value contraction of task q (the q-th task of this CTA): dz (+)= G_q z_J  (G and the accumulator are ready)
             auto mma2 = [&](uint32_t q) {
                 const uint32_t sbq = q % kSBufs, bstq = q % kBStages;
                 const bool first = (first_mask >> (q & 31)) & 1u, last = (last_mask >> (q & 31)) & 1u;
                 tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < kTaskN / 16; ++ks) {
                     // MN-major bf16 B: 64-element (128 B) atoms along d at LBO = 8 KiB, 8-row K groups at SBO = 1 KiB,
@@ -411,16 +446,23 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 tc_commit(&bars->sg_empty[sbq]);
                 tc_commit(&bars->empty_b[bstq]);
                 if (last) tc_commit(&bars->dz_full);
+                }
+                __syncwarp();
             };
             if (!BWD) {
                 for (int s = s_begin; s < s_end; ++s) {
                     const int2 strip = strips[s];
+                    TR_LAP(0);
                     mbar_wait(&bars->a_full, a_ph, fail, 6);
+                    TR_LAP(1);                                                      // [1] waiting for A
                     a_ph ^= 1u;
                     for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
                         mbar_wait(&bars->full_b[seq % kBStages], (seq / kBStages) & 1u, fail, 7);
+                        TR_LAP(2);                                                  // [2] waiting for the z block
                         mbar_wait(&bars->sg_empty[seq % kSBufs], ((seq / kSBufs) & 1u) ^ 1u, fail, 8);
+                        TR_LAP(3);                                                  // [3] waiting for a free S buffer
                         mma1(ti + 1 == strip.y);
+                        TR_LAP(4);                                                  // [4] issuing the logit MMAs
                     }
                 }
             } else if (s_begin < s_end) {
@@ -438,26 +480,34 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 while (done2 < total) {
                     bool progress = false;
                     // value MMA first: it frees an S buffer and a z block
-                    if (done2 < seq && mbar_test_wait(&bars->g_ready[done2 % kSBufs], (done2 / kSBufs) & 1u)) {
+                    // (votes: every lane probes the same barrier; the vote makes the decision provably warp-uniform)
+                    if (done2 < seq &&
+                        __all_sync(0xffffffffu, mbar_test_wait(&bars->g_ready[done2 % kSBufs], (done2 / kSBufs) & 1u))) {
                         const bool first = (first_mask >> (done2 & 31)) & 1u;
-                        if (!first || mbar_test_wait(&bars->dz_empty, dz_ph ^ 1u)) {
+                        if (!first || __all_sync(0xffffffffu, mbar_test_wait(&bars->dz_empty, dz_ph ^ 1u))) {
                             if (first) dz_ph ^= 1u;
+                            TR_LAP(1);                                              // [1] polling before a value MMA
                             mma2(done2++);
+                            TR_LAP(3);                                              // [3] issuing the value MMAs
                             progress = true;
                         }
                     }
                     if (seq < total && seq - done2 < (uint32_t)kSBufs) {
-                        if (!a_ok && mbar_test_wait(&bars->a_full, a_ph)) {
+                        if (!a_ok && __all_sync(0xffffffffu, mbar_test_wait(&bars->a_full, a_ph))) {
                             a_ok = true;
                             a_ph ^= 1u;
                         }
-                        if (a_ok && mbar_test_wait(&bars->full_b[seq % kBStages], (seq / kBStages) & 1u) &&
-                            mbar_test_wait(&bars->sg_empty[seq % kSBufs], ((seq / kSBufs) & 1u) ^ 1u)) {
+                        if (a_ok &&
+                            __all_sync(0xffffffffu, mbar_test_wait(&bars->full_b[seq % kBStages], (seq / kBStages) & 1u) &&
+                                                        mbar_test_wait(&bars->sg_empty[seq % kSBufs],
+                                                                       ((seq / kSBufs) & 1u) ^ 1u))) {
                             const uint32_t bit = 1u << (seq & 31);
                             const bool last1 = ti1 + 1 == strip1.y;
                             first_mask = (ti1 == strip1.x) ? (first_mask | bit) : (first_mask & ~bit);
                             last_mask = last1 ? (last_mask | bit) : (last_mask & ~bit);
+                            TR_LAP(2);                                              // [2] polling before a logit MMA
                             mma1(last1);
+                            TR_LAP(4);                                              // [4] issuing the logit MMAs
                             ++seq;
                             if (last1) {
                                 a_ok = false;
@@ -473,13 +523,19 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                     }
                     if (progress) {
                         idle = 0;
+                        TR_LAP(0);
+                    } else {
+                        TR_LAP(5);                                                  // [5] polls that found nothing ready
+                    }
+                    if (progress) {
                     } else if ((++idle & 1023u) == 0u &&
-                               (clock64() - t0 > 4000000000ll || *(volatile uint32_t *)fail != 0u)) {
-                        atomicCAS(fail, 0u, 7u);
+                               __any_sync(0xffffffffu, clock64() - t0 > 4000000000ll || *(volatile uint32_t *)fail != 0u)) {
+                        if (lane == 0) atomicCAS(fail, 0u, 7u);
                         break;
                     }
                 }
             }
+            if (lane == 0) TR_STORE(2, 7);
         }
     } else if (warp >= 2 && warp < 2 + kEpiWarps) {
         // ------------------------------------------------------------------ epilogue (warps 2..17)
@@ -509,6 +565,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         const uint32_t sD_s = smem_u32(sD);
         uint32_t seq = 0, dz_ph = 0;
         f2 rowsum[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
+        TR_DECL(7);
         for (int s = s_begin; s < s_end; ++s) {
             const int2 strip = strips[s];
             int row_block = -1;
@@ -518,7 +575,9 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 const uint32_t dst = seq % kDStages, sb = seq % kSBufs;
                 // fills of a stage seen by this group: every fill (even stage count) or every other one (odd)
                 const uint32_t my_fill = (kDStages & 1) ? (seq / kDStages) >> 1 : seq / kDStages;
+                TR_LAP(0);
                 mbar_wait(&bars->full_d[dst][group], my_fill & 1u, fail, 10);
+                TR_LAP(1);                                                          // [1] waiting for the tile
                 const int4 task = task_slot[dst];
                 const int gi = task.x * kTile + r;
                 const bool row_ok = gi < m;
@@ -533,12 +592,15 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 const float rni_t = (dense && transposed) ? 0.f : rni;
                 const float cs = (dense && !transposed) ? 0.f : 1.f;
                 const f2 cs2 = pack2(cs, cs);
+                TR_LAP(0);
                 mbar_wait(&bars->sg_full[sb], (seq / kSBufs) & 1u, fail, 9);
+                TR_LAP(2);                                                          // [2] waiting for S
                 tc_fence_after();
                 const uint32_t dstage = sD_s + dst * kDBytes;
                 uint32_t v[32], pk[16];
                 tc_ld32(lane_addr + sb * kTaskN + half * 32, v);
                 tc_wait_ld();
+                TR_LAP(3);                                                          // [3] tcgen05.ld + wait
 #define SMH_EPI(T, M, S)                                                                                              \
     epilogue_chunk<BWD, T, M, Q16, S>(v, pk, dstage, r, half, gi, gj0, m, diagonal, negc2, k2c2, rni_t, cs2, no_tile, k2, \
                                       rn, rowsum)
@@ -564,7 +626,10 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                     mbar_arrive(BWD ? &bars->g_ready[sb] : &bars->sg_empty[sb]);
                     mbar_arrive(&bars->empty_d[dst]);
                 }
+                TR_LAP(4);                                                          // [4] weights, exp, sums / G, arrive
+                TR_COUNT(6);
             }
+            TR_LAP(0);
             // strip flush: both groups hold partial results for the strip's row block
             const int gi = (row_block < 0 ? 0 : row_block) * kTile + r;
             const bool row_ok = row_block >= 0 && gi < m;
@@ -602,7 +667,9 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->dz_empty);
             }
+            TR_LAP(5);                                                              // [5] strip flush
         }
+        if (e == 0 && lane == 0) TR_STORE(3, 7);
     }
 
     tc_fence_before();
@@ -628,7 +695,8 @@ static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, co
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
     sweep_tc_kernel<BWD, SBF16, Q16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
                                                                    ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
-                                                                   dims.n, n_local, k2, inv_k2, wmode, dims.lambda_neg, idesc1);
+                                                                   dims.n, n_local, k2, inv_k2, wmode, dims.lambda_neg, idesc1,
+                                                                        reinterpret_cast<long long *>(ws.rowloss));
     return check_launch("sweep_tc_kernel");
 }
 

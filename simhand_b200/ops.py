@@ -96,11 +96,11 @@ def get_context(n: int, d: int, world: int, rank: int, device, strip_len: int = 
 
 
 def step_flags(engine_name: str, weighting=None, neg_weighted: bool = True) -> int:
-    """smh_dims_t.flags of the fused step.  With SMH_Q16=1 in the environment the tensor-core engines stage the 16-bit
-    image of the distance tiles (SMH_DIMS_Q16_TILES: half the workspace and half the tile traffic of the sweeps, W within
-    1.6e-5) when the weights are the linear / mpjpe ones built from the joints.  Off by default: measured speed is the same
-    (DESIGN.md section 5), so the default keeps the exact fp32 distances."""
-    if os.environ.get("SMH_Q16", "0") != "1" or engine_name == "fp32" or not neg_weighted:
+    """smh_dims_t.flags of the fused step.  The tensor-core engines stage the 16-bit image of the distance tiles
+    (SMH_DIMS_Q16_TILES: half the workspace, half the tile bytes and twice the prefetch depth of the sweeps; W within
+    1.6e-5, far inside the 2^-11 operand rounding of the logits; Dmax exact) when the weights are the linear / mpjpe
+    ones built from the joints.  SMH_Q16=0 in the environment keeps fp32 tiles."""
+    if os.environ.get("SMH_Q16", "1") == "0" or engine_name == "fp32" or not neg_weighted:
         return 0
     if tuple(weighting or DEFAULT_WEIGHTING) != DEFAULT_WEIGHTING:
         return 0

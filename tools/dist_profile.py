@@ -26,7 +26,7 @@ def main():
     sl = slice(rank * n_local, (rank + 1) * n_local)
     a, b = z1[sl].to(dev), z2[sl].to(dev)
     c, e = j1[sl].to(dev)[:, :, :2], j2[sl].to(dev)[:, :, :2]
-    ctx = get_context(n, 128, world, rank, dev)
+    ctx = get_context(n, 128, world, rank, dev, 0, _lib.DIMS_Q16_TILES)
     lay, dims = ctx.layout, ctx.dims
     from simhand_b200.ops import make_inputs
     chunk = 2 * n_local * (128 + 42)

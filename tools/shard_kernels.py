@@ -20,7 +20,7 @@ def main():
     lib = _lib.load()
     z1, z2, j1, j2 = synth.make_batch(n, d, 5, "hand")
     z1, z2, a, b = z1.to(dev), z2.to(dev), j1.to(dev)[:, :, :2], j2.to(dev)[:, :, :2]
-    ctx = ops.get_context(n, d, world, rank, dev, 0, _lib.DIMS_Q16_TILES if os.environ.get('SMH_Q16', '0') == '1' else 0)
+    ctx = ops.get_context(n, d, world, rank, dev, 0, _lib.DIMS_Q16_TILES if os.environ.get('SMH_Q16', '1') == '1' else 0)
     lay = ctx.layout
     # the full batch described as one "rank" of n samples (n_local = n): same addressing as a gathered buffer
     inp, keep = ops.make_inputs(z1, z2, a, b)
