@@ -161,7 +161,9 @@ int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_i
 {
     const int n_local = dims.n / dims.world;
     const int rows = phase == 0 ? lay.m : 2 * n_local;
-    const int blocks = (rows + 7) / 8 < 1184 ? (rows + 7) / 8 : 1184;
+    // 4 blocks per SM at most: every block ends with a ticket atomic on one address (last-block reduction of the loss),
+    // and ~1200 of them serialised cost more than the few extra rows per warp
+    const int blocks = (rows + 7) / 8 < 4 * kNumCtas ? (rows + 7) / 8 : 4 * kNumCtas;
     // a rank-local block (reduce-scattered buffer or peer-exchange accumulator) starts at this rank's first row
     const int64_t src_off = local_block ? (int64_t)dims.rank * 2 * n_local : 0;
     smh_inputs_t inp = in;
