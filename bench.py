@@ -126,7 +126,7 @@ def _make_batch(n):
 # --------------------------------------------------------------------------------------------------
 # CPU legs (the only place bench.py touches oracle/)
 # --------------------------------------------------------------------------------------------------
-def cpu_port_sample(rows: int = 128, repeats: int = 3, warmup: int = 1):
+def cpu_port_sample(rows: int = 128, repeats: int = 3, warmup: int = 1, min_seconds: float = 0.0):
     """Times the reference's torch ops on a row block of the 2N = 16384 problem and extrapolates to a step.
     The reference itself cannot run this size on a host (63 GiB of temporaries)."""
     from oracle import restate as R
@@ -137,13 +137,17 @@ def cpu_port_sample(rows: int = 128, repeats: int = 3, warmup: int = 1):
     m = z.shape[0]
     dmax = 70.0   # value only scales the weights; timing is data independent
     times = []
-    for it in range(warmup + repeats):
+    it = 0
+    # at least `repeats` samples and, for the cpu_baseline leg, about min_seconds of CPU work (bounded at 400 samples)
+    while len(times) < repeats or (sum(times) < min_seconds and len(times) < 400):
         r0 = (it * rows) % (m - rows)
         t0 = time.perf_counter()
         R.port_step_rows(z, bj, r0, r0 + rows, dmax, TAU)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+        it += 1
+    repeats = len(times)
     t_sample = statistics.median(times)
     steps_per_s = 1.0 / (t_sample * (m / rows))
     return dict(value=steps_per_s, unit=UNIT, cores=torch.get_num_threads(), kind="port",
@@ -336,7 +340,7 @@ def run_ours(args):
             kernels[k + "_hbm_frac"] = hbm_bytes / (kernels[k] * 1e-3) / 1e9 / peaks["hbm_gbs"]
         line["kernels_ms"] = kernels
         line["peaks"] = peaks
-        line["cpu_baseline"] = cpu_port_sample(rows=128, repeats=3, warmup=1)
+        line["cpu_baseline"] = cpu_port_sample(rows=128, repeats=3, warmup=1, min_seconds=10.0)
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

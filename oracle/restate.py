@@ -97,7 +97,7 @@ def port_step_rows(z, bj, r0: int, r1: int, dmax: float, temperature: float = 0.
     neg = sim.masked_select(mask).view(r1 - r0, -1).sum(dim=-1)
     loss = torch.log(neg).sum()
     loss.backward()
-    return float(loss), zr.grad
+    return float(loss.detach()), zr.grad
 
 
 # --------------------------------------------------------------------------------------
