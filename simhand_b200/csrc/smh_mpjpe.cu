@@ -18,13 +18,22 @@ namespace smh {
 // MODE 0: IEEE intrinsics (any input).  MODE 1: branch-free exact forms with the zero guard.  MODE 2: without the
 // guard (a coincident joint gives NaN; the caller repairs that pair with MODE 1).
 // distances of joints (2p, 2p+1) of one pair of samples
-template <int MODE>
+// APPROX (16-bit tile image only): one MUFU.SQRT per joint and no correction step -- the value is about to be rounded to
+// 16 bits, so the ~2^-22 relative error of the approximation is invisible, and sqrt(+0) = +0 needs no guard.  This takes
+// the two Newton FFMAs, the x * rsqrt(x) FMUL and the exponent decrement (3 of 8 FMA-pipe operations per joint) out of
+// the kernel: the XU pipe alone binds it.  The exact forms stay for the fp32 tiles (weights API, fp32 engine).
+template <int MODE, bool APPROX = false>
 __device__ __forceinline__ f2 joint_pair(const f2 ax, const f2 ay, const float *__restrict__ col, int p)
 {
     const float4 b = *reinterpret_cast<const float4 *>(col + 4 * p);   // (bx_2p, bx_2p+1, by_2p, by_2p+1)
     f2 dx = sub2(ax, pack2(b.x, b.y));
     f2 dy = sub2(ay, pack2(b.z, b.w));
     f2 x = fma2(dy, dy, mul2(dx, dx));
+    if (APPROX) {
+        float x0, x1;
+        unpack2(x, x0, x1);
+        return pack2(sqrt_approx(x0), sqrt_approx(x1));
+    }
     if (MODE == 2) return sqrt2_rn_fast_nz(x);
     if (MODE == 1) return sqrt2_rn_fast(x);
     float x0, x1;
@@ -34,28 +43,29 @@ __device__ __forceinline__ f2 joint_pair(const f2 ax, const f2 ay, const float *
 
 // Joints are evaluated in the order the ATen summation consumes them (16..20 first, then k and k+8 together), so only
 // two pair results are live at a time.
-// SUM: return the 21-term sum s instead of D = s / 21 (the 16-bit tile image scales s directly, and max_ij D_ij =
-// (max_ij s_ij) / 21 because the correctly rounded division is monotonic: one division per tile instead of one per pair).
+// SUM (16-bit tile image): return the 21-term sum s instead of D = s / 21 (the image scales s directly, and max_ij D_ij =
+// (max_ij s_ij) / 21: one division per tile instead of one per pair), with the approximate square roots of joint_pair.
 template <int MODE, bool SUM>
 __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10], float ax20, float ay20,
                                            const float *__restrict__ col, const DivConst &div21)
 {
     constexpr bool FAST = MODE != 0;
     float a, b;
-    unpack2(joint_pair<MODE>(ax[8], ay[8], col, 8), a, b);          // (n16, n17)
+    unpack2(joint_pair<MODE, SUM>(ax[8], ay[8], col, 8), a, b);          // (n16, n17)
     float s = __fadd_rn(a, b);
-    unpack2(joint_pair<MODE>(ax[9], ay[9], col, 9), a, b);          // (n18, n19)
+    unpack2(joint_pair<MODE, SUM>(ax[9], ay[9], col, 9), a, b);          // (n18, n19)
     s = __fadd_rn(s, a);
     s = __fadd_rn(s, b);
     {
         const float2 b20 = *reinterpret_cast<const float2 *>(col + 40);
         const float dx20 = __fsub_rn(ax20, b20.x), dy20 = __fsub_rn(ay20, b20.y);
         const float x20 = __fmaf_rn(dy20, dy20, __fmul_rn(dx20, dx20));
-        s = __fadd_rn(s, MODE == 2 ? sqrt_rn_fast_nz(x20) : (MODE == 1 ? sqrt_rn_fast(x20) : __fsqrt_rn(x20)));
+        s = __fadd_rn(s, SUM ? sqrt_approx(x20)
+                             : (MODE == 2 ? sqrt_rn_fast_nz(x20) : (MODE == 1 ? sqrt_rn_fast(x20) : __fsqrt_rn(x20))));
     }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-        f2 t = add2(joint_pair<MODE>(ax[p], ay[p], col, p), joint_pair<MODE>(ax[p + 4], ay[p + 4], col, p + 4));
+        f2 t = add2(joint_pair<MODE, SUM>(ax[p], ay[p], col, p), joint_pair<MODE, SUM>(ax[p + 4], ay[p + 4], col, p + 4));
         unpack2(t, a, b);                 // (n_2p + n_2p+8, n_2p+1 + n_2p+9)
         s = __fadd_rn(s, a);
         s = __fadd_rn(s, b);

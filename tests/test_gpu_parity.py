@@ -247,7 +247,8 @@ def test_q16_tile_image_matches_reference(golden, engine, monkeypatch):
     stats = aux["stats"].cpu().numpy().view(np.uint32)
     monkeypatch.setenv("SMH_Q16", "0")
     _, _, _, aux32 = ops.run_step(z1, z2, a, b, 0.5, engine, True, return_aux=True)
-    assert stats[0] == aux32["stats"].cpu().numpy().view(np.uint32)[0]          # Dmax stays exact
+    d16, d32 = stats[:1].view(np.float32)[0], aux32["stats"].cpu().numpy().view(np.float32)[0]
+    assert abs(float(d16) - float(d32)) <= 4e-7 * float(d32)      # Dmax from approximate square roots: a few ulp
 
 
 def test_q16_full_size_agrees_with_fp32_tiles(monkeypatch):
