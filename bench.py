@@ -333,7 +333,8 @@ def run_ours(args):
             note="frac counts the sqrt the kernel executes.  algorithmic_frac counts 21 per ORDERED pair (M^2, as the "
                  "reference evaluates them) over the same launch time and step_frac is SURVEY 8d's figure, "
                  "(21 sqrt + 1 exp) M^2 / whole step time over the MUFU peak: both exceed frac because symmetry "
-                 "halves the executed count.  The FMA pipe is co-critical (ncu: fma 66 %, xu 65 % busy).")
+                 "halves the executed count.  ncu (profiles/): xu 85 %, fma 54 % busy with the default 16-bit tile image "
+                 "(one MUFU.SQRT per joint); the exact-distance variant is fma/xu co-critical (66 % / 65 %).")
         tile_bytes = 32768.0 if ops.step_flags(engine) else 65536.0      # 16-bit image of the tiles, or fp32
         hbm_bytes = 8256 * tile_bytes * 2          # each stored tile is read direct + transposed
         for k in ("sweep_fwd", "sweep_bwd"):
