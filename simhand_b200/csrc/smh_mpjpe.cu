@@ -139,7 +139,7 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
 // stored tile (thread = row x 32 columns) -- twice as many, half as long CTAs, used when a rank has few tiles (sharded
 // runs) so that the last wave of the 2-CTAs-per-SM grid is not mostly empty (1032 tiles = 3.5 waves -> 7.0 waves).
 template <bool HALF, bool Q16>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, Q16 ? 3 : 2)
 mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m,
              Stats *__restrict__ stats, Peers peers)
 {
