@@ -5,6 +5,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -87,3 +88,24 @@ def test_rank_plans_partition_the_work():
     n, world = 8192, 8
     counts = [L.build_plan(n, 128, world, r)[0].n_stored_tiles for r in range(world)]
     assert sum(counts) == 128 * 129 // 2 and max(counts) == min(counts) == 1032
+
+
+def test_host_pipeline_and_step_flags_without_gpu(monkeypatch):
+    """Host-side behaviour that needs no device: the pipeline refuses a CPU device, and the tile-image flag follows the
+    engine / weighting / environment."""
+    import torch
+    from simhand_b200 import _lib, ops
+    from simhand_b200.pipeline import HostPipeline
+    with pytest.raises(RuntimeError):
+        HostPipeline(lambda *a: None, (torch.zeros(2, 2),), torch.device("cpu"))
+    monkeypatch.delenv("SMH_Q16", raising=False)
+    assert ops.step_flags("fp16") == _lib.DIMS_Q16_TILES and ops.step_flags("bf16") == _lib.DIMS_Q16_TILES
+    assert ops.step_flags("fp32") == 0 and ops.step_flags("fp16", neg_weighted=False) == 0
+    assert ops.step_flags("fp16", ops.make_weighting("non_linear", "mpjpe", 1.0, 0.05)) == 0
+    assert ops.step_flags("fp16", ops.make_weighting("linear", "w_abs")) == 0
+    monkeypatch.setenv("SMH_Q16", "0")
+    assert ops.step_flags("fp16") == 0
+    with pytest.raises(ValueError):
+        ops.make_weighting("cubic", "mpjpe")
+    with pytest.raises(ValueError):
+        ops.make_weighting("linear", "l1")
