@@ -222,3 +222,27 @@ def test_q16_tile_layout_mirrors():
     assert lib.smh_layout(ctypes.byref(_lib.Dims(64, 128, 1, 0, 0, _lib.DIMS_Q16_TILES, 1)), ctypes.byref(lo)) == -6
     assert lib.smh_layout(ctypes.byref(_lib.Dims(64, 128, 1, 0, 0, _lib.DIMS_Q16_TILES | _lib.DIMS_DENSE_WEIGHTS)),
                           ctypes.byref(lo)) == -6
+
+
+def test_plan_properties_random_shapes():
+    """Seeded sweep over odd shapes: every ordered 128 x 64 piece is covered exactly once across the ranks, strips never
+    mix row blocks, and the 16-bit tile flag changes the layout size but not the task list."""
+    rng = np.random.default_rng(7)
+    for _ in range(12):
+        world = int(rng.choice([1, 2, 4, 8]))
+        n = int(rng.integers(1, 90)) * world
+        m = 2 * n
+        tp = (m + 127) // 128
+        cover = np.zeros((tp, 2 * tp), np.int32)
+        for rank in range(world):
+            lay, (h, tiles, tasks, strips) = L.build_plan(n, 128, world, rank)
+            layq, (hq, tiles_q, tasks_q, strips_q) = L.build_plan(n, 128, world, rank, 0, _lib.DIMS_Q16_TILES)
+            assert layq.n_tasks == lay.n_tasks and layq.n_stored_tiles == lay.n_stored_tiles
+            assert sorted(map(tuple, tasks_q[:, :3])) == sorted(map(tuple, tasks[:, :3]))
+            assert lay.ws_bytes - lay.off_dist == 2 * (layq.ws_bytes - layq.off_dist)
+            for row, cj, lt, flags in tasks:
+                cover[row, cj] += 1
+            for a, b in strips:
+                assert len(set(tasks[a:b, 0])) == 1
+        live = np.array([[cj * 64 < m for cj in range(2 * tp)]] * tp)
+        assert (cover[live] == 1).all() and (cover[~live] == 0).all(), (n, world)
