@@ -17,7 +17,8 @@
 // Persistent CTAs (one per SM) walk strips of 128x64 tasks that share a 128-row block.  Warp roles:
 //   warp 0      tile producer: cp.async.bulk of the MPJPE tile halves (HBM), up to 3-4 tasks ahead, on mbarriers
 //   warp 18     operand producer: cp.async.bulk of the z blocks (pre-swizzled SWIZZLE_128B images, smh_prep.cu)
-//   warp 1      one elected thread issues tcgen05.mma and tcgen05.commit
+//   warp 1      one elected thread issues the logit tcgen05.mma and tcgen05.commit
+//   warp 19     (backward) one elected thread issues the value tcgen05.mma: dz += G z
 //   warps 2..17 epilogue, two groups of 8 warps taking alternate tasks; one row per thread (TMEM lane == row); two
 //               warps of a group share a TMEM lane quadrant and split the 64 columns of a task: tcgen05.ld -> weights -> ex2 -> row sums (forward) or tcgen05.st of G
 //               (backward); strip flush of dzacc with red.global.add.v4.f32
@@ -45,7 +46,7 @@ namespace smh {
 constexpr int kEpiGroups = 2;                            // epilogue groups take alternate tasks
 constexpr int kGroupWarps = 8;                           // 4 TMEM lane quadrants x 2 column halves
 constexpr int kEpiWarps = kEpiGroups * kGroupWarps;      // 16
-constexpr int kTcThreads = 64 + 32 * kEpiWarps + 32;     // 608: tile producer, MMA, 16 epilogue, operand producer
+constexpr int kTcThreads = 64 + 32 * kEpiWarps + 64;     // 640: tile producer, logit MMA, 16 epilogue, operand producer, value MMA
 constexpr int kSBufs = 4;                                // S / G buffers in TMEM (64 columns each)
 constexpr int kMaxBStages = 4;                           // z blocks come from L2
 constexpr int kMaxDStages = 8;                           // MPJPE tile pieces come from HBM: deeper prefetch
@@ -386,12 +387,9 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         // ------------------------------------------------------------------ MMA issuer (one elected lane issues; the
         // control flow and every operand stay warp-uniform, see elect_one)
         {
-            constexpr uint32_t idesc2 = umma_idesc_bf16(kTile, kD, 0, 1);
             const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-            uint32_t a_ph = 0, dz_ph = 0;
+            uint32_t a_ph = 0;
             uint32_t seq = 0;                       // logit MMAs issued so far by this CTA
-            uint32_t done2 = 0;                     // value MMAs issued so far (backward)
-            uint32_t first_mask = 0, last_mask = 0; // per pending task (bit = seq % 32): first / last of its strip
             TR_DECL(7);
             // logit contraction of task `seq` into S buffer seq % kSBufs (operands and buffer are known to be ready)
             auto mma1 = [&](bool last_of_strip) {
@@ -427,29 +425,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 }
                 __syncwarp();
             };
-            // value contraction of task q (the q-th task of this CTA): dz (+)= G_q z_J  (G and the accumulator are ready)
-            auto mma2 = [&](uint32_t q) {
-                const uint32_t sbq = q % kSBufs, bstq = q % kBStages;
-                const bool first = (first_mask >> (q & 31)) & 1u, last = (last_mask >> (q & 31)) & 1u;
-                tc_fence_after();
-                if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < kTaskN / 16; ++ks) {
-                    // MN-major bf16 B: 64-element (128 B) atoms along d at LBO = 8 KiB, 8-row K groups at SBO = 1 KiB,
-                    // 16 sample rows (2 KiB) per K step.  A = packed bf16 G: columns [0,16) hold task columns 0..31,
-                    // columns [32,48) hold task columns 32..63 (each epilogue half overwrites its own S columns).
-                    const uint64_t bdesc = umma_desc_sw128(sB_u + bstq * kBBytes + ks * 2048, 8192, 1024);
-                    const uint32_t a_col = (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u;
-                    tc_mma_ts_f16(tmem_base + kDzCol, tmem_base + sbq * kTaskN + a_col, bdesc, idesc2,
-                                  (first && ks == 0) ? 0u : 1u);
-                }
-                tc_commit(&bars->sg_empty[sbq]);
-                tc_commit(&bars->empty_b[bstq]);
-                if (last) tc_commit(&bars->dz_full);
-                }
-                __syncwarp();
-            };
-            if (!BWD) {
+            {
                 for (int s = s_begin; s < s_end; ++s) {
                     const int2 strip = strips[s];
                     TR_LAP(0);
@@ -465,77 +441,46 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                         TR_LAP(4);                                                  // [4] issuing the logit MMAs
                     }
                 }
-            } else if (s_begin < s_end) {
-                // Event-driven issue: the logit MMA of task t + k only needs its operands and a free S buffer, the
-                // value MMA of task t only needs G_t from the epilogue.  Issuing them in a fixed interleave makes the
-                // logit MMAs queue behind the epilogue of an older task; polling both conditions keeps up to kSBufs
-                // logit tiles ahead of the epilogue groups.
-                const uint32_t total = (uint32_t)(strips[s_end - 1].y - strips[s_begin].x);
-                int s1 = s_begin;                                // strip of the next logit MMA
-                int2 strip1 = strips[s1];
-                int ti1 = strip1.x;
-                bool a_ok = false;
-                uint32_t idle = 0;
-                const long long t0 = clock64();
-                while (done2 < total) {
-                    bool progress = false;
-                    // value MMA first: it frees an S buffer and a z block
-                    // (votes: every lane probes the same barrier; the vote makes the decision provably warp-uniform)
-                    if (done2 < seq &&
-                        __all_sync(0xffffffffu, mbar_test_wait(&bars->g_ready[done2 % kSBufs], (done2 / kSBufs) & 1u))) {
-                        const bool first = (first_mask >> (done2 & 31)) & 1u;
-                        if (!first || __all_sync(0xffffffffu, mbar_test_wait(&bars->dz_empty, dz_ph ^ 1u))) {
-                            if (first) dz_ph ^= 1u;
-                            TR_LAP(1);                                              // [1] polling before a value MMA
-                            mma2(done2++);
-                            TR_LAP(3);                                              // [3] issuing the value MMAs
-                            progress = true;
-                        }
-                    }
-                    if (seq < total && seq - done2 < (uint32_t)kSBufs) {
-                        if (!a_ok && __all_sync(0xffffffffu, mbar_test_wait(&bars->a_full, a_ph))) {
-                            a_ok = true;
-                            a_ph ^= 1u;
-                        }
-                        if (a_ok &&
-                            __all_sync(0xffffffffu, mbar_test_wait(&bars->full_b[seq % kBStages], (seq / kBStages) & 1u) &&
-                                                        mbar_test_wait(&bars->sg_empty[seq % kSBufs],
-                                                                       ((seq / kSBufs) & 1u) ^ 1u))) {
-                            const uint32_t bit = 1u << (seq & 31);
-                            const bool last1 = ti1 + 1 == strip1.y;
-                            first_mask = (ti1 == strip1.x) ? (first_mask | bit) : (first_mask & ~bit);
-                            last_mask = last1 ? (last_mask | bit) : (last_mask & ~bit);
-                            TR_LAP(2);                                              // [2] polling before a logit MMA
-                            mma1(last1);
-                            TR_LAP(4);                                              // [4] issuing the logit MMAs
-                            ++seq;
-                            if (last1) {
-                                a_ok = false;
-                                if (++s1 < s_end) {
-                                    strip1 = strips[s1];
-                                    ti1 = strip1.x;
-                                }
-                            } else {
-                                ++ti1;
-                            }
-                            progress = true;
-                        }
-                    }
-                    if (progress) {
-                        idle = 0;
-                        TR_LAP(0);
-                    } else {
-                        TR_LAP(5);                                                  // [5] polls that found nothing ready
-                    }
-                    if (progress) {
-                    } else if ((++idle & 1023u) == 0u &&
-                               __any_sync(0xffffffffu, clock64() - t0 > 4000000000ll || *(volatile uint32_t *)fail != 0u)) {
-                        if (lane == 0) atomicCAS(fail, 0u, 7u);
-                        break;
-                    }
-                }
             }
             if (lane == 0) TR_STORE(2, 7);
+        }
+    } else if (BWD && warp == 3 + kEpiWarps) {
+        // ------------------------------------------------------------------ value-MMA issuer (backward only).  A second
+        // issuing warp: the logit MMAs (warp 1) wait for operands and S buffers, the value MMAs for G from the epilogue;
+        // with one thread doing both, each kind queued behind the other's waits (first a fixed interleave, then a polling
+        // loop that spent half its time polling).  tcgen05.commit tracks the MMAs of the committing thread, and every
+        // dependency between the two streams goes through an mbarrier, so they need no ordering between them.
+        constexpr uint32_t idesc2 = umma_idesc_bf16(kTile, kD, 0, 1);
+        const uint32_t sB_u = smem_u32(sB);
+        uint32_t q = 0, dz_ph = 0;
+        for (int s = s_begin; s < s_end; ++s) {
+            const int2 strip = strips[s];
+            for (int ti = strip.x; ti < strip.y; ++ti, ++q) {
+                const uint32_t sbq = q % kSBufs, bstq = q % kBStages;
+                const bool first = ti == strip.x, last = ti + 1 == strip.y;
+                mbar_wait(&bars->g_ready[sbq], (q / kSBufs) & 1u, fail, 4);
+                if (first) {
+                    mbar_wait(&bars->dz_empty, dz_ph ^ 1u, fail, 5);
+                    dz_ph ^= 1u;
+                }
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < kTaskN / 16; ++ks) {
+                        // MN-major bf16 B: 64-element (128 B) atoms along d at LBO = 8 KiB, 8-row K groups at SBO = 1 KiB,
+                        // 16 sample rows (2 KiB) per K step.  A = packed bf16 G: columns [0,16) hold task columns 0..31,
+                        // columns [32,48) hold task columns 32..63 (each epilogue half overwrites its own S columns).
+                        const uint64_t bdesc = umma_desc_sw128(sB_u + bstq * kBBytes + ks * 2048, 8192, 1024);
+                        const uint32_t a_col = (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u;
+                        tc_mma_ts_f16(tmem_base + kDzCol, tmem_base + sbq * kTaskN + a_col, bdesc, idesc2,
+                                      (first && ks == 0) ? 0u : 1u);
+                    }
+                    tc_commit(&bars->sg_empty[sbq]);
+                    tc_commit(&bars->empty_b[bstq]);
+                    if (last) tc_commit(&bars->dz_full);
+                }
+                __syncwarp();
+            }
         }
     } else if (warp >= 2 && warp < 2 + kEpiWarps) {
         // ------------------------------------------------------------------ epilogue (warps 2..17)
