@@ -1,28 +1,28 @@
-// simhand_b200 K1/K2, tensor-core engines (SMH_ENGINE_TC_TF32 / SMH_ENGINE_TC_BF16): the fused forward / backward sweeps.
+// simhand_b200 K1/K2, tensor-core engines (SMH_ENGINE_TC_FP16 / _TF32 / _BF16): the fused forward / backward sweeps.
 //
-//   forward  (src/models/utils.py:411-417): S = z z^T on tcgen05 (kind::tf32 from the tf32 image of z, or kind::f16
-//            from its bf16 image in the bf16 engine; fp32 accumulate in TMEM); the
-//            epilogue turns each S tile into E = exp(S * W / tau) with W built on the fly from the stored MPJPE
-//            tile (W = (Dmax - D) / Dmax, correctly rounded), masks the diagonal and accumulates the row sums.
-//            The 2N x 2N logit matrix never leaves the SM.
+//   forward  (src/models/utils.py:411-417): S = z z^T on tcgen05 (kind::f16 from the fp16 or bf16 image of z, or kind::tf32
+//            from its tf32 image; fp32 accumulate in TMEM); the epilogue turns each S tile into E = exp(S * W / tau) with
+//            W * log2(e) / tau built on the fly from the staged distance tile (one FFMA per weight), masks the diagonal and
+//            accumulates the row sums.  The 2N x 2N logit matrix never leaves the SM.
 //   backward (autograd of :411-426): the same S tile and weights; the epilogue writes
 //            G = W E (1/neg_i + 1/neg_j) back into the TMEM columns S came from (packed bf16) and a second
 //            tcgen05.mma (kind::f16: A = G from TMEM, B = the staged bf16 z block read MN-major; tf32 operands
 //            cannot be read MN-major from a SWIZZLE_128B image) accumulates dzacc_I += G z_J in fp32 in TMEM
 //            across the whole strip; the softmax is never materialised.  The backward recomputes S from the bf16
-//            image in both engines (its effect on the gradient is ~1e-5 max|g|, below the bf16 rounding of G), which
+//            image in every engine (its effect on the gradient is ~1e-5 max|g|, below the bf16 rounding of G), which
 //            lets one staged bf16 block serve both contractions (K-major for S, MN-major for dz) and frees the
-//            shared memory for a deeper prefetch of the MPJPE tiles.
+//            shared memory for a deeper prefetch of the distance tiles.
 //
-// Persistent CTAs (one per SM) walk strips of 128x64 tasks that share a 128-row block.  Warp roles:
-//   warp 0      tile producer: cp.async.bulk of the MPJPE tile halves (HBM), up to 3-4 tasks ahead, on mbarriers
+// Persistent CTAs (one per SM, 640 threads) walk strips of 128x64 tasks that share a 128-row block.  Warp roles:
+//   warp 0      tile producer: cp.async.bulk of the distance-tile halves (fp32, or the 16-bit image: 8 stages), on mbarriers
 //   warp 18     operand producer: cp.async.bulk of the z blocks (pre-swizzled SWIZZLE_128B images, smh_prep.cu)
-//   warp 1      one elected thread issues the logit tcgen05.mma and tcgen05.commit
-//   warp 19     (backward) one elected thread issues the value tcgen05.mma: dz += G z
+//   warp 1      issues the logit tcgen05.mma and tcgen05.commit
+//   warp 19     (backward) issues the value tcgen05.mma: dz += G z
 //   warps 2..17 epilogue, two groups of 8 warps taking alternate tasks; one row per thread (TMEM lane == row); two
-//               warps of a group share a TMEM lane quadrant and split the 64 columns of a task: tcgen05.ld -> weights -> ex2 -> row sums (forward) or tcgen05.st of G
-//               (backward); strip flush of dzacc with red.global.add.v4.f32
-// Every pipeline wait is bounded (smh_common.cuh: mbar_wait) so a protocol bug cannot hang the device.
+//               warps of a group share a TMEM lane quadrant and split the 64 columns of a task: tcgen05.ld -> weights ->
+//               ex2 -> row sums (forward) or tcgen05.st of G (backward); strip flush of dzacc with red.global.add.v4.f32
+// The single-thread roles run their control flow warp-uniformly and guard only the issuing instruction with elect.sync
+// (smh_common.cuh: elect_one).  Every pipeline wait is bounded (mbar_wait) so a protocol bug cannot hang the device.
 #include "smh_common.cuh"
 #include "smh_internal.h"
 
