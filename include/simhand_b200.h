@@ -235,6 +235,12 @@ int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev,
                  float *loss_dev, float *dz1_dev, float *dz2_dev, int64_t dz_row_stride,
                  int flags, const smh_exchange_t *exch, void *stream);
 
+/* autograd backward of the fused loss (the gradients were produced with the forward): out1 = *scale_dev * dz1,
+ * out2 = *scale_dev * dz2 over `count` contiguous floats each, one launch (the upstream gradient of the 0-dim loss
+ * stays on the device). */
+int smh_scale_grads(const float *dz1_dev, const float *dz2_dev, const float *scale_dev, float *out1_dev, float *out2_dev,
+                    int64_t count, void *stream);
+
 /* materialised weights with the reference's return shapes: pos_w [N], neg_w [M, M] row-major
  * (utils.py:235, :259).  world == 1 only.  Needs smh_prep + smh_mpjpe. */
 int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev,

@@ -31,6 +31,9 @@ CASES = [
     ("r33_d64_crop_rot", 33, 64, True, True, 14),
     ("r16_d6_crop_rot", 16, 6, True, True, 15),            # d not a multiple of 4
     ("r20_d128_plain", 20, 128, False, False, 16),         # two normalisations only
+    ("r24_d64_crop", 24, 64, True, False, 17),             # crop only with d < 128: padding lanes must not move
+    ("r12_d6_crop", 12, 6, True, False, 18),               # crop only, d % 4 == 2: half-used lane
+    ("r12_d30_rot", 12, 30, False, True, 19),              # rotate only, d % 4 == 2
 ]
 
 

@@ -79,7 +79,8 @@ class Stats(ctypes.Structure):
 EXPORTS = ("smh_version", "smh_last_error", "smh_layout", "smh_plan_build", "smh_prep", "smh_mpjpe",
            "smh_forward", "smh_backward", "smh_finalize", "smh_weights_dense", "smh_l2norm_fwd",
            "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params", "smh_push_inputs",
-           "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz", "smh_import_weights", "smh_transform_fwd", "smh_transform_bwd")
+           "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz", "smh_import_weights", "smh_transform_fwd", "smh_transform_bwd",
+           "smh_scale_grads")
 
 _lib = None
 
@@ -112,6 +113,7 @@ def load() -> ctypes.CDLL:
     lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, ctypes.c_int, ctypes.POINTER(Exchange), vp]
     lib.smh_weights_dense.argtypes = [pd, vp, vp, vp, vp, vp]
     lib.smh_import_weights.argtypes = [pd, vp, vp, vp, i64, vp, vp]
+    lib.smh_scale_grads.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     lib.smh_l2norm_fwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     lib.smh_l2norm_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]
     lib.smh_transform_fwd.argtypes = [vp, i64, vp, vp, vp, vp, i64, vp, i64, i32, f32, vp]

@@ -586,6 +586,14 @@ int smh_barrier(const smh_exchange_t *exch, void *stream)
     return launch_barrier(*exch, (cudaStream_t)stream);
 }
 
+int smh_scale_grads(const float *dz1_dev, const float *dz2_dev, const float *scale_dev, float *out1_dev, float *out2_dev,
+                    int64_t count, void *stream)
+{
+    if (!dz1_dev || !dz2_dev || !scale_dev || !out1_dev || !out2_dev) return set_error(SMH_E_ARG, "scale_grads: null pointer");
+    if (count <= 0) return set_error(SMH_E_ARG, "scale_grads: count must be positive");
+    return launch_scale_pair(dz1_dev, dz2_dev, scale_dev, out1_dev, out2_dev, count, (cudaStream_t)stream);
+}
+
 int smh_l2norm_fwd(const float *x_dev, float *y_dev, float *norm_dev, int64_t rows, int32_t d, float eps,
                    void *stream)
 {

@@ -355,6 +355,41 @@ l2norm_bwd_kernel(const float *__restrict__ y, const float *__restrict__ norm, c
     }
 }
 
+// autograd backward of the fused loss: both saved gradients times the upstream scalar, one launch
+__global__ void __launch_bounds__(256)
+scale_pair_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, const float *__restrict__ scale,
+                  float4 *__restrict__ oa, float4 *__restrict__ ob, int64_t n4, int64_t tail_from,
+                  const float *__restrict__ at, const float *__restrict__ bt, float *__restrict__ oat,
+                  float *__restrict__ obt, int64_t count)
+{
+    const float s = __ldg(scale);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 va = a[i], vb = b[i];
+        oa[i] = make_float4(s * va.x, s * va.y, s * va.z, s * va.w);
+        ob[i] = make_float4(s * vb.x, s * vb.y, s * vb.z, s * vb.w);
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = tail_from + threadIdx.x; i < count; i += blockDim.x) {
+            oat[i] = s * at[i];
+            obt[i] = s * bt[i];
+        }
+}
+
+int launch_scale_pair(const float *a, const float *b, const float *scale, float *oa, float *ob, int64_t count,
+                      cudaStream_t stream)
+{
+    const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(oa) |
+                       reinterpret_cast<uintptr_t>(ob)) & 15) == 0;
+    const int64_t n4 = vec ? count / 4 : 0;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    scale_pair_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b),
+                                                       scale, reinterpret_cast<float4 *>(oa), reinterpret_cast<float4 *>(ob),
+                                                       n4, n4 * 4, a, b, oa, ob, count);
+    return check_launch("scale_pair_kernel");
+}
+
 int launch_l2norm_fwd(const float *x, float *y, float *norm, int64_t rows, int d, float eps, cudaStream_t stream)
 {
     int64_t blocks = (rows + 7) / 8;

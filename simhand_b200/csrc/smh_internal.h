@@ -58,6 +58,8 @@ int launch_finalize(const smh_dims_t &dims, const smh_layout_t &lay, const smh_i
                     const Peers &peers, cudaStream_t stream);
 int launch_weights_dense(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
                          float *pos_w, float *neg_w, cudaStream_t stream);
+int launch_scale_pair(const float *a, const float *b, const float *scale, float *oa, float *ob, int64_t count,
+                      cudaStream_t stream);
 int launch_l2norm_fwd(const float *x, float *y, float *norm, int64_t rows, int d, float eps, cudaStream_t stream);
 int launch_l2norm_bwd(const float *y, const float *norm, const float *dy, float *dx, int64_t rows, int d,
                       float eps, cudaStream_t stream);

@@ -52,10 +52,9 @@ transform_fwd_kernel(const float *__restrict__ x, int64_t x_stride, const float 
             const float mxy = warp_max(fmaxf(p0 ? v[1] : -big, p1 ? v[3] : -big));
             const float mny = warp_min(fminf(p0 ? v[1] : big, p1 ? v[3] : big));
             const float sx = tx[row] * (mxx - mnx), sy = ty[row] * (mxy - mny);
-            v[0] += sx;
-            v[2] += sx;
-            v[1] += sy;
-            v[3] += sy;
+            // only points that exist move: padding lanes (4 lane + u >= d) must stay 0 for the second norm
+            if (p0) { v[0] += sx; v[1] += sy; }
+            if (p1) { v[2] += sx; v[3] += sy; }
         }
         float a = 1.f, b = 0.f;
         if (angle != nullptr) {

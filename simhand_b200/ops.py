@@ -95,12 +95,24 @@ def get_context(n: int, d: int, world: int, rank: int, device, strip_len: int = 
     return ctx
 
 
-def step_flags(engine_name: str, weighting=None, neg_weighted: bool = True) -> int:
-    """smh_dims_t.flags of the fused step.  The tensor-core engines stage the 16-bit image of the distance tiles
-    (SMH_DIMS_Q16_TILES: half the workspace, half the tile bytes and twice the prefetch depth of the sweeps; W within
-    1.6e-5, far inside the 2^-11 operand rounding of the logits; Dmax exact) when the weights are the linear / mpjpe
-    ones built from the joints.  SMH_Q16=0 in the environment keeps fp32 tiles."""
-    if os.environ.get("SMH_Q16", "1") == "0" or engine_name == "fp32" or not neg_weighted:
+def exact_weights_default() -> bool:
+    """Process-wide default of `exact_weights` (see step_flags): SMH_EXACT_WEIGHTS=1 or SMH_Q16=0 in the environment."""
+    return os.environ.get("SMH_EXACT_WEIGHTS", "0") == "1" or os.environ.get("SMH_Q16", "1") == "0"
+
+
+def step_flags(engine_name: str, weighting=None, neg_weighted: bool = True, exact_weights: Optional[bool] = None) -> int:
+    """smh_dims_t.flags of the fused step: which image of the joint distances the sweeps read.
+
+    exact_weights=True: fp32 tiles holding the bit-exact MPJPE of the reference (0 ulp; Dmax bit-exact), i.e. the
+    weights inside the fused loss are the ones the weights API materialises.
+    exact_weights=False (default for the tensor-core engines with linear / mpjpe weights): SMH_DIMS_Q16_TILES, a 16-bit
+    fixed-point image built from approximate square roots: |D error| <= Dbound / 130000 + ~2e-6 D, |W error| <= 1.6e-5
+    (hundreds of ulp -- NOT the 1-ulp weight contract; it rides inside the 2^-11 operand rounding of the logits), Dmax
+    within 4e-7 relative.  Half the workspace and tile bytes, twice the prefetch depth of the sweeps.
+    None: exact_weights_default() (environment)."""
+    if exact_weights is None:
+        exact_weights = exact_weights_default()
+    if exact_weights or engine_name == "fp32" or not neg_weighted:
         return 0
     if tuple(weighting or DEFAULT_WEIGHTING) != DEFAULT_WEIGHTING:
         return 0
@@ -146,11 +158,13 @@ def _stream_ptr(device) -> int:
 
 def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _DEFAULT_ENGINE,
              want_grad: bool = True, grad_scale: float = 1.0, strip_len: int = 0, return_aux: bool = False,
-             pos_weighted: bool = True, neg_weighted: bool = True, weighting=None):
+             pos_weighted: bool = True, neg_weighted: bool = True, weighting=None,
+             exact_weights: Optional[bool] = None):
     """One fused fwd(+bwd) step on a single GPU.  Returns (loss[()], dz1, dz2[, aux]).
     pos_weighted / neg_weighted = False give the reference's neg-only / pos-only / unweighted losses
     (utils.py:468, :430, :157): the corresponding weight is 1.  weighting = make_weighting(...) selects
-    weight_type linear / non_linear and diff_type mpjpe / w_abs / w_o_abs (utils.py:218-261, :304-346)."""
+    weight_type linear / non_linear and diff_type mpjpe / w_abs / w_o_abs (utils.py:218-261, :304-346).
+    exact_weights: see step_flags (True = bit-exact distances inside the fused step)."""
     for t, nm in ((z1, "z1"), (z2, "z2"), (joints1, "joints1"), (joints2, "joints2")):
         _require_cuda(t, nm)
     lib = _lib.load()
@@ -159,7 +173,8 @@ def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _
     engine_name = resolve_engine(engine, n)
     eng = _lib.ENGINES[engine_name]
     with torch.cuda.device(dev):
-        ctx = get_context(n, d, 1, 0, dev, strip_len, step_flags(engine_name, weighting, neg_weighted), weighting)
+        ctx = get_context(n, d, 1, 0, dev, strip_len, step_flags(engine_name, weighting, neg_weighted, exact_weights),
+                          weighting)
         lay, dims = ctx.layout, ctx.dims
         inp, keep = make_inputs(z1, z2, joints1, joints2)
         ws = torch.empty(int(lay.ws_bytes), dtype=torch.uint8, device=dev)
@@ -183,7 +198,7 @@ def run_step(z1, z2, joints1, joints2, temperature: float = 0.5, engine: str = _
         del keep
         if return_aux:
             aux = dict(ws=ws, ctx=ctx, neg=ctx.view(ws, lay.off_neg, lay.m),
-                       stats=ctx.view(ws, lay.off_stats, 8, torch.int32),
+                       stats=ctx.view(ws, lay.off_stats, 12, torch.int32),
                        posd=ctx.view(ws, lay.off_posd, n))
             return loss, dz1, dz2, aux
     return loss, dz1, dz2
@@ -256,6 +271,22 @@ def run_step_dense(z1, z2, pos_weights, neg_weights, temperature: float = 0.5, e
     return loss, dz1, dz2
 
 
+def _scale_saved_grads(ctx, grad_out):
+    """backward() of the fused losses: the gradients were computed with the forward; one launch scales both by the
+    upstream gradient of the 0-dim loss (which stays on the device)."""
+    dz1, dz2 = ctx.saved_tensors
+    if not (ctx.needs_input_grad[0] and ctx.needs_input_grad[1]) or not dz1.is_contiguous() or not dz2.is_contiguous():
+        return (grad_out * dz1 if ctx.needs_input_grad[0] else None,
+                grad_out * dz2 if ctx.needs_input_grad[1] else None)
+    lib = _lib.load()
+    g = grad_out.reshape(1).to(dtype=torch.float32)
+    o1, o2 = torch.empty_like(dz1), torch.empty_like(dz2)
+    with torch.cuda.device(dz1.device):
+        check(lib.smh_scale_grads(dz1.data_ptr(), dz2.data_ptr(), g.data_ptr(), o1.data_ptr(), o2.data_ptr(),
+                                  dz1.numel(), _stream_ptr(dz1.device)), "smh_scale_grads")
+    return o1, o2
+
+
 class _DenseWeightedNTXentFn(torch.autograd.Function):
     """Weighted NT-Xent with materialised weight tensors (no gradient flows to the weights, as in the reference,
     where they are built from the joints outside the graph)."""
@@ -272,9 +303,7 @@ class _DenseWeightedNTXentFn(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_out):
-        dz1, dz2 = ctx.saved_tensors
-        g1 = grad_out * dz1 if ctx.needs_input_grad[0] else None
-        g2 = grad_out * dz2 if ctx.needs_input_grad[1] else None
+        g1, g2 = _scale_saved_grads(ctx, grad_out)
         return g1, g2, None, None, None, None
 
 
@@ -285,16 +314,18 @@ class _WeightedNTXentFn(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, z1, z2, joints1, joints2, temperature, engine, group, pos_weighted=True, neg_weighted=True,
-                weighting=None):
+                weighting=None, exact_weights=None, grad_scale=1.0):
         want = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         if group is None:
-            loss, dz1, dz2 = run_step(z1, z2, joints1, joints2, temperature, engine, want,
-                                      pos_weighted=pos_weighted, neg_weighted=neg_weighted, weighting=weighting)
+            loss, dz1, dz2 = run_step(z1, z2, joints1, joints2, temperature, engine, want, grad_scale,
+                                      pos_weighted=pos_weighted, neg_weighted=neg_weighted, weighting=weighting,
+                                      exact_weights=exact_weights)
         else:
             if not (pos_weighted and neg_weighted) or tuple(weighting or DEFAULT_WEIGHTING) != DEFAULT_WEIGHTING:
                 raise NotImplementedError("the sharded path implements linear / mpjpe / pos_neg weighting only")
             from .dist import run_step_sharded
-            loss, dz1, dz2 = run_step_sharded(z1, z2, joints1, joints2, temperature, engine, want, group)
+            loss, dz1, dz2 = run_step_sharded(z1, z2, joints1, joints2, temperature, engine, want, group, grad_scale,
+                                              exact_weights=exact_weights)
         if want:
             ctx.save_for_backward(dz1, dz2)
         return loss
@@ -302,21 +333,23 @@ class _WeightedNTXentFn(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, grad_out):
-        dz1, dz2 = ctx.saved_tensors
-        g1 = grad_out * dz1 if ctx.needs_input_grad[0] else None
-        g2 = grad_out * dz2 if ctx.needs_input_grad[1] else None
-        return g1, g2, None, None, None, None, None, None, None, None
+        g1, g2 = _scale_saved_grads(ctx, grad_out)
+        return g1, g2, None, None, None, None, None, None, None, None, None, None
 
 
 def weighted_ntxent(z1: torch.Tensor, z2: torch.Tensor, joints1: torch.Tensor, joints2: torch.Tensor,
                     temperature: float = 0.5, group=None, engine: str = _DEFAULT_ENGINE,
-                    pos_weighted: bool = True, neg_weighted: bool = True, weighting=None) -> torch.Tensor:
+                    pos_weighted: bool = True, neg_weighted: bool = True, weighting=None,
+                    exact_weights: Optional[bool] = None, grad_scale: float = 1.0) -> torch.Tensor:
     """Fused similarity-weighted NT-Xent (weight_type linear, diff_type mpjpe, pos_neg): equals
     `vanila_weights_contrastive_loss(z1, z2, *get_weights_linear(joints1, joints2, 'mpjpe'), temperature)`
     of the reference.  With `group` (a torch.distributed process group) the batch is the concatenation of
-    every rank's local batch and the work is sharded over the ranks."""
+    every rank's local batch and the work is sharded over the ranks: every rank gets the GLOBAL loss and
+    d(global loss)/d(its local z).  `grad_scale` multiplies the gradients only: DistributedDataParallel averages
+    parameter gradients over the ranks, so pass grad_scale=world_size under DDP to obtain the gradient of the
+    global-batch loss.  exact_weights: see ops.step_flags."""
     return _WeightedNTXentFn.apply(z1, z2, joints1, joints2, float(temperature), engine, group,
-                                   bool(pos_weighted), bool(neg_weighted), weighting)
+                                   bool(pos_weighted), bool(neg_weighted), weighting, exact_weights, float(grad_scale))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -350,8 +383,27 @@ class LazyWeights:
         n = self._source.joints1.shape[0]
         return torch.Size([n]) if self.kind == "pos" else torch.Size([2 * n, 2 * n])
 
-    def __getattr__(self, name):            # anything else: act on the real tensor
-        return getattr(self.materialize(), name)
+    @property
+    def device(self):
+        return self._source.joints1.device
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    def dim(self):
+        return len(self.shape)
+
+    def size(self, i=None):
+        return self.shape if i is None else self.shape[i]
+
+    def __getattr__(self, name):
+        # A handle is not a tensor: building the [2N, 2N] matrix (1 GiB at 2N = 16384) is never done behind the
+        # caller's back.  Tensor code that needs the values calls .materialize().
+        if name.startswith("__"):
+            raise AttributeError(name)
+        raise AttributeError(f"LazyWeights has no attribute {name!r}: it stands for the {self.kind} weights of "
+                             f"get_weights_*; call .materialize() for the real tensor of shape {tuple(self.shape)}")
 
     def __repr__(self):
         return f"LazyWeights(kind={self.kind!r}, shape={tuple(self.shape)})"
@@ -399,7 +451,8 @@ def get_weights_nonlinear(joints1: torch.Tensor, joints2: torch.Tensor, lambda_p
 
 
 def vanila_weights_contrastive_loss(z1: torch.Tensor, z2: torch.Tensor, pos_weights, neg_weights,
-                                    temperature: float = 0.5, engine: str = _DEFAULT_ENGINE) -> torch.Tensor:
+                                    temperature: float = 0.5, engine: str = _DEFAULT_ENGINE,
+                                    exact_weights: Optional[bool] = None) -> torch.Tensor:
     """Drop-in for `src/models/utils.py:391`: mean-reduced weighted NT-Xent, differentiable in z1, z2."""
     if isinstance(pos_weights, LazyWeights) and isinstance(neg_weights, LazyWeights):
         if pos_weights._source is not neg_weights._source or pos_weights.kind != "pos" or neg_weights.kind != "neg":
@@ -407,7 +460,8 @@ def vanila_weights_contrastive_loss(z1: torch.Tensor, z2: torch.Tensor, pos_weig
         src = pos_weights._source
         if src.joints1.shape[0] != z1.shape[0]:
             raise ValueError(f"weights were built for batch {src.joints1.shape[0]}, z1 has {z1.shape[0]}")
-        return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, weighting=src.weighting)
+        return weighted_ntxent(z1, z2, src.joints1, src.joints2, temperature, None, engine, weighting=src.weighting,
+                               exact_weights=exact_weights)
     if isinstance(pos_weights, LazyWeights):
         pos_weights = pos_weights.materialize()
     if isinstance(neg_weights, LazyWeights):

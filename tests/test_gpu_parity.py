@@ -227,39 +227,3 @@ def test_l2_normalize_matches_torch():
         (y2 * w).sum().backward()
         assert torch.allclose(x1.grad[1:], x2.grad[1:], rtol=1e-4, atol=1e-6)
 
-
-@pytest.mark.parametrize("engine", ["fp16", "bf16", "tf32"])
-def test_q16_tile_image_matches_reference(golden, engine, monkeypatch):
-    """SMH_DIMS_Q16_TILES (opt-in, SMH_Q16=1): the sweeps stage a 16-bit fixed-point image of the distance tiles.  Same
-    tolerances as the fp32 tiles, and the step really runs on the flagged layout."""
-    monkeypatch.setenv("SMH_Q16", "1")
-    z1, z2, a, b = _to_dev(golden)
-    if z1.shape[0] < 8:
-        pytest.skip("tensor-core logits over < 16 samples do not average to 1e-5")
-    assert ops.step_flags(engine) == _lib.DIMS_Q16_TILES
-    loss, g1, g2, aux = ops.run_step(z1, z2, a, b, 0.5, engine, True, return_aux=True)
-    assert aux["ctx"].dims.flags == _lib.DIMS_Q16_TILES
-    ref = float(golden["loss_f64"])
-    assert abs(float(loss) - ref) <= (1e-3 if engine == "bf16" else LOSS_RTOL) * abs(ref)
-    for got, key in ((g1, "dz1_f64"), (g2, "dz2_f64")):
-        cos, mx = R.grad_metrics(got.cpu().numpy(), golden[key])
-        assert cos >= GRAD_COS and mx <= GRAD_MAXABS
-    stats = aux["stats"].cpu().numpy().view(np.uint32)
-    monkeypatch.setenv("SMH_Q16", "0")
-    _, _, _, aux32 = ops.run_step(z1, z2, a, b, 0.5, engine, True, return_aux=True)
-    d16, d32 = stats[:1].view(np.float32)[0], aux32["stats"].cpu().numpy().view(np.float32)[0]
-    assert abs(float(d16) - float(d32)) <= 4e-7 * float(d32)      # Dmax from approximate square roots: a few ulp
-
-
-def test_q16_full_size_agrees_with_fp32_tiles(monkeypatch):
-    from simhand_b200 import synth as S
-    dev = _dev()
-    z1, z2, j1, j2 = S.make_batch(8192, 128, 41, "uniform")
-    z1, z2, a, b = z1.to(dev), z2.to(dev), j1.to(dev)[:, :, :2], j2.to(dev)[:, :, :2]
-    monkeypatch.setenv("SMH_Q16", "1")
-    lq, gq, _ = ops.run_step(z1, z2, a, b, 0.5, "fp16", True)
-    monkeypatch.setenv("SMH_Q16", "0")
-    lf, gf, _ = ops.run_step(z1, z2, a, b, 0.5, "fp16", True)
-    assert abs(float(lq) - float(lf)) <= 2e-6 * abs(float(lf))
-    cos, mx = R.grad_metrics(gq.cpu().numpy(), gf.cpu().numpy())
-    assert cos >= 0.999999 and mx <= 1e-4
