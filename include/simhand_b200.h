@@ -68,6 +68,9 @@ extern "C" {
  * needs no closing barrier. */
 #define SMH_FINALIZE_LOSS_PART 0x4000
 #define SMH_FINALIZE_GRAD 0x8000
+/* Fused exchange (exch->fused): smh_finalize takes the rank's LOCAL inputs (as smh_shard_prep), waits for the gradient
+ * partials of every rank, writes the local gradients and the loss of the GLOBAL batch, which every rank evaluates in the
+ * same fixed order from the delivered row sums and positive-pair terms (no further exchange). */
 
 /* smh_dims_t.flags */
 #define SMH_DIMS_DENSE_WEIGHTS 1  /* materialised-weights path (the reference's two-call API with real tensors,
@@ -121,6 +124,8 @@ typedef struct smh_layout {
     int64_t off_negparts;        /* [world][Tp*128] fp32 row-sum partials received from the ranks (peer exchange) */
     int64_t off_dzparts;         /* [world][2*n_local][128] fp32 gradient partials received from the ranks (peer exchange) */
     int64_t off_dist;            /* stored MPJPE tiles of this rank, 64 KiB each */
+    int64_t off_posinfo;         /* (world > 1) [2 parities][2][N] fp32: positive-pair distance and <z1_k, z2_k> of every
+                                  * sample, delivered by the owning ranks (fused exchange) */
     int32_t m;                   /* 2N */
     int32_t tiles_per_side;      /* Tp = ceil(M / 128) */
     int32_t n_stored_tiles;      /* upper-triangular 128x128 tiles assigned to this rank */
@@ -170,11 +175,22 @@ typedef struct smh_inputs {
  * finalize) add the `world` partials in rank order, so the reduction is deterministic; smh_barrier separates the
  * phases.  Without it (exch == NULL) the caller runs all-reduce / reduce-scatter between the calls. */
 #define SMH_MAX_PEERS 8
+#define SMH_SIGNAL_WORDS 256             /* uint32 words of a rank's signal block */
+#define SMH_SIG_EPOCH 16                 /* word: steps this rank has started (fused exchange) */
+#define SMH_SIG_POISON 17                /* word: != 0 once any cross-rank wait of the group timed out (sticky; every later
+                                          * loss is NaN until the exchange is rebuilt); value = site of the first failure */
 typedef struct smh_exchange {
     int32_t world, rank;
     void *ws_peer[SMH_MAX_PEERS];        /* workspace blob of every rank (ws_peer[rank] == the local ws_dev) */
-    void *xin_peer[SMH_MAX_PEERS];       /* gathered-input buffer of every rank: world x chunk floats */
-    void *signal_peer[SMH_MAX_PEERS];    /* 64 x uint32 barrier words of every rank (zero-initialised once) */
+    void *xin_peer[SMH_MAX_PEERS];       /* gathered-input buffer of every rank: world x chunk floats (unused when fused) */
+    void *signal_peer[SMH_MAX_PEERS];    /* SMH_SIGNAL_WORDS x uint32 of every rank (zero-initialised once) */
+    int32_t fused;                       /* 0: phases separated by smh_barrier launches (smh_push_inputs / smh_prep /
+                                          * smh_exchange_*).  1: fused exchange -- smh_shard_prep ships every rank's operand
+                                          * images, and the cross-rank signals and payloads ride in the heads and tails of
+                                          * smh_mpjpe / smh_forward / smh_backward / smh_finalize (6 launches per step, no
+                                          * barrier or exchange kernels).  The workspaces must be zero-filled once. */
+    uint32_t timeout_ms;                 /* bound of every cross-rank wait; 0 = 30000.  A timeout poisons the group
+                                          * (SMH_SIG_POISON on every rank) and the loss is NaN: never a silent wrong result */
 } smh_exchange_t;
 
 int smh_version(void);
@@ -213,6 +229,16 @@ int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, floa
  * this rank's tasks for all M rows, rows in rank-major order).  Needs ws.neg complete. */
 int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, float temperature,
                  int engine, const smh_exchange_t *exch, void *stream);
+
+/* Fused exchange, first launch of a step (replaces smh_push_inputs + smh_prep_zero + smh_barrier + smh_prep): every rank
+ * converts its OWN 2 * n_local rows (local_in: this rank's z1/z2/joints, rank strides ignored) into the operand images of
+ * the selected engine and the packed joints and stores them into every rank's workspace over NVLink; the positive-pair
+ * distance and <z1_k, z2_k> of its samples go to every rank's posinfo; the max / min / domain flags / distance bound are
+ * combined with remote atomicMax; the local accumulators are zeroed; stage 1 is signalled.  The distance bound is taken
+ * against global sample 0 (rank 0 publishes its joints first), so the 16-bit image has the scale of the single-GPU
+ * step. */
+int smh_shard_prep(const smh_dims_t *dims, const smh_inputs_t *local_in, void *ws_dev, const smh_exchange_t *exch,
+                   int engine, void *stream);
 
 /* peer exchange: pack this rank's local inputs (n_local samples per view, described like smh_inputs_t with
  * rank strides ignored) as [z1|z2|joints1|joints2] into slot `rank` of every peer's gathered-input buffer

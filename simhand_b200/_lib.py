@@ -46,7 +46,7 @@ class Layout(ctypes.Structure):
                 ("off_jp", ctypes.c_int64), ("off_posd", ctypes.c_int64),
                 ("off_neg", ctypes.c_int64), ("off_rn", ctypes.c_int64), ("off_rowloss", ctypes.c_int64),
                 ("off_dzacc", ctypes.c_int64), ("off_negparts", ctypes.c_int64), ("off_dzparts", ctypes.c_int64),
-                ("off_dist", ctypes.c_int64),
+                ("off_dist", ctypes.c_int64), ("off_posinfo", ctypes.c_int64),
                 ("m", ctypes.c_int32), ("tiles_per_side", ctypes.c_int32), ("n_stored_tiles", ctypes.c_int32),
                 ("n_tasks", ctypes.c_int32), ("n_strips", ctypes.c_int32), ("strip_len", ctypes.c_int32)]
 
@@ -65,7 +65,13 @@ MAX_PEERS = 8
 class Exchange(ctypes.Structure):
     _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32),
                 ("ws_peer", ctypes.c_void_p * MAX_PEERS), ("xin_peer", ctypes.c_void_p * MAX_PEERS),
-                ("signal_peer", ctypes.c_void_p * MAX_PEERS)]
+                ("signal_peer", ctypes.c_void_p * MAX_PEERS), ("fused", ctypes.c_int32),
+                ("timeout_ms", ctypes.c_uint32)]
+
+
+SIGNAL_WORDS = 256
+SIG_EPOCH = 16
+SIG_POISON = 17
 
 
 class Stats(ctypes.Structure):
@@ -80,7 +86,7 @@ EXPORTS = ("smh_version", "smh_last_error", "smh_layout", "smh_plan_build", "smh
            "smh_forward", "smh_backward", "smh_finalize", "smh_weights_dense", "smh_l2norm_fwd",
            "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params", "smh_push_inputs",
            "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz", "smh_import_weights", "smh_transform_fwd", "smh_transform_bwd",
-           "smh_scale_grads")
+           "smh_scale_grads", "smh_shard_prep")
 
 _lib = None
 
@@ -107,6 +113,7 @@ def load() -> ctypes.CDLL:
     lib.smh_backward.argtypes = [pd, vp, vp, f32, ctypes.c_int, px, vp]
     lib.smh_push_inputs.argtypes = [px, pi, i32, i32, vp]
     lib.smh_barrier.argtypes = [px, vp]
+    lib.smh_shard_prep.argtypes = [pd, pi, vp, px, ctypes.c_int, vp]
     lib.smh_exchange_neg.argtypes = [pd, vp, px, vp]
     lib.smh_exchange_dz.argtypes = [pd, vp, px, vp]
     lib.smh_prep_zero.argtypes = [pd, vp, vp]

@@ -57,8 +57,6 @@ static int validate_dims(const smh_dims_t *dims)
         return set_error(SMH_E_MODE, "unknown diff_type %d", dims->diff_type);
     if (dims->weight_type != SMH_WEIGHT_LINEAR && dims->weight_type != SMH_WEIGHT_NONLINEAR)
         return set_error(SMH_E_MODE, "unknown weight_type %d", dims->weight_type);
-    if (dims->weight_type == SMH_WEIGHT_NONLINEAR && dims->world != 1)
-        return set_error(SMH_E_DIM, "non_linear weights need the global mean distance: single rank only (world == 1)");
     if (dims->weight_type == SMH_WEIGHT_NONLINEAR && !(dims->lambda_pos == dims->lambda_pos && dims->lambda_neg == dims->lambda_neg))
         return set_error(SMH_E_ARG, "non_linear weights: lambda is NaN");
     return 0;
@@ -213,8 +211,10 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     lay->off_jp = take(mp * kJP * 4);
     // partial buffers of the peer exchange (unused, and not allocated, on a single rank)
     // + 64 B tail: one partial loss per rank (sharded finalize)
-    lay->off_negparts = take(dims.world > 1 ? (int64_t)dims.world * mp * 4 + 64 : 0);
+    // + 128 B tail: one partial loss per rank (sharded finalize) | one partial distance sum per rank (non_linear)
+    lay->off_negparts = take(dims.world > 1 ? (int64_t)dims.world * mp * 4 + 128 : 0);
     lay->off_dzparts = take(dims.world > 1 ? (int64_t)m * kD * 4 : 0);
+    lay->off_posinfo = take(dims.world > 1 ? (int64_t)4 * dims.n * 4 : 0);
     lay->off_dist = take((int64_t)lay->n_stored_tiles * kTileFloats * ((dims.flags & SMH_DIMS_Q16_TILES) ? 2 : 4));
     lay->ws_bytes = off;
     lay->plan_bytes = align_up((int64_t)sizeof(PlanHeader), 16) + align_up((int64_t)lay->n_stored_tiles * 8, 16) +
@@ -271,6 +271,8 @@ static int make_peers(const smh_dims_t &dims, const smh_layout_t &lay, void *ws_
     out->off_negparts = lay.off_negparts;
     out->off_dzparts = lay.off_dzparts;
     out->off_lossparts = lay.off_negparts + (int64_t)dims.world * lay.tiles_per_side * kTile * 4;
+    out->off_posinfo = lay.off_posinfo;
+    out->n = dims.n;
     if (!exch) {
         out->world = 1;
         out->rank = 0;
@@ -287,7 +289,11 @@ static int make_peers(const smh_dims_t &dims, const smh_layout_t &lay, void *ws_
     for (int p = 0; p < exch->world; ++p) {
         if (!exch->ws_peer[p]) return set_error(SMH_E_ARG, "exchange ws_peer[%d] is null", p);
         out->ws[p] = (unsigned char *)exch->ws_peer[p];
+        if (exch->fused && !exch->signal_peer[p]) return set_error(SMH_E_ARG, "exchange signal_peer[%d] is null", p);
+        out->sig[p] = (uint32_t *)exch->signal_peer[p];
     }
+    out->fused = exch->fused ? 1 : 0;
+    out->timeout_ms = exch->timeout_ms;
     return 0;
 }
 
@@ -462,15 +468,18 @@ int smh_forward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, floa
     SMH_COMMON_PROLOGUE(true)
     if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
     PlanView pv = carve_plan(plan_dev, lay);
-    (void)exch;                       // the sweep accumulates locally; smh_exchange_neg ships the partial sums
-    Peers peers;
+    // the sweep accumulates locally (`peers` = local view); the partial sums travel with smh_exchange_neg, or, with the
+    // fused exchange (`xp` = the real ranks), in the tail of the sweep itself
+    Peers peers, xp;
     if ((rc = make_peers(*dims, lay, ws_dev, nullptr, &peers))) return rc;
+    if ((rc = make_peers(*dims, lay, ws_dev, (exch && exch->fused) ? exch : nullptr, &xp))) return rc;
     int wmode;
     if ((rc = weight_mode(*dims, engine, false, &wmode))) return rc;
     engine &= 0xff;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16 || engine == SMH_ENGINE_TC_FP16)
         return launch_sweep_tc(false, engine == SMH_ENGINE_TC_TF32 ? 0 : (engine == SMH_ENGINE_TC_BF16 ? 1 : 2), wmode,
-                               *dims, lay, pv, ws, peers, temperature, st);
+                               *dims, lay, pv, ws, peers, xp, temperature, st);
+    if (xp.fused) return set_error(SMH_E_MODE, "the fused exchange runs the tensor-core engines only");
     if (engine == SMH_ENGINE_FP32 && (dims->flags & SMH_DIMS_Q16_TILES))
         return set_error(SMH_E_MODE, "the fp32 engine reads fp32 distance tiles (clear SMH_DIMS_Q16_TILES)");
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(false, wmode, *dims, lay, pv, ws, peers, temperature, st);
@@ -483,16 +492,22 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
     SMH_COMMON_PROLOGUE(true)
     if (!(temperature > 0.f)) return set_error(SMH_E_ARG, "temperature must be positive");
     PlanView pv = carve_plan(plan_dev, lay);
-    Peers peers;
+    Peers peers, xp;
     if ((rc = make_peers(*dims, lay, ws_dev, nullptr, &peers))) return rc;
+    if ((rc = make_peers(*dims, lay, ws_dev, (exch && exch->fused) ? exch : nullptr, &xp))) return rc;
     // peer exchange: the row sums are the rank-ordered sum of the partials every rank delivered
-    if ((rc = launch_rn(lay, ws, exch ? dims->world : 1, st))) return rc;
+    if (xp.fused) {
+        if ((rc = launch_rn_fused(lay, ws, xp, (engine & SMH_BACKWARD_RN_ONLY) != 0, st))) return rc;
+    } else if ((rc = launch_rn(lay, ws, exch ? dims->world : 1, st))) {
+        return rc;
+    }
     if (engine & SMH_BACKWARD_RN_ONLY) return 0;
     int wmode;
     if ((rc = weight_mode(*dims, engine, true, &wmode))) return rc;
     engine &= 0xff;
     if (engine == SMH_ENGINE_TC_TF32 || engine == SMH_ENGINE_TC_BF16 || engine == SMH_ENGINE_TC_FP16)
-        return launch_sweep_tc(true, 1, wmode, *dims, lay, pv, ws, peers, temperature, st);
+        return launch_sweep_tc(true, 1, wmode, *dims, lay, pv, ws, peers, xp, temperature, st);
+    if (xp.fused) return set_error(SMH_E_MODE, "the fused exchange runs the tensor-core engines only");
     if (engine == SMH_ENGINE_FP32 && (dims->flags & SMH_DIMS_Q16_TILES))
         return set_error(SMH_E_MODE, "the fp32 engine reads fp32 distance tiles (clear SMH_DIMS_Q16_TILES)");
     if (engine == SMH_ENGINE_FP32) return launch_sweep_fp32(true, wmode, *dims, lay, pv, ws, peers, temperature, st);
@@ -516,6 +531,12 @@ int smh_finalize(const smh_dims_t *dims, const smh_inputs_t *in, void *ws_dev, c
     if (!dzacc_src_dev) dzacc_src_dev = ws.dzacc;
     Peers peers;
     if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
+    if (exch && exch->fused) {
+        if (in->n_local * dims->world != dims->n) return set_error(SMH_E_DIM, "fused finalize takes the rank's local inputs");
+        const int pm = (flags & SMH_UNIT_POS_WEIGHTS) ? 1 : (dims->weight_type == SMH_WEIGHT_NONLINEAR ? 3 : 0);
+        return launch_finalize_fused(*dims, lay, *in, ws, pm, temperature, grad_scale, loss_dev, dz1_dev, dz2_dev,
+                                     dz_row_stride, peers, st);
+    }
     int phase = 0;
     if (flags & (SMH_FINALIZE_LOSS_PART | SMH_FINALIZE_GRAD)) {
         if (!exch) return set_error(SMH_E_ARG, "sharded finalize phases need the peer exchange");
@@ -543,6 +564,25 @@ int smh_weights_dense(const smh_dims_t *dims, const void *plan_dev, void *ws_dev
     if (dims->flags & SMH_DIMS_Q16_TILES) return set_error(SMH_E_MODE, "smh_weights_dense needs the fp32 tiles");
     if (!pos_w_dev && !neg_w_dev) return set_error(SMH_E_ARG, "no output requested");
     return launch_weights_dense(*dims, lay, carve_plan(plan_dev, lay), ws, pos_w_dev, neg_w_dev, st);
+}
+
+int smh_shard_prep(const smh_dims_t *dims, const smh_inputs_t *local_in, void *ws_dev, const smh_exchange_t *exch,
+                   int engine, void *stream)
+{
+    const void *plan_dev = nullptr;
+    SMH_COMMON_PROLOGUE(false)
+    (void)plan_dev;
+    (void)ws;
+    if (!exch || !exch->fused) return set_error(SMH_E_ARG, "shard_prep needs an exchange with fused = 1");
+    if (!local_in || !local_in->z1_dev || !local_in->z2_dev || !local_in->j1_dev || !local_in->j2_dev)
+        return set_error(SMH_E_ARG, "shard_prep: null input pointer");
+    if (local_in->z_row_stride < dims->d) return set_error(SMH_E_ARG, "z_row_stride < d");
+    if (dims->world < 2) return set_error(SMH_E_DIM, "shard_prep: world must be >= 2");
+    if (engine != SMH_ENGINE_TC_TF32 && engine != SMH_ENGINE_TC_BF16 && engine != SMH_ENGINE_TC_FP16)
+        return set_error(SMH_E_MODE, "the fused exchange runs the tensor-core engines only (got %d)", engine);
+    Peers peers;
+    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
+    return launch_shard_prep(*dims, lay, *local_in, engine, peers, st);
 }
 
 int smh_push_inputs(const smh_exchange_t *exch, const smh_inputs_t *local_in, int32_t n_local, int32_t d, void *stream)

@@ -43,7 +43,14 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
 int launch_sweep_fp32(bool backward, int wmode /* 0 fused, 1 unit, 2 materialised */, const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan,
                       const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
 int launch_sweep_tc(bool backward, int logit_format /* 0 tf32, 1 bf16, 2 fp16 */, int wmode, const smh_dims_t &dims, const smh_layout_t &lay,
-                    const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream);
+                    const PlanView &plan, const WsView &ws, const Peers &peers, const Peers &xp /* fused exchange, or world 1 */,
+                    float temperature, cudaStream_t stream);
+int launch_shard_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, int engine,
+                      const Peers &peers, cudaStream_t stream);
+int launch_rn_fused(const smh_layout_t &lay, const WsView &ws, const Peers &peers, bool signal4, cudaStream_t stream);
+int launch_finalize_fused(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
+                          int pos_mode, float temperature, float grad_scale, float *loss, float *dz1, float *dz2,
+                          int64_t dz_row_stride, const Peers &peers, cudaStream_t stream);
 int launch_push_inputs(const smh_exchange_t &exch, const smh_inputs_t &in, int n_local, int d, cudaStream_t stream);
 int launch_barrier(const smh_exchange_t &exch, cudaStream_t stream);
 int launch_rn(const smh_layout_t &lay, const WsView &ws, int n_parts, cudaStream_t stream);

@@ -15,6 +15,50 @@
 
 namespace smh {
 
+// Fused exchange (smh_shard.cu): head = wait until every rank has delivered its rows (stage 1) and take the step's
+// combined scalars; tail = the rank's last CTA pushes Dmax (and the non-finite flag) to every rank and, unless a
+// distance-sum pass follows (non_linear weights), signals stage 2.
+struct DistCtx {
+    uint32_t epoch;
+    const Stats *gs;          // scalars the kernel reads (distance bound, domain flags)
+};
+__device__ __forceinline__ DistCtx dist_head(Stats *stats, const Peers &peers)
+{
+    DistCtx c;
+    c.epoch = 0u;
+    c.gs = stats;
+    if (peers.fused) {
+        c.epoch = peers.my_sig()[kSigEpoch];
+        stage_wait(peers, 1, c.epoch);
+        c.gs = peers.gstats(peers.rank, c.epoch);
+    }
+    return c;
+}
+// thread 0 of every CTA, after the CTA's maximum went into stats->dmax_bits / stats->flags (rank-local)
+__device__ __forceinline__ void dist_tail(Stats *stats, const Peers &peers, const DistCtx &c, bool signal2)
+{
+    if (peers.world <= 1) return;
+    __threadfence();
+    const unsigned ticket = atomicAdd(&stats->ticket2, 1u);
+    if (ticket != gridDim.x - 1) return;
+    const uint32_t mine = atomicMax(&stats->dmax_bits, 0u);
+    if (peers.fused) {
+        const uint32_t fl = atomicOr(&stats->flags, 0u);
+        for (int p = 0; p < peers.world; ++p) {
+            Stats *o = peers.gstats(p, c.epoch);
+            atomicMax_system(&o->dmax_bits, mine);
+            if (fl) atomicOr_system(&o->flags, fl);
+        }
+        stats->ticket2 = 0u;
+        if (signal2) stage_signal(peers, 2, c.epoch);
+        return;
+    }
+    for (int p = 0; p < peers.world; ++p)
+        if (p != peers.rank) atomicMax(&peers.stats(p)->dmax_bits, mine);
+    stats->ticket2 = 0u;
+    __threadfence_system();
+}
+
 // MODE 0: IEEE intrinsics (any input).  MODE 1: branch-free exact forms with the zero guard.  MODE 2: without the
 // guard (a coincident joint gives NaN; the caller repairs that pair with MODE 1).
 // distances of joints (2p, 2p+1) of one pair of samples
@@ -141,7 +185,7 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
 template <bool HALF, bool Q16>
 __global__ void __launch_bounds__(256, Q16 ? 3 : 2)
 mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m,
-             Stats *__restrict__ stats, Peers peers)
+             Stats *__restrict__ stats, Peers peers, int signal2)
 {
     constexpr int kCols = HALF ? 64 : 128;            // columns staged per CTA
     constexpr int kPerThread = kCols / 2;
@@ -152,14 +196,15 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
     const int col0 = cs0 + (threadIdx.x >> 7) * kPerThread;
     const int2 ij = tiles[tile_id];
     void *tile_out = reinterpret_cast<unsigned char *>(dist) + (int64_t)tile_id * kTileFloats * (Q16 ? 2 : 4);
-    const float qscale = Q16 ? q16_scale(__uint_as_float(stats->dbound_bits)) * (1.0f / 21.0f) : 0.f;    // applied to the sum
+    const DistCtx dc = dist_head(stats, peers);
+    const float qscale = Q16 ? q16_scale(__uint_as_float(dc.gs->dbound_bits)) * (1.0f / 21.0f) : 0.f;    // applied to the sum
     {
         const float4 *src = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.y * kTile + cs0) * kJP);
         float4 *dst = reinterpret_cast<float4 *>(cs);
         for (int i = threadIdx.x; i < kCols * kJP / 4; i += 256) dst[i] = src[i];
     }
     __syncthreads();
-    const uint32_t flags = stats->flags;
+    const uint32_t flags = dc.gs->flags;
     const bool slow = flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE);
     uint32_t vmax_bits = 0u;
     if (slow)
@@ -191,18 +236,8 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
             atomicOr(&stats->flags, SMH_FLAG_NONFINITE);      // non-finite inputs (IEEE path): the loss is NaN
         else
             atomicMax(&stats->dmax_bits, Q16 ? __float_as_uint(__fdiv_rn(__uint_as_float(bmax), 21.0f)) : bmax);
-        if (peers.world > 1) {
-            // fused all-reduce(MAX): the last CTA of this rank pushes the rank's maximum into every peer's stats
-            __threadfence();
-            const unsigned ticket = atomicAdd(&stats->ticket2, 1u);
-            if (ticket == gridDim.x - 1) {
-                const uint32_t mine = atomicMax(&stats->dmax_bits, 0u);
-                for (int p = 0; p < peers.world; ++p)
-                    if (p != peers.rank) atomicMax(&peers.stats(p)->dmax_bits, mine);
-                stats->ticket2 = 0u;
-                __threadfence_system();
-            }
-        }
+        // fused all-reduce(MAX): the last CTA of this rank pushes the rank's maximum into every peer's stats
+        dist_tail(stats, peers, dc, signal2 != 0);
     }
 }
 
@@ -214,10 +249,11 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
 template <bool ABS>
 __global__ void __launch_bounds__(256, 2)
 altdist_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float *__restrict__ dist, int m,
-               Stats *__restrict__ stats)
+               Stats *__restrict__ stats, Peers peers, int signal2)
 {
     __shared__ __align__(16) float cs[kTile * kJP];
     __shared__ uint32_t wmax[8];
+    const DistCtx dc = dist_head(stats, peers);
     const int2 ij = tiles[blockIdx.x];
     float *tile_out = dist + (int64_t)blockIdx.x * kTileFloats;
     {
@@ -276,13 +312,17 @@ altdist_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, flo
             atomicOr(&stats->flags, SMH_FLAG_NONFINITE);
         else
             atomicMax(&stats->dmax_bits, v);
+        dist_tail(stats, peers, dc, signal2 != 0);
     }
 }
 
 // non_linear weights (utils.py:343-346) need mean_ij D_ij over all M^2 ordered pairs: one pass over the stored tiles
 // (an off-diagonal tile stands for both (I, J) and (J, I)), summed in double.
+// Fused exchange: the rank's last CTA stores the rank's partial sum into slot `rank` of every rank's part array (the
+// consumers add the parts in rank order) and signals stage 2.
 __global__ void __launch_bounds__(256)
-tile_sum_kernel(const int2 *__restrict__ tiles, const float *__restrict__ dist, int m, Stats *__restrict__ stats)
+tile_sum_kernel(const int2 *__restrict__ tiles, const float *__restrict__ dist, int m, Stats *__restrict__ stats,
+                Peers peers)
 {
     __shared__ double part[8];
     const int2 ij = tiles[blockIdx.x];
@@ -309,35 +349,64 @@ tile_sum_kernel(const int2 *__restrict__ tiles, const float *__restrict__ dist, 
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += part[w];
         atomicAdd(&stats->dsum, ij.x == ij.y ? t : 2.0 * t);
+        if (peers.fused) {
+            __threadfence();
+            const unsigned ticket = atomicAdd(&stats->ticket2, 1u);
+            if (ticket == gridDim.x - 1) {
+                const double mine = atomicAdd(&stats->dsum, 0.0);
+                for (int p = 0; p < peers.world; ++p)
+                    reinterpret_cast<double *>(peers.lossparts(p) + 16)[peers.rank] = mine;
+                stats->ticket2 = 0u;
+                stage_signal(peers, 2, peers.my_sig()[kSigEpoch]);
+            }
+        }
     }
+}
+
+// a rank with nothing to do in a stage: wait for the previous stage, signal this one
+__global__ void stage_relay_kernel(Peers pe, int wait_stage, int stage)
+{
+    const uint32_t epoch = pe.my_sig()[kSigEpoch];
+    if (wait_stage > 0) stage_wait(pe, wait_stage, epoch);
+    if (threadIdx.x == 0) stage_signal(pe, stage, epoch);
 }
 
 int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView &plan, const WsView &ws,
                  const Peers &peers, cudaStream_t stream)
 {
-    if (lay.n_stored_tiles == 0) return 0;
     Stats *st = (Stats *)ws.stats;
+    if (lay.n_stored_tiles == 0) {
+        // a rank without tiles (fewer row-block pairs than ranks) still takes part in the exchange protocol
+        if (peers.fused) {
+            stage_relay_kernel<<<1, 32, 0, stream>>>(peers, 1, 2);
+            return check_launch("stage_relay_kernel");
+        }
+        return 0;
+    }
+    const bool nonlinear = dims.weight_type == SMH_WEIGHT_NONLINEAR;
+    const int signal2 = nonlinear ? 0 : 1;           // non_linear: the distance-sum pass closes stage 2
+    if (peers.world > 1 && !peers.fused && (dims.diff_type != SMH_DIFF_MPJPE || nonlinear))
+        return set_error(SMH_E_DIM, "w_abs / w_o_abs / non_linear on several ranks need the fused exchange");
     if (dims.diff_type != SMH_DIFF_MPJPE) {
-        if (peers.world > 1) return set_error(SMH_E_DIM, "diff_type w_abs / w_o_abs: single rank only");
         if (dims.diff_type == SMH_DIFF_W_ABS)
-            altdist_kernel<true><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st);
+            altdist_kernel<true><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
         else
-            altdist_kernel<false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st);
+            altdist_kernel<false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
     } else if (lay.n_stored_tiles < 8 * 2 * kNumCtas) {
         // fewer than ~8 waves of whole tiles (2 CTAs x 148 SMs per wave): cut the tiles in halves
         if (dims.flags & SMH_DIMS_Q16_TILES)
-            mpjpe_kernel<true, true><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
+            mpjpe_kernel<true, true><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
         else
-            mpjpe_kernel<true, false><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
+            mpjpe_kernel<true, false><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
     } else {
         if (dims.flags & SMH_DIMS_Q16_TILES)
-            mpjpe_kernel<false, true><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
+            mpjpe_kernel<false, true><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
         else
-            mpjpe_kernel<false, false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers);
+            mpjpe_kernel<false, false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
     }
     int rc = check_launch(dims.diff_type != SMH_DIFF_MPJPE ? "altdist_kernel" : "mpjpe_kernel");
-    if (rc || dims.weight_type != SMH_WEIGHT_NONLINEAR) return rc;
-    tile_sum_kernel<<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.dist, lay.m, st);
+    if (rc || !nonlinear) return rc;
+    tile_sum_kernel<<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.dist, lay.m, st, peers);
     return check_launch("tile_sum_kernel");
 }
 

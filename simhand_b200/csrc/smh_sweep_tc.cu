@@ -242,7 +242,7 @@ template <bool BWD, bool SBF16, bool Q16>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const void *__restrict__ dist,
-                const float *__restrict__ rn, Peers peers, Stats *__restrict__ stats, int m, int n, int n_local,
+                const float *__restrict__ rn, Peers peers, Peers xp, Stats *__restrict__ stats, int m, int n, int n_local,
                 float k2, float inv_k2, int wmode, float lambda_neg, uint32_t idesc1, long long *trace)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
@@ -295,6 +295,16 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Fused exchange (xp: the real ranks; `peers` stays the local view the accumulators are addressed through): the forward
+    // sweep starts once every rank has delivered Dmax (stage 2); the backward sweep follows rn_fused_kernel, which has
+    // already waited for the row sums.  gs: the step's combined scalars.
+    uint32_t epoch = 0u;
+    const Stats *gs = stats;
+    if (xp.fused) {
+        epoch = xp.my_sig()[kSigEpoch];
+        if (!BWD) stage_wait(xp, 2, epoch);
+        gs = xp.gstats(xp.rank, epoch);
+    }
 
     if (warp == 0) {
         // ------------------------------------------------------------------ tile producer (MPJPE pieces, HBM)
@@ -490,20 +500,26 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         const int w4 = warp & 3;                       // TMEM lane quadrant this warp may touch
         const int r = w4 * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16);
-        const float dmax = __uint_as_float(stats->dmax_bits);
+        const float dmax = __uint_as_float(gs->dmax_bits);
         // wk = W * k2 = k2 - D * (k2 / Dmax)  (Dmin = +0, the diagonal); unit weights: wk = k2
         const bool no_tile = wmode == 1, dense = wmode == 2, sigmoid = wmode == 3;
         float negc = no_tile ? 0.f : (dense ? k2 : -__fdiv_rn(k2, dmax));
         float addc = dense ? 0.f : k2;
         if (sigmoid) {
             // exponent of the sigmoid in base 2: lambda log2(e) (D - mean D), mean over all M^2 ordered pairs
-            const float mu = (float)(stats->dsum / ((double)m * (double)m));
+            double dsum = stats->dsum;
+            if (xp.fused) {                  // rank-ordered sum of the parts every rank delivered with stage 2
+                const double *parts = reinterpret_cast<const double *>(xp.lossparts(xp.rank) + 16);
+                dsum = 0.0;
+                for (int p = 0; p < xp.world; ++p) dsum += __ldcg(parts + p);
+            }
+            const float mu = (float)(dsum / ((double)m * (double)m));
             negc = lambda_neg * 1.4426950408889634f;
             addc = -mu * negc;
         }
         if (Q16 && !no_tile) {
             // the staged value is q = D * qscale: fold 1 / qscale into the slope (wk = k2 - q k2 / (Dmax qscale))
-            const float qs = q16_scale(__uint_as_float(stats->dbound_bits));
+            const float qs = q16_scale(__uint_as_float(gs->dbound_bits));
             negc = qs > 0.f ? __fdiv_rn(negc, qs) : negc;
         }
         const f2 negc2 = pack2(negc, negc), k2c2 = pack2(addc, addc);
@@ -618,14 +634,49 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     }
 
     tc_fence_before();
+    if (xp.fused) __threadfence();               // this thread's row-sum / gradient reductions precede the grid barrier
     __syncthreads();
     if (warp == 2) tc_dealloc(tmem_base, kTmemCols);
+    if (xp.fused) {
+        // Tail of the fused exchange: once every CTA of the rank has flushed, the CTAs ship the rank's partial results --
+        // forward: all-gather of the partial row sums into slot `rank` of every rank's negparts; backward: reduce-scatter
+        // payload, rows [p * 2 n_local, (p + 1) * 2 n_local) of the gradient accumulator into slot `rank` of rank p's
+        // dzparts -- with plain 16-byte stores over NVLink; the rank's last CTA signals the stage.
+        uint32_t *sig = xp.my_sig();
+        if (threadIdx.x == 0) grid_barrier(xp, epoch * 8u + (BWD ? 2u : 1u));
+        __syncthreads();
+        if (!BWD) {
+            const int mp4 = ((m + kTile - 1) / kTile) * kTile / 4;
+            const float4 *src = reinterpret_cast<const float4 *>(xp.neg(xp.rank));
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mp4; i += gridDim.x * blockDim.x) {
+                const float4 v = __ldcg(src + i);
+                for (int p = 0; p < xp.world; ++p) reinterpret_cast<float4 *>(xp.negparts(p))[(int64_t)xp.rank * mp4 + i] = v;
+            }
+        } else {
+            const int64_t block4 = (int64_t)2 * n_local * kD / 4;
+            const int64_t total = block4 * xp.world;
+            const float4 *src = reinterpret_cast<const float4 *>(xp.dzacc(xp.rank));
+            for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+                const int p = (int)(i / block4);
+                reinterpret_cast<float4 *>(xp.dzparts(p))[(int64_t)xp.rank * block4 + (i - (int64_t)p * block4)] = __ldcg(src + i);
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t ticket = atomicAdd(sig + kSigTicket, 1u);
+            if (ticket == gridDim.x - 1) {
+                sig[kSigTicket] = 0u;
+                stage_signal(xp, BWD ? 4 : 3, epoch);
+            }
+        }
+    }
 }
 
 template <bool BWD, bool SBF16, bool Q16>
 static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, const smh_dims_t &dims,
                       const smh_layout_t &lay, const PlanView &plan, const WsView &ws, const Peers &peers,
-                      float temperature, cudaStream_t stream)
+                      const Peers &xp, float temperature, cudaStream_t stream)
 {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -639,23 +690,24 @@ static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, co
     cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16, Q16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
     sweep_tc_kernel<BWD, SBF16, Q16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
-                                                                   ws.dist, ws.rn, peers, (Stats *)ws.stats, lay.m,
+                                                                   ws.dist, ws.rn, peers, xp, (Stats *)ws.stats, lay.m,
                                                                    dims.n, n_local, k2, inv_k2, wmode, dims.lambda_neg, idesc1,
                                                                         reinterpret_cast<long long *>(ws.rowloss));
     return check_launch("sweep_tc_kernel");
 }
 
 int launch_sweep_tc(bool backward, int logit_format, int wmode, const smh_dims_t &dims, const smh_layout_t &lay,
-                    const PlanView &plan, const WsView &ws, const Peers &peers, float temperature, cudaStream_t stream)
+                    const PlanView &plan, const WsView &ws, const Peers &peers, const Peers &xp, float temperature,
+                    cudaStream_t stream)
 {
-    if (lay.n_strips == 0) return 0;
+    if (lay.n_strips == 0 && !xp.fused) return 0;          // fused exchange: a rank without tasks still signals its stage
     const uint32_t id_bf16 = umma_idesc_bf16(kTile, kTaskN, 0, 0), id_f16 = umma_idesc_f16(kTile, kTaskN, 0, 0),
                    id_tf32 = umma_idesc_tf32(kTile, kTaskN, 0, 0);
     const bool q16 = dims.flags & SMH_DIMS_Q16_TILES;
     if (q16 && wmode != 0) return set_error(SMH_E_MODE, "SMH_DIMS_Q16_TILES: linear weights from the joints only");
 #define SMH_SWEEP(B, S, IMG, ID)                                                                                      \
-    (q16 ? launch_one<B, S, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, temperature, stream)                    \
-         : launch_one<B, S, false>(wmode, IMG, ID, dims, lay, plan, ws, peers, temperature, stream))
+    (q16 ? launch_one<B, S, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)                \
+         : launch_one<B, S, false>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream))
     if (backward) return SMH_SWEEP(true, true, ws.zb, id_bf16);
     if (logit_format == 1) return SMH_SWEEP(false, true, ws.zb, id_bf16);
     if (logit_format == 2) return SMH_SWEEP(false, true, ws.zh, id_f16);

@@ -17,6 +17,7 @@ real collectives rather than bookkeeping.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -24,7 +25,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import check
-from .ops import _as_f32, _stream_ptr, get_context, make_inputs, resolve_engine, step_flags
+from .ops import DEFAULT_WEIGHTING, _as_f32, _stream_ptr, get_context, make_inputs, resolve_engine, step_flags
 
 
 def pack_local(z1, z2, joints1, joints2) -> torch.Tensor:
@@ -56,12 +57,22 @@ def dz_out_row(i: int, n: int, n_local: int) -> int:
     return (k // n_local) * 2 * n_local + v * n_local + k % n_local
 
 
+DEFAULT_TIMEOUT_MS = 30000
+
+
+def exchange_timeout_ms() -> int:
+    """Bound of every cross-rank wait on the device (SMH_EXCHANGE_TIMEOUT_MS; a rank that stays away longer -- a
+    checkpoint, a stalled dataloader -- poisons the group: the loss becomes NaN instead of a silently wrong value)."""
+    return int(os.environ.get("SMH_EXCHANGE_TIMEOUT_MS", DEFAULT_TIMEOUT_MS))
+
+
 class PeerExchange:
     """Symmetric buffers of one sharded problem shape, mapped into every rank (torch.distributed._symmetric_memory):
-    the workspace blob (peers add row sums / gradient rows / Dmax into it over NVLink), the gathered-input buffer
-    (peers push their packed inputs into it) and the barrier words.  Built once per (shape, group) and reused."""
+    the workspace blob (peers store operand images / row sums / gradient rows / Dmax into it over NVLink), for the
+    unfused transport the gathered-input buffer (peers push their packed inputs into it), and the signal words.
+    Built once per (shape, group) and reused."""
 
-    def __init__(self, ctx, group, chunk_floats: int):
+    def __init__(self, ctx, group, chunk_floats: int, fused: bool):
         import torch.distributed._symmetric_memory as symm
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         dev = ctx.device
@@ -70,32 +81,40 @@ class PeerExchange:
         ws_bytes = torch.tensor([int(lay.ws_bytes)], dtype=torch.int64, device=dev)
         dist.all_reduce(ws_bytes, op=dist.ReduceOp.MAX, group=group)
         self.ws = symm.empty(int(ws_bytes.item()), dtype=torch.uint8, device=dev)
-        self.xin = symm.empty(self.world * chunk_floats, dtype=torch.float32, device=dev)
-        self.signal = symm.empty(64, dtype=torch.int32, device=dev)
+        self.ws.zero_()                    # fused: padding rows of the images and both slots of the per-step scalars
+        self.xin = None if fused else symm.empty(self.world * chunk_floats, dtype=torch.float32, device=dev)
+        self.signal = symm.empty(_lib.SIGNAL_WORDS, dtype=torch.int32, device=dev)
         self.signal.zero_()
         self.h_ws = symm.rendezvous(self.ws, group)
-        self.h_xin = symm.rendezvous(self.xin, group)
+        self.h_xin = None if fused else symm.rendezvous(self.xin, group)
         self.h_sig = symm.rendezvous(self.signal, group)
         ex = _lib.Exchange()
         ex.world, ex.rank = self.world, self.rank
         for p in range(self.world):
             ex.ws_peer[p] = self.h_ws.buffer_ptrs[p]
-            ex.xin_peer[p] = self.h_xin.buffer_ptrs[p]
+            ex.xin_peer[p] = None if fused else self.h_xin.buffer_ptrs[p]
             ex.signal_peer[p] = self.h_sig.buffer_ptrs[p]
+        ex.fused = 1 if fused else 0
+        ex.timeout_ms = exchange_timeout_ms()
         assert ex.ws_peer[self.rank] == self.ws.data_ptr()
         self.struct = ex
+        self.fused = fused
         torch.cuda.synchronize(dev)
-        dist.barrier(group)                # every rank's barrier words are zero before anyone signals
+        dist.barrier(group)                # every rank's signal words are zero before anyone signals
+
+    def poisoned(self) -> int:
+        """Site of the first cross-rank wait that timed out anywhere in the group (0 = healthy).  Synchronises."""
+        return int(self.signal[_lib.SIG_POISON].item())
 
 
 _exchanges = {}
 
 
-def get_exchange(ctx, group, chunk_floats: int) -> PeerExchange:
-    key = (id(ctx), id(group), chunk_floats)
+def get_exchange(ctx, group, chunk_floats: int, fused: bool = False) -> PeerExchange:
+    key = (id(ctx), id(group), chunk_floats, fused)
     ex = _exchanges.get(key)
     if ex is None:
-        ex = PeerExchange(ctx, group, chunk_floats)
+        ex = PeerExchange(ctx, group, chunk_floats, fused)
         _exchanges[key] = ex
     return ex
 
@@ -109,7 +128,7 @@ def peer_exchange_available() -> bool:
 
 
 def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, want_grad: bool, group,
-                  grad_scale: float = 1.0, strip_len: int = 0):
+                  grad_scale: float = 1.0, strip_len: int = 0, exact_weights: Optional[bool] = None):
     """Sharded step with the collectives done by the library over peer memory (NVLink): push-gather of the inputs,
     Dmax pushed by the MPJPE kernel's last CTA, partial row sums / gradient rows stored into the peers' partial
     buffers and reduced in rank order by their consumers; device-side barriers separate the phases.  No NCCL call
@@ -122,7 +141,7 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
     engine_name = resolve_engine(engine, n)
     eng = _lib.ENGINES[engine_name]
     with torch.cuda.device(dev):
-        ctx = get_context(n, d, world, rank, dev, strip_len, step_flags(engine_name))
+        ctx = get_context(n, d, world, rank, dev, strip_len, step_flags(engine_name, exact_weights=exact_weights))
         lay, dims = ctx.layout, ctx.dims
         chunk = 2 * n_local * (d + 42)
         ex = get_exchange(ctx, group, chunk)
@@ -172,15 +191,152 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
     return loss, dz1, dz2
 
 
+def _fused_launches(lib, ctx, exch_struct, ws_ptr, local, temperature, eng, want_grad, grad_scale, outs, st,
+                    pos_weighted=True, neg_weighted=True, stages=None):
+    """The six launches of one rank's fused step (smh_shard.cu).  `stages`: subset to issue (the single-GPU emulation
+    runs the ranks stage by stage)."""
+    dims = ctx.dims
+    pd, pl, px = ctypes.byref(dims), ctypes.byref(local), ctypes.byref(exch_struct)
+    plan = ctx.plan_dev.data_ptr()
+    loss, dz1, dz2 = outs
+    d = dims.d
+    sweep_eng = eng | (0 if neg_weighted else _lib.UNIT_NEG_WEIGHTS)
+    fin_flags = 0 if pos_weighted else _lib.UNIT_POS_WEIGHTS
+    table = {
+        "prep": lambda: check(lib.smh_shard_prep(pd, pl, ws_ptr, px, eng, st), "smh_shard_prep"),
+        "mpjpe": lambda: check(lib.smh_mpjpe(pd, plan, ws_ptr, px, st), "smh_mpjpe"),
+        "fwd": lambda: check(lib.smh_forward(pd, plan, ws_ptr, temperature, sweep_eng, px, st), "smh_forward"),
+        "bwd": lambda: check(lib.smh_backward(pd, plan, ws_ptr, temperature,
+                                              sweep_eng | (0 if want_grad else _lib.BACKWARD_RN_ONLY), px, st), "smh_backward"),
+        "fin": lambda: check(lib.smh_finalize(pd, pl, ws_ptr, None, temperature, grad_scale, loss.data_ptr(),
+                                              dz1.data_ptr() if want_grad else None, dz2.data_ptr() if want_grad else None,
+                                              d, fin_flags, px, st), "smh_finalize"),
+    }
+    for name in (stages or FUSED_STAGES):
+        table[name]()
+
+
+FUSED_STAGES = ("prep", "mpjpe", "fwd", "bwd", "fin")
+
+
+def run_step_fused(z1, z2, joints1, joints2, temperature: float, engine: str, want_grad: bool, group,
+                   grad_scale: float = 1.0, strip_len: int = 0, pos_weighted: bool = True, neg_weighted: bool = True,
+                   weighting=None, exact_weights: Optional[bool] = None):
+    """Sharded step with the exchange fused into the kernels (smh_exchange_t.fused; smh_shard.cu): 6 launches per rank
+    and step, no barrier / copy kernels, no NCCL call on the data path; CUDA-graph capturable.  Every weighting of the
+    single-GPU path is available (the non_linear mean distance and the positive terms travel with the stage signals)."""
+    lib = _lib.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = z1.device
+    n_local, d = z1.shape
+    n = n_local * world
+    engine_name = resolve_engine(engine, n)
+    if engine_name == "fp32":
+        raise ValueError("the fused exchange runs the tensor-core engines (fp16 / tf32 / bf16)")
+    eng = _lib.ENGINES[engine_name]
+    with torch.cuda.device(dev):
+        ctx = get_context(n, d, world, rank, dev, strip_len, step_flags(engine_name, weighting, neg_weighted, exact_weights),
+                          weighting)
+        ex = get_exchange(ctx, group, 0, fused=True)
+        local_in, keep = make_inputs(z1, z2, joints1, joints2)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        dz1 = dz2 = None
+        if want_grad:
+            dz1 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
+            dz2 = torch.empty((n_local, d), dtype=torch.float32, device=dev)
+        _fused_launches(lib, ctx, ex.struct, ex.ws.data_ptr(), local_in, temperature, eng, want_grad, grad_scale,
+                        (loss, dz1, dz2), _stream_ptr(dev), pos_weighted, neg_weighted)
+        del keep
+    return loss, dz1, dz2
+
+
+class EmulatedGroup:
+    """All ranks of a fused sharded step on ONE device: `world` workspaces and signal blocks in the same memory, every
+    rank's kernels launched stage by stage on one stream (rank 0 first, so no wait ever blocks).  The kernels, plans,
+    layouts and the exchange protocol are exactly those of the multi-GPU run; only NVLink is missing.  Used by the
+    single-GPU tests (tests/test_gpu_shard_emulation.py) and for timing one rank's kernels without an 8-GPU box."""
+
+    def __init__(self, n: int, d: int, world: int, device, engine: str = "fp16", weighting=None, neg_weighted: bool = True,
+                 exact_weights: Optional[bool] = None, strip_len: int = 0):
+        if n % world:
+            raise ValueError("n must be a multiple of world")
+        self.n, self.d, self.world, self.device = n, d, world, torch.device(device)
+        self.engine_name = resolve_engine(engine, n)
+        flags = step_flags(self.engine_name, weighting, neg_weighted, exact_weights)
+        self.ctxs = [get_context(n, d, world, r, self.device, strip_len, flags, weighting) for r in range(world)]
+        ws_bytes = max(int(c.layout.ws_bytes) for c in self.ctxs)
+        self.ws = [torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device) for _ in range(world)]
+        self.signal = [torch.zeros(_lib.SIGNAL_WORDS, dtype=torch.int32, device=self.device) for _ in range(world)]
+        self.structs = []
+        for r in range(world):
+            ex = _lib.Exchange()
+            ex.world, ex.rank = world, r
+            for p in range(world):
+                ex.ws_peer[p] = self.ws[p].data_ptr()
+                ex.xin_peer[p] = None
+                ex.signal_peer[p] = self.signal[p].data_ptr()
+            ex.fused = 1
+            ex.timeout_ms = 2000               # a protocol bug must not hold the device for long in a test
+            self.structs.append(ex)
+
+    def step(self, z1, z2, joints1, joints2, temperature: float = 0.5, want_grad: bool = True, grad_scale: float = 1.0,
+             pos_weighted: bool = True, neg_weighted: bool = True, timing: Optional[dict] = None):
+        """z1 / z2 / joints: the GLOBAL batch ([n, d], [n, 21, 2] views); rank r takes samples [r n_local, (r+1) n_local).
+        Returns per-rank lists (loss, dz1, dz2).  timing: dict filled with CUDA-event milliseconds per (stage, rank)."""
+        lib = _lib.load()
+        n_local = self.n // self.world
+        eng = _lib.ENGINES[self.engine_name]
+        st = _stream_ptr(self.device)
+        outs, locals_, keeps = [], [], []
+        for r in range(self.world):
+            sl = slice(r * n_local, (r + 1) * n_local)
+            li, keep = make_inputs(z1[sl], z2[sl], joints1[sl], joints2[sl])
+            locals_.append(li)
+            keeps.append(keep)
+            loss = torch.empty((), dtype=torch.float32, device=self.device)
+            g1 = torch.empty((n_local, self.d), dtype=torch.float32, device=self.device) if want_grad else None
+            g2 = torch.empty((n_local, self.d), dtype=torch.float32, device=self.device) if want_grad else None
+            outs.append((loss, g1, g2))
+        with torch.cuda.device(self.device):
+            for stage in FUSED_STAGES:
+                for r in range(self.world):
+                    if timing is not None:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                    _fused_launches(lib, self.ctxs[r], self.structs[r], self.ws[r].data_ptr(), locals_[r], temperature, eng,
+                                    want_grad, grad_scale, outs[r], st, pos_weighted, neg_weighted, stages=(stage,))
+                    if timing is not None:
+                        e1.record()
+                        timing.setdefault((stage, r), []).append((e0, e1))
+        del keeps
+        return [o[0] for o in outs], [o[1] for o in outs], [o[2] for o in outs]
+
+    def poisoned(self):
+        return [int(s[_lib.SIG_POISON].item()) for s in self.signal]
+
+
 def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, want_grad: bool,
                      group: Optional[dist.ProcessGroup], grad_scale: float = 1.0, strip_len: int = 0,
-                     transport: str = "auto"):
-    """transport: "peer" (collectives fused into the kernels over peer memory), "nccl" (NCCL calls between the
-    kernels) or "auto" (peer when symmetric memory is available and the group fits SMH_MAX_PEERS)."""
+                     transport: str = "auto", pos_weighted: bool = True, neg_weighted: bool = True, weighting=None,
+                     exact_weights: Optional[bool] = None):
+    """transport: "fused" (6 launches, the exchange rides in the kernels' heads and tails over peer memory; every
+    weighting), "peer" (the same exchange as separate push / barrier kernels: 14 launches), "nccl" (NCCL calls between
+    the kernels) or "auto" (fused when symmetric memory is available, the group fits SMH_MAX_PEERS and a tensor-core
+    engine is selected)."""
+    n_glob = z1.shape[0] * dist.get_world_size(group)
+    plain = pos_weighted and neg_weighted and tuple(weighting or DEFAULT_WEIGHTING) == DEFAULT_WEIGHTING
     if transport == "auto":
-        transport = "peer" if (peer_exchange_available() and dist.get_world_size(group) <= _lib.MAX_PEERS) else "nccl"
+        can_peer = peer_exchange_available() and dist.get_world_size(group) <= _lib.MAX_PEERS
+        transport = "nccl" if not can_peer else ("fused" if resolve_engine(engine, n_glob) != "fp32" else "peer")
+        transport = os.environ.get("SMH_TRANSPORT", transport)
+    if transport == "fused":
+        return run_step_fused(z1, z2, joints1, joints2, temperature, engine, want_grad, group, grad_scale, strip_len,
+                              pos_weighted, neg_weighted, weighting, exact_weights)
+    if not plain:
+        raise NotImplementedError("only the fused transport implements the other weightings on several ranks")
     if transport == "peer":
-        return run_step_peer(z1, z2, joints1, joints2, temperature, engine, want_grad, group, grad_scale, strip_len)
+        return run_step_peer(z1, z2, joints1, joints2, temperature, engine, want_grad, group, grad_scale, strip_len,
+                             exact_weights)
     lib = _lib.load()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = z1.device
@@ -189,7 +345,7 @@ def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, 
     engine_name = resolve_engine(engine, n)
     eng = _lib.ENGINES[engine_name]
     with torch.cuda.device(dev):
-        ctx = get_context(n, d, world, rank, dev, strip_len, step_flags(engine_name))
+        ctx = get_context(n, d, world, rank, dev, strip_len, step_flags(engine_name, exact_weights=exact_weights))
         lay, dims = ctx.layout, ctx.dims
         local = pack_local(z1, z2, joints1, joints2)
         gathered = torch.empty(world * local.numel(), dtype=torch.float32, device=dev)

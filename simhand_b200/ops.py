@@ -321,10 +321,9 @@ class _WeightedNTXentFn(torch.autograd.Function):
                                       pos_weighted=pos_weighted, neg_weighted=neg_weighted, weighting=weighting,
                                       exact_weights=exact_weights)
         else:
-            if not (pos_weighted and neg_weighted) or tuple(weighting or DEFAULT_WEIGHTING) != DEFAULT_WEIGHTING:
-                raise NotImplementedError("the sharded path implements linear / mpjpe / pos_neg weighting only")
             from .dist import run_step_sharded
             loss, dz1, dz2 = run_step_sharded(z1, z2, joints1, joints2, temperature, engine, want, group, grad_scale,
+                                              pos_weighted=pos_weighted, neg_weighted=neg_weighted, weighting=weighting,
                                               exact_weights=exact_weights)
         if want:
             ctx.save_for_backward(dz1, dz2)

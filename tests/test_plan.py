@@ -25,8 +25,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.Dims) == 40
     assert ctypes.sizeof(_lib.Stats) == 48
-    assert ctypes.sizeof(_lib.Exchange) == 8 + 3 * 8 * 8
-    assert ctypes.sizeof(_lib.Layout) == 15 * 8 + 6 * 4
+    assert ctypes.sizeof(_lib.Exchange) == 8 + 3 * 8 * 8 + 8
+    assert ctypes.sizeof(_lib.Layout) == 16 * 8 + 6 * 4
     assert ctypes.sizeof(_lib.Inputs) == 88
 
 
