@@ -164,8 +164,7 @@ def run_reference(args):
     line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 / base["value"], higher_is_better=True, scaling="strong",
                 vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="handclr_w loss fwd+bwd, global batch 8192 (2N=16384), d=128, 21 joints, "
-                                     "mpjpe/linear/pos_neg, tau 0.5", global_batch=N_PER_VIEW, proj_dim=DIM),
+                config=dict(workload=WORKLOAD, global_batch=N_PER_VIEW, proj_dim=DIM),
                 cpu_baseline=dict(value=base["value"], unit=UNIT, cores=base["cores"], kind=base["kind"],
                                   sample=base["sample"]),
                 e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -176,10 +175,14 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+WORKLOAD = ("handclr_w loss fwd+bwd, global batch 8192 (2N=16384), d=128, 21 joints, mpjpe/linear/pos_neg, tau 0.5")
+
+
 def run_ours(args):
     import torch.distributed as dist
     from simhand_b200 import _lib, ops
     from simhand_b200.dist import run_step_sharded
+    from simhand_b200.pipeline import HostPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -199,95 +202,128 @@ def run_ours(args):
     hj1, hj2 = j1[sl].contiguous().pin_memory(), j2[sl].contiguous().pin_memory()
     dz1_, dz2_, dj1, dj2 = hz1.to(dev), hz2.to(dev), hj1.to(dev), hj2.to(dev)
     engine = args.engine
+    transport = args.transport
+    steps, warmup = args.steps, max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier(group)
         torch.cuda.synchronize(dev)
 
-    transport = args.transport
+    def make_step(exact):
+        """The library's step on device-resident inputs (what `value` times)."""
+        def fn(a, b, c, e):
+            if world == 1:
+                return ops.run_step(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True, exact_weights=exact)
+            return run_step_sharded(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True, group, transport=transport,
+                                    exact_weights=exact)
+        return fn
 
-    def eager_step(a, b, c, e):
-        if world == 1:
-            return ops.run_step(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True)
-        return run_step_sharded(a, b, c[:, :, :2], e[:, :, :2], TAU, engine, True, group, transport=transport)
+    def make_dropin(exact):
+        """The reference's call pattern through the public API (simhand_w_model.py:122-136): get_weights_linear ->
+        vanila_weights_contrastive_loss -> backward (what `e2e` times); on several ranks weighted_ntxent(group=...)."""
+        def fn(a, b, c, e):
+            a = a.detach().requires_grad_(True)
+            b = b.detach().requires_grad_(True)
+            if world == 1:
+                pw, nw = ops.get_weights_linear(c[:, :, :2], e[:, :, :2], "mpjpe")
+                loss = ops.vanila_weights_contrastive_loss(a, b, pw, nw, TAU, engine=engine, exact_weights=exact)
+            else:
+                loss = ops.weighted_ntxent(a, b, c[:, :, :2], e[:, :, :2], TAU, group=group, engine=engine,
+                                           exact_weights=exact)
+            g1, g2 = torch.autograd.grad(loss, (a, b))
+            return loss, g1, g2
+        return fn
 
-    # The step is a fixed sequence of kernel launches on one stream (no host decisions, no NCCL when the peer
-    # exchange is used): capture it once into a CUDA graph and replay it, as a training loop would.
+    # The step is a fixed sequence of kernel launches on one stream (no host decisions, no NCCL with the peer
+    # transports): capture it once into a CUDA graph and replay it, as a training loop would.
     use_graph = args.graph and (world == 1 or transport != "nccl")
-    graph = None
-    if use_graph:
+
+    def time_device(step_fn):
+        graph, static_out = None, None
+        if use_graph:
+            for _ in range(3):
+                step_fn(dz1_, dz2_, dj1, dj2)
+            barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = step_fn(dz1_, dz2_, dj1, dj2)
+            barrier()
+
+        def step():
+            if graph is None:
+                return step_fn(dz1_, dz2_, dj1, dj2)
+            graph.replay()
+            return static_out
+
+        for _ in range(warmup):
+            out = step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            out = step()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), float(out[0]), graph is not None
+
+    def time_e2e(step_fn):
+        """Host buffers in, loss out, copies inside the timed region: simhand_b200.HostPipeline copies batch k+1 H2D on a
+        copy stream while batch k computes, replays the captured drop-in step, reads every step's loss back to pinned
+        host memory and hands it to the caller one step later (one step in flight); the last loss is drained inside the
+        timed region too."""
+        pipe = HostPipeline(step_fn, (hz1, hz2, hj1, hj2), dev, depth=2, use_graph=use_graph, sync_all=barrier, lag=1)
+        pipe.prefetch(hz1, hz2, hj1, hj2)
         for _ in range(3):
-            eager_step(dz1_, dz2_, dj1, dj2)
+            pipe.prefetch(hz1, hz2, hj1, hj2)
+            pipe.step()
+        pipe.step()
+        pipe.drain()
         barrier()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_out = eager_step(dz1_, dz2_, dj1, dj2)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        pipe.prefetch(hz1, hz2, hj1, hj2)
+        host_loss = None
+        for k in range(steps):
+            if k + 1 < steps:
+                pipe.prefetch(hz1, hz2, hj1, hj2)
+            got, _, _ = pipe.step()                    # the previous step's loss, already on the host
+            if got is not None:
+                host_loss = float(got)
+        got, _, _ = pipe.drain()
+        host_loss = float(got)
+        f1.record()
         barrier()
-
-    def step(a, b, c, e):
-        if graph is None:
-            return eager_step(a, b, c, e)
-        if a is not dz1_:
-            dz1_.copy_(a, non_blocking=True)
-            dz2_.copy_(b, non_blocking=True)
-            dj1.copy_(c, non_blocking=True)
-            dj2.copy_(e, non_blocking=True)
-        graph.replay()
-        return static_out
-
-    for _ in range(max(args.warmup, 3)):
-        loss, g1, g2 = step(dz1_, dz2_, dj1, dj2)
-    barrier()
+        return f0.elapsed_time(f1), host_loss
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    # ---- device-resident timing: exactly K steps between two synchronised points
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        loss, g1, g2 = step(dz1_, dz2_, dj1, dj2)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    # ---- end to end: host buffers in, loss out, copies inside the timed region.  simhand_b200.HostPipeline is the
-    # host-buffer front end: batch k+1 is copied H2D on a copy stream while batch k computes; every step's inputs are
-    # copied once (pinned -> device) and every step's loss is read back before the next step is issued.
-    from simhand_b200.pipeline import HostPipeline
-    pipe = HostPipeline(eager_step, (hz1, hz2, hj1, hj2), dev, depth=2, use_graph=use_graph, sync_all=barrier)
-    pipe.prefetch(hz1, hz2, hj1, hj2)
-    for k in range(3):
-        pipe.prefetch(hz1, hz2, hj1, hj2)
-        pipe.step()
-    pipe.step()
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    pipe.prefetch(hz1, hz2, hj1, hj2)
-    for k in range(args.steps):
-        if k + 1 < args.steps:
-            pipe.prefetch(hz1, hz2, hj1, hj2)
-        host_loss, g1, g2 = pipe.step()                # returns after this step's loss is on the host
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-    loss_dev, loss_e2e = float(loss), float(host_loss)
+    ms_total, loss_dev, graphed = time_device(make_step(False))
+    ms_exact, loss_exact, _ = time_device(make_step(True))
+    ms_e2e, loss_e2e = time_e2e(make_dropin(False))
+    ms_e2e_exact, loss_e2e_exact = time_e2e(make_dropin(True))
     if sampler:
         sampler.stop()
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_exact, ms_e2e, ms_e2e_exact], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-    ms_total, ms_e2e = t.tolist()
-    ms_step = ms_total / args.steps
+    ms_total, ms_exact, ms_e2e, ms_e2e_exact = t.tolist()
+    ms_step = ms_total / steps
     value = 1e3 / ms_step
 
-    # ---- per-kernel durations of the same step (instrumented pass; N = 1 only)
-    kernels = None
+    # ---- per-launch durations of the same step (instrumented eager pass), both distance images
+    iters = max(3, min(steps, 10))
     if world == 1:
-        kernels = time_kernels(ops, _lib, dz1_, dz2_, dj1, dj2, engine, max(3, min(args.steps, 10)))
+        kernels = {False: time_kernels(ops, _lib, dz1_, dz2_, dj1, dj2, engine, iters, False),
+                   True: time_kernels(ops, _lib, dz1_, dz2_, dj1, dj2, engine, iters, True)}
+    elif transport in ("auto", "fused"):
+        kernels = {False: time_kernels_sharded(ops, _lib, dz1_, dz2_, dj1, dj2, engine, iters, False, group, barrier),
+                   True: time_kernels_sharded(ops, _lib, dz1_, dz2_, dj1, dj2, engine, iters, True, group, barrier)}
+    else:
+        kernels = None
 
     if rank != 0:
         if world > 1:
@@ -296,65 +332,93 @@ def run_ours(args):
     peaks = _peaks()
     clocks = sampler.summary() if sampler else None
     m = 2 * N_PER_VIEW
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+    h2d = int(hz1.numel() * 8 + hj1.numel() * 8) * world
+    resolved_transport = None
+    if world > 1:
+        resolved_transport = "fused" if transport == "auto" else transport
+    launches = 6 if (world == 1 or resolved_transport == "fused") else 14
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,
                 dtype={"tf32": "tf32 logits / bf16 value operands, fp32 accumulate", "bf16": "bf16",
                        "fp16": "f16 logits (11-bit significand, as tf32) / bf16 value operands, fp32 accumulate"
                        }.get(engine, "f32"), data="synthetic",
-                config=dict(workload="handclr_w loss fwd+bwd, global batch 8192 (2N=16384), d=128, 21 joints, "
-                                     "mpjpe/linear/pos_neg, tau 0.5", global_batch=N_PER_VIEW, proj_dim=DIM,
+                config=dict(workload=WORKLOAD, global_batch=N_PER_VIEW, proj_dim=DIM,
                             engine=engine, parallelism=f"tile-pair sharded x{world}" if world > 1 else "single GPU",
-                            transport=(transport if world > 1 else None), cuda_graph=bool(graph is not None),
-                            l2="per-step working set (MPJPE tile workspace, 0.5 GiB at 1 GPU) exceeds the 126 MB L2; "
+                            transport=resolved_transport, cuda_graph=bool(graphed),
+                            weights="value / e2e: relaxed-weights mode (16-bit image of the joint distances, |dW| <= 1.6e-5, "
+                                    "loss and gradients inside BASELINE.json's tolerances at this size: "
+                                    "tests/test_gpu_fullsize.py); exact_weights: bit-exact distances (0 ulp, the 1-ulp "
+                                    "weight contract) in the fused step",
+                            l2="per-step working set (MPJPE tile workspace, 0.27 / 0.54 GiB at 1 GPU) exceeds the 126 MB L2; "
                                "no explicit flush"),
                 clocks=clocks,
-                e2e=dict(value=1e3 / (ms_e2e / args.steps), unit=UNIT,
-                         h2d_bytes_per_step=int(hz1.numel() * 8 + hj1.numel() * 8) * world, d2h_bytes_per_step=4 * world,
+                e2e=dict(value=1e3 / (ms_e2e / steps), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * world,
                          bytes_scope="whole job (sum over ranks; every rank copies its own shard and reads the loss)",
-                         loss=loss_e2e, api="simhand_b200.HostPipeline (double-buffered H2D, graph replay, loss D2H)"),
+                         loss=loss_e2e,
+                         api="simhand_b200.HostPipeline(lag=1) over the reference's call pattern: get_weights_linear -> "
+                             "vanila_weights_contrastive_loss -> autograd backward (simhand_w_model.py:122-136)"
+                             if world == 1 else
+                             "simhand_b200.HostPipeline(lag=1) over weighted_ntxent(group=WORLD) -> autograd backward"),
+                exact_weights=dict(value=1e3 / (ms_exact / steps), unit=UNIT, ms_per_step=ms_exact / steps, loss=loss_exact,
+                                   e2e=dict(value=1e3 / (ms_e2e_exact / steps), unit=UNIT, loss=loss_e2e_exact,
+                                            h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * world),
+                                   note="same step with exact_weights=True: fp32 tiles of the bit-exact MPJPE (weights 0 ulp "
+                                        "from the reference), correctly rounded sqrt in the distance kernel"),
                 loss=loss_dev,
-                gpu_launches=(6 if world == 1 else 14) * args.steps)
+                gpu_launches=launches * steps)
     if kernels is not None:
         f_clk = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
         xu_peak = NUM_SMS * MUFU_LANES_PER_SM * f_clk * 1e6 / 1e9          # G special-function ops / s
-        t_mpjpe = kernels["mpjpe_kernel"] * 1e-3
-        tiles = (m // 128) * (m // 128 + 1) // 2                          # stored (upper-triangular) MPJPE tiles
-        traffic = _ncu_traffic("mpjpe_kernel")
-        executed = 21.0 * tiles * 128 * 128 / t_mpjpe / 1e9              # sqrt the launch evaluates / its duration
-        line["roofline"] = dict(
-            kernel="mpjpe_kernel", bound="xu (MUFU pipe; neither HBM nor tensor binds this path, SURVEY.md 8d)",
-            achieved=executed, peak=xu_peak, unit="Gop/s (correctly rounded sqrt: 21 per pair the launch evaluates)",
-            frac=executed / xu_peak, traffic=(traffic or {}).get("bytes"),
-            traffic_source=(traffic or {}).get("source"),
-            peak_source=f"148 SMs x 16 MUFU lanes/clk x {f_clk:.0f} MHz (median SM clock under load)",
-            units_per_launch=f"{tiles} tiles x 16384 unordered pairs (symmetry: D_ij == D_ji bitwise)",
-            algorithmic_frac=(21.0 * m * m / t_mpjpe / 1e9) / xu_peak,
-            step_frac=(22.0 * m * m / (ms_step * 1e-3) / 1e9) / xu_peak,
-            note="frac counts the sqrt the kernel executes.  algorithmic_frac counts 21 per ORDERED pair (M^2, as the "
-                 "reference evaluates them) over the same launch time and step_frac is SURVEY 8d's figure, "
-                 "(21 sqrt + 1 exp) M^2 / whole step time over the MUFU peak: both exceed frac because symmetry "
-                 "halves the executed count.  ncu (profiles/): xu 85 %, fma 54 % busy with the default 16-bit tile image "
-                 "(one MUFU.SQRT per joint); the exact-distance variant is fma/xu co-critical (66 % / 65 %).")
-        tile_bytes = 32768.0 if ops.step_flags(engine) else 65536.0      # 16-bit image of the tiles, or fp32
-        hbm_bytes = 8256 * tile_bytes * 2          # each stored tile is read direct + transposed
-        for k in ("sweep_fwd", "sweep_bwd"):
-            kernels[k + "_hbm_frac"] = hbm_bytes / (kernels[k] * 1e-3) / 1e9 / peaks["hbm_gbs"]
-        line["kernels_ms"] = kernels
+        tiles_total = (m // 128) * (m // 128 + 1) // 2                     # stored (upper-triangular) MPJPE tiles
+        tiles = tiles_total / world                                        # per rank (balanced to +-1 tile)
+
+        def roofline_of(kern, exact):
+            t_mpjpe = kern["mpjpe_kernel"] * 1e-3
+            traffic = _ncu_traffic("mpjpe_kernel")
+            executed = 21.0 * tiles * 128 * 128 / t_mpjpe / 1e9            # sqrt one rank's launch evaluates / its duration
+            step_ms = (ms_exact if exact else ms_total) / steps
+            return dict(
+                kernel="mpjpe_kernel", bound="xu (MUFU pipe; neither HBM nor tensor binds this path, SURVEY.md 8d)",
+                achieved=executed, peak=xu_peak,
+                unit=("Gop/s per GPU: correctly rounded sqrt (MUFU.RSQ + Newton step on the FMA pipe), 21 per pair the launch evaluates"
+                      if exact else
+                      "Gop/s per GPU: approximate sqrt (one MUFU.SQRT, no correction: relaxed-weights mode), 21 per pair the launch evaluates"),
+                frac=executed / xu_peak, traffic=(traffic or {}).get("bytes") if (world == 1 and not exact) else None,
+                traffic_source=(traffic or {}).get("source") if (world == 1 and not exact) else None,
+                peak_source=f"148 SMs x 16 MUFU lanes/clk x {f_clk:.0f} MHz (median SM clock under load); nominal issue rate, "
+                            "tools/microbench.cu measures it",
+                units_per_launch=f"{tiles:.0f} tiles x 16384 unordered pairs per rank (symmetry: D_ij == D_ji bitwise)",
+                algorithmic_frac=(21.0 * m * m / world / t_mpjpe / 1e9) / xu_peak,
+                step_frac=(22.0 * m * m / world / (step_ms * 1e-3) / 1e9) / xu_peak,
+                note="frac counts the sqrt the kernel executes.  algorithmic_frac counts 21 per ORDERED pair (M^2 / P per rank, "
+                     "as the reference evaluates them) over the same launch time and step_frac is SURVEY 8d's figure, "
+                     "(21 sqrt + 1 exp) M^2 / (P x whole step time) over the MUFU peak: both exceed frac because symmetry "
+                     "halves the executed count.")
+        line["roofline"] = roofline_of(kernels[False], False)
+        line["exact_weights"]["roofline"] = roofline_of(kernels[True], True)
+        for exact in (False, True):
+            tile_bytes = 65536.0 if exact else 32768.0       # fp32 tiles, or their 16-bit image
+            hbm_bytes = tiles * tile_bytes * 2               # each stored tile is read direct + transposed
+            for k in ("sweep_fwd", "sweep_bwd"):
+                kernels[exact][k + "_hbm_frac"] = hbm_bytes / (kernels[exact][k] * 1e-3) / 1e9 / peaks["hbm_gbs"]
+        line["kernels_ms"] = kernels[False]
+        line["exact_weights"]["kernels_ms"] = kernels[True]
         line["peaks"] = peaks
+    if world == 1:
         line["cpu_baseline"] = cpu_port_sample(rows=128, repeats=3, warmup=1, min_seconds=10.0)
     _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def time_kernels(ops, _lib, z1, z2, j1, j2, engine, iters):
+def time_kernels(ops, _lib, z1, z2, j1, j2, engine, iters, exact):
     """CUDA-event duration of every launch of one step (same stream, same inputs), averaged."""
     import ctypes
     lib = _lib.load()
     eng = _lib.ENGINES[engine]
     dev = z1.device
     n, d = z1.shape
-    ctx = ops.get_context(n, d, 1, 0, dev, 0, ops.step_flags(engine))
+    ctx = ops.get_context(n, d, 1, 0, dev, 0, ops.step_flags(engine, exact_weights=exact))
     inp, keep = ops.make_inputs(z1, z2, j1[:, :, :2], j2[:, :, :2])
     ws = torch.empty(int(ctx.layout.ws_bytes), dtype=torch.uint8, device=dev)
     loss = torch.empty((), device=dev)
@@ -384,6 +448,43 @@ def time_kernels(ops, _lib, z1, z2, j1, j2, engine, iters):
     return {k: v / iters for k, v in acc.items()}
 
 
+def time_kernels_sharded(ops, _lib, z1, z2, j1, j2, engine, iters, exact, group, barrier):
+    """Fused transport: CUDA-event duration of each of the six launches of a rank (a launch's time includes its wait for
+    the other ranks' stage signal), max over ranks."""
+    import torch.distributed as dist
+    from simhand_b200 import dist as sd
+    lib = _lib.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = z1.device
+    n_local, d = z1.shape
+    n = n_local * world
+    eng = _lib.ENGINES[engine]
+    ctx = ops.get_context(n, d, world, rank, dev, 0, ops.step_flags(engine, exact_weights=exact))
+    ex = sd.get_exchange(ctx, group, 0, fused=True)
+    local_in, keep = ops.make_inputs(z1, z2, j1[:, :, :2], j2[:, :, :2])
+    loss = torch.empty((), device=dev)
+    g1, g2 = torch.empty((n_local, d), device=dev), torch.empty((n_local, d), device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    names = {"prep": "shard_prep", "mpjpe": "mpjpe_kernel", "fwd": "sweep_fwd", "bwd": "sweep_bwd", "fin": "finalize"}
+    acc = {v: 0.0 for v in names.values()}
+    for it in range(iters + 1):
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(sd.FUSED_STAGES) + 1)]
+        evs[0].record()
+        for i, stage in enumerate(sd.FUSED_STAGES):
+            sd._fused_launches(lib, ctx, ex.struct, ex.ws.data_ptr(), local_in, TAU, eng, True, 1.0, (loss, g1, g2), st,
+                               stages=(stage,))
+            evs[i + 1].record()
+        torch.cuda.synchronize(dev)
+        if it == 0:
+            continue
+        for i, stage in enumerate(sd.FUSED_STAGES):
+            acc[names[stage]] += evs[i].elapsed_time(evs[i + 1])
+    t = torch.tensor([acc[v] / iters for v in names.values()], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return dict(zip(names.values(), t.tolist()))
+
+
 _JSON_FD = None
 
 
@@ -409,8 +510,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="fp16", choices=["tf32", "fp32", "auto", "bf16", "fp16"])
-    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
-                    help="multi-GPU exchange: collectives fused into the kernels over peer memory, or NCCL calls")
+    ap.add_argument("--transport", default="auto", choices=["auto", "fused", "peer", "nccl"],
+                    help="multi-GPU exchange: fused into the kernels over peer memory (default), the same as separate "
+                         "push / barrier kernels, or NCCL calls")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch the step eagerly")
     args = ap.parse_args()
     if args.impl == "reference":

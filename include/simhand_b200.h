@@ -103,6 +103,10 @@ typedef struct smh_dims {
 #define SMH_DIFF_W_ABS 1    /* negatives: || ((|dx_k| + |dy_k|) / 2)_k ||; positives: || mean_k (|dx_k|, |dy_k|) || */
 #define SMH_DIFF_W_O_ABS 2  /* negatives: || ((dx_k + dy_k) / 2)_k ||;     positives: || mean_k (dx_k, dy_k) ||
                              * (the reference reduces over different axes for the two, utils.py:219-227 vs :241-249) */
+#define SMH_DIFF_EUCLID 3   /* || a - b ||_2 over all 42 coordinates of the joint block: the *_with_pca weightings
+                             * (utils.py:264-301, :349-388), whose inputs are [N, K <= 42] PCA coordinates (apply_pca,
+                             * utils.py:192-215) handed over zero-padded as [N, 21, 2]; all three reference diff_types
+                             * reduce to this distance there */
 /* smh_dims_t.weight_type */
 #define SMH_WEIGHT_LINEAR 0     /* W = (max D - D) / (max D - min D) */
 #define SMH_WEIGHT_NONLINEAR 1  /* W = 1 / (1 + exp(lambda (D - mean D))); single rank */

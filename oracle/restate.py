@@ -282,6 +282,13 @@ def port_distances(joints1, joints2, diff_type: str):
         fn = torch.abs if diff_type == "w_abs" else (lambda t: t)
         pos = torch.norm(fn(joints1 - joints2).mean(dim=1), dim=1)                            # :219-227: mean over joints
         neg = torch.norm(torch.mean(fn(bj.unsqueeze(1) - bj.unsqueeze(0)), dim=-1), dim=2)    # :241-249: mean over x, y
+    elif diff_type == "pca":
+        # *_with_pca (utils.py:264-301, :349-388): joints are [N, K] coordinate vectors; every reference diff_type is
+        # the Euclidean distance between them
+        j1, j2 = joints1.reshape(joints1.shape[0], -1), joints2.reshape(joints2.shape[0], -1)
+        bj = torch.cat((j1, j2), dim=0)
+        pos = torch.norm(j1 - j2, dim=-1)                                                     # :265-274
+        neg = torch.norm(bj.unsqueeze(1) - bj.unsqueeze(0), dim=-1)                            # :282-293
     else:
         raise ValueError(diff_type)
     return pos, neg

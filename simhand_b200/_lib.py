@@ -27,7 +27,7 @@ FINALIZE_GRAD = 0x8000
 DIMS_DENSE_WEIGHTS = 1
 DIMS_DENSE_BACKWARD = 2
 DIMS_Q16_TILES = 4
-DIFF_TYPES = {"mpjpe": 0, "w_abs": 1, "w_o_abs": 2}
+DIFF_TYPES = {"mpjpe": 0, "w_abs": 1, "w_o_abs": 2, "pca": 3}
 WEIGHT_TYPES = {"linear": 0, "non_linear": 1}
 FLAG_SLOW_DOMAIN = 1
 FLAG_NONFINITE = 2

@@ -53,7 +53,7 @@ static int validate_dims(const smh_dims_t *dims)
     if ((dims->flags & SMH_DIMS_Q16_TILES) &&
         ((dims->flags & SMH_DIMS_DENSE_WEIGHTS) || dims->diff_type != SMH_DIFF_MPJPE || dims->weight_type != SMH_WEIGHT_LINEAR))
         return set_error(SMH_E_MODE, "SMH_DIMS_Q16_TILES: only with linear / mpjpe weights built from the joints");
-    if (dims->diff_type < SMH_DIFF_MPJPE || dims->diff_type > SMH_DIFF_W_O_ABS)
+    if (dims->diff_type < SMH_DIFF_MPJPE || dims->diff_type > SMH_DIFF_EUCLID)
         return set_error(SMH_E_MODE, "unknown diff_type %d", dims->diff_type);
     if (dims->weight_type != SMH_WEIGHT_LINEAR && dims->weight_type != SMH_WEIGHT_NONLINEAR)
         return set_error(SMH_E_MODE, "unknown weight_type %d", dims->weight_type);
@@ -289,7 +289,7 @@ static int make_peers(const smh_dims_t &dims, const smh_layout_t &lay, void *ws_
     for (int p = 0; p < exch->world; ++p) {
         if (!exch->ws_peer[p]) return set_error(SMH_E_ARG, "exchange ws_peer[%d] is null", p);
         out->ws[p] = (unsigned char *)exch->ws_peer[p];
-        if (exch->fused && !exch->signal_peer[p]) return set_error(SMH_E_ARG, "exchange signal_peer[%d] is null", p);
+        if (!exch->signal_peer[p]) return set_error(SMH_E_ARG, "exchange signal_peer[%d] is null", p);
         out->sig[p] = (uint32_t *)exch->signal_peer[p];
     }
     out->fused = exch->fused ? 1 : 0;

@@ -4,7 +4,9 @@
 //                       pointers, NVLink)
 //   barrier_kernel      device-side barrier between the phases of a step.  Monotonic counters (word 0 = barriers this
 //                       rank has entered, word 8 + p = last barrier peer p announced), so the same kernel node can be
-//                       replayed from a CUDA graph without host-side epochs.
+//                       replayed from a CUDA graph without host-side epochs.  The wait is bounded (smh_exchange_t.timeout_ms,
+//                       30 s by default); a timeout poisons the group and the loss becomes NaN.
+// This is the UNFUSED form of the exchange (14 launches per step); the default is the fused one in smh_shard.cu.
 //   exchange_neg_kernel / exchange_dz_kernel   all-gather of the partial row sums and reduce-scatter payload of the
 //                       partial gradient rows: plain 16-byte stores into slot `rank` of the peers' partial buffers; the
 //                       consumers add the partials in rank order (deterministic).  (Adding straight into the peers'
@@ -118,6 +120,7 @@ int launch_exchange_dz(const smh_dims_t &dims, const smh_layout_t &lay, const Pe
 struct BarrierArgs {
     uint32_t *sig[kMaxPeers];
     int world, rank;
+    unsigned timeout_ms;
 };
 
 __global__ void __launch_bounds__(32) barrier_kernel(BarrierArgs a)
@@ -136,9 +139,16 @@ __global__ void __launch_bounds__(32) barrier_kernel(BarrierArgs a)
         volatile uint32_t *theirs = a.sig[p] + 8 + a.rank;
         *theirs = cnt;                             // announce: this rank has entered barrier `cnt`
         volatile uint32_t *from_p = mine + 8 + p;
-        const long long t0 = clock64();
+        // bounded: a missing peer must not hang the device -- but a timeout is a FAILURE, never a fall-through: the
+        // group is poisoned (sticky word on every rank) and smh_finalize turns the loss into NaN
+        const unsigned long long t0 = global_ns();
+        const unsigned long long limit = (unsigned long long)(a.timeout_ms ? a.timeout_ms : 30000u) * 1000000ull;
+        uint32_t spin = 0;
         while ((int32_t)(*from_p - cnt) < 0) {
-            if (clock64() - t0 > 4000000000ll) break;      // bounded: a missing peer must not hang the device
+            if ((++spin & 255u) == 0u && global_ns() - t0 > limit) {
+                for (int q = 0; q < a.world; ++q) atomicCAS_system(a.sig[q] + kSigPoison, 0u, 130u);
+                break;
+            }
         }
     }
     __threadfence_system();
@@ -149,6 +159,7 @@ int launch_barrier(const smh_exchange_t &exch, cudaStream_t stream)
     BarrierArgs a;
     a.world = exch.world;
     a.rank = exch.rank;
+    a.timeout_ms = exch.timeout_ms;
     for (int p = 0; p < exch.world; ++p) {
         if (!exch.signal_peer[p]) return set_error(SMH_E_ARG, "exchange signal_peer[%d] is null", p);
         a.sig[p] = (uint32_t *)exch.signal_peer[p];

@@ -86,6 +86,8 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
         for (int p = 0; p < peers.world; ++p) total += __ldcg(peers.lossparts(peers.rank) + p);       // rank order
         float loss = total / (float)m;
         if ((stats->flags & SMH_FLAG_NONFINITE) || stats->fail_site != 0u) loss = CUDART_NAN_F;
+        if (peers.sig[peers.rank] != nullptr && ld_acquire_sys(peers.sig[peers.rank] + kSigPoison) != 0u)
+            loss = CUDART_NAN_F;          // a barrier of the group timed out (now or earlier): nothing of this step is trusted
         stats->loss = loss;
         if (loss_out) *loss_out = loss;
     }

@@ -246,7 +246,9 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
 // dx, dy for w_abs.  One sqrt per pair: a light kernel (same tiles, same layout, same max reduction).  Symmetric with
 // a zero diagonal like the MPJPE, so the upper triangle is enough.  IEEE sqrt: no input-domain restriction.
 // ----------------------------------------------------------------------------------------------
-template <bool ABS>
+// MODE 0: w_o_abs, 1: w_abs, 2: euclid (SMH_DIFF_EUCLID, the *_with_pca weightings: D_ij = || a - b ||_2 over the 42
+// packed coordinates, utils.py:282-293)
+template <int MODE>
 __global__ void __launch_bounds__(256, 2)
 altdist_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float *__restrict__ dist, int m,
                Stats *__restrict__ stats, Peers peers, int signal2)
@@ -286,15 +288,27 @@ altdist_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, flo
             for (int p = 0; p < 10; ++p) {          // packed (x_2p, x_2p+1, y_2p, y_2p+1)
                 float dx0 = a[4 * p] - b[4 * p], dx1 = a[4 * p + 1] - b[4 * p + 1];
                 float dy0 = a[4 * p + 2] - b[4 * p + 2], dy1 = a[4 * p + 3] - b[4 * p + 3];
-                if (ABS) { dx0 = fabsf(dx0); dx1 = fabsf(dx1); dy0 = fabsf(dy0); dy1 = fabsf(dy1); }
+                if (MODE == 2) {
+                    acc = fmaf(dx0, dx0, acc);
+                    acc = fmaf(dy0, dy0, acc);
+                    acc = fmaf(dx1, dx1, acc);
+                    acc = fmaf(dy1, dy1, acc);
+                    continue;
+                }
+                if (MODE == 1) { dx0 = fabsf(dx0); dx1 = fabsf(dx1); dy0 = fabsf(dy0); dy1 = fabsf(dy1); }
                 const float t0 = 0.5f * (dx0 + dy0), t1 = 0.5f * (dx1 + dy1);
                 acc = fmaf(t0, t0, acc);
                 acc = fmaf(t1, t1, acc);
             }
             float dx = a[40] - b[40], dy = a[41] - b[41];
-            if (ABS) { dx = fabsf(dx); dy = fabsf(dy); }
-            const float t = 0.5f * (dx + dy);
-            acc = fmaf(t, t, acc);
+            if (MODE == 2) {
+                acc = fmaf(dx, dx, acc);
+                acc = fmaf(dy, dy, acc);
+            } else {
+                if (MODE == 1) { dx = fabsf(dx); dy = fabsf(dy); }
+                const float t = 0.5f * (dx + dy);
+                acc = fmaf(t, t, acc);
+            }
             dv[u] = __fsqrt_rn(acc);
             if (row_ok && (c0 + u) < col_limit) vmax_bits = max(vmax_bits, __float_as_uint(dv[u]));
         }
@@ -389,9 +403,11 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
         return set_error(SMH_E_DIM, "w_abs / w_o_abs / non_linear on several ranks need the fused exchange");
     if (dims.diff_type != SMH_DIFF_MPJPE) {
         if (dims.diff_type == SMH_DIFF_W_ABS)
-            altdist_kernel<true><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
+            altdist_kernel<1><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
+        else if (dims.diff_type == SMH_DIFF_EUCLID)
+            altdist_kernel<2><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
         else
-            altdist_kernel<false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
+            altdist_kernel<0><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
     } else if (lay.n_stored_tiles < 8 * 2 * kNumCtas) {
         // fewer than ~8 waves of whole tiles (2 CTAs x 148 SMs per wave): cut the tiles in halves
         if (dims.flags & SMH_DIMS_Q16_TILES)

@@ -161,6 +161,8 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(ShardPrepArgs a, Peers 
                 for (int q = 0; q < 8; ++q)
                     s = __fadd_rn(s, __fadd_rn(__shfl_sync(0xffffffffu, nk, q), __shfl_sync(0xffffffffu, nk, q + 8)));
                 dk = __fdiv_rn(s, 21.0f);
+            } else if (a.diff == SMH_DIFF_EUCLID) {
+                dk = __fsqrt_rn(warp_sum(__fmaf_rn(dy, dy, __fmul_rn(dx, dx))));       // utils.py:265-274: || p1 - p2 ||_2
             } else {
                 if (a.diff == SMH_DIFF_W_ABS) {
                     dx = fabsf(dx);

@@ -449,6 +449,45 @@ def get_weights_nonlinear(joints1: torch.Tensor, joints2: torch.Tensor, lambda_p
     return LazyWeights(src, "pos"), LazyWeights(src, "neg")
 
 
+def apply_pca(joints: torch.Tensor, target_dim: int = 14) -> torch.Tensor:
+    """Drop-in for `src/models/utils.py:192-215`: `[B, 21, 2]` joints -> `[B, target_dim]` coordinates in the basis of
+    `torch.pca_lowrank` (a randomised library routine, as in the reference).  Unlike the reference it stays on the joints'
+    device (the reference moves the batch to the CPU and back every step)."""
+    if joints.dim() != 3 or tuple(joints.shape[1:]) != (21, 2):
+        raise ValueError(f"Expected joints to have shape (batch, 21, 2), but got {tuple(joints.shape)}")
+    flat = joints.contiguous().view(joints.shape[0], -1).float()
+    _, _, v = torch.pca_lowrank(flat, q=target_dim)
+    return torch.matmul(flat, v[:, :target_dim])
+
+
+def _pca_source(joints1: torch.Tensor, joints2: torch.Tensor, weight_type: str, lambda_pos: float, lambda_neg: float,
+                diff_type: str) -> "_WeightSource":
+    if diff_type not in ("mpjpe", "w_abs", "w_o_abs"):
+        raise ValueError(f"diff_type must be mpjpe, w_abs or w_o_abs, got {diff_type!r}")
+    if joints1.dim() != 2 or joints1.shape != joints2.shape or joints1.shape[1] > 42:
+        raise ValueError(f"PCA coordinates must be [N, K <= 42] with equal shapes, got {tuple(joints1.shape)} / "
+                         f"{tuple(joints2.shape)}")
+    k = joints1.shape[1]
+    pad = lambda t: torch.nn.functional.pad(_as_f32(t), (0, 42 - k)).view(t.shape[0], 21, 2)      # noqa: E731
+    # all three diff_types are the Euclidean distance between the coordinate vectors there (utils.py:265-293):
+    # || |a - b| || == || a - b ||
+    return _WeightSource(pad(joints1), pad(joints2), make_weighting(weight_type, "pca", lambda_pos, lambda_neg))
+
+
+def get_weights_linear_with_pca(joints1: torch.Tensor, joints2: torch.Tensor, diff_type: str):
+    """Drop-in for `src/models/utils.py:264-301` (`config.use_pca`): linear weights from the Euclidean distance between
+    `[N, K]` PCA coordinates (`apply_pca`).  Returns lazy handles, as `get_weights_linear`."""
+    src = _pca_source(joints1, joints2, "linear", 0.0, 0.0, diff_type)
+    return LazyWeights(src, "pos"), LazyWeights(src, "neg")
+
+
+def get_weights_nonlinear_with_pca(joints1: torch.Tensor, joints2: torch.Tensor, lambda_pos: float, lambda_neg: float,
+                                   diff_type: str):
+    """Drop-in for `src/models/utils.py:349-388`: sigmoid weights from the same distance."""
+    src = _pca_source(joints1, joints2, "non_linear", lambda_pos, lambda_neg, diff_type)
+    return LazyWeights(src, "pos"), LazyWeights(src, "neg")
+
+
 def vanila_weights_contrastive_loss(z1: torch.Tensor, z2: torch.Tensor, pos_weights, neg_weights,
                                     temperature: float = 0.5, engine: str = _DEFAULT_ENGINE,
                                     exact_weights: Optional[bool] = None) -> torch.Tensor:
@@ -505,7 +544,8 @@ def vanila_contrastive_loss(z1, z2, temperature: float = 0.5, engine: str = _DEF
 
 
 _DROP_INS = ("get_weights_linear", "get_weights_nonlinear", "vanila_weights_contrastive_loss", "vanila_pos_weights_contrastive_loss",
-             "vanila_neg_weights_contrastive_loss", "vanila_contrastive_loss")
+             "vanila_neg_weights_contrastive_loss", "vanila_contrastive_loss", "apply_pca", "get_weights_linear_with_pca",
+             "get_weights_nonlinear_with_pca")
 
 
 def install(*modules) -> None:

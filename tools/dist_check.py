@@ -65,6 +65,33 @@ def main():
         print(f"rank {rank}/{world}: 24 skewed back-to-back steps + loss-only step: worst scaled error {worst:.1e} -> "
               f"{'PASS' if ok2 else 'MISMATCH'}", flush=True)
         ok = ok and ok2
+    if transport in ("auto", "fused"):
+        # a rank that stays away for 3 s (checkpoint, dataloader stall): the others wait (bounded at 30 s by default) and
+        # the step is still exact -- a timeout would poison the group and give NaN, never a silently wrong loss
+        if rank == world - 1:
+            torch.cuda._sleep(int(3.0 * 1.9e9))
+        l3, g31, g32 = run_step_sharded(*local[0], 0.5, "tf32", True, dist.group.WORLD, transport=transport)
+        torch.cuda.synchronize()
+        ok3 = abs(float(l3) - float(refs[0][0])) <= 2e-6 * abs(float(refs[0][0]))
+        # the other weightings on several ranks (fused exchange only)
+        ok4 = True
+        for wt, pos, neg in ((ops.make_weighting("non_linear", "mpjpe", 2.5, 0.05), True, True),
+                             (ops.make_weighting("linear", "w_abs"), True, True),
+                             (ops.make_weighting("linear", "mpjpe"), True, False),
+                             (ops.make_weighting("linear", "mpjpe"), False, True)):
+            ls, s1, s2 = run_step_sharded(*local[0], 0.5, "fp16", True, dist.group.WORLD, transport=transport,
+                                          pos_weighted=pos, neg_weighted=neg, weighting=wt)
+            p, q, r, s_ = batches[0]
+            lf, f1, f2 = ops.run_step(p.to(dev), q.to(dev), r.to(dev)[:, :, :2], s_.to(dev)[:, :, :2], 0.5, "fp16", True,
+                                      pos_weighted=pos, neg_weighted=neg, weighting=wt)
+            torch.cuda.synchronize()
+            sc = float(f1.abs().max())
+            e = max(abs(float(ls) - float(lf)) / abs(float(lf)), float((s1 - f1[sl]).abs().max()) / sc * 1e-2,
+                    float((s2 - f2[sl]).abs().max()) / sc * 1e-2)
+            ok4 = ok4 and e < 2e-6
+        print(f"rank {rank}/{world}: step after a 3 s stall of one rank -> {'PASS' if ok3 else 'MISMATCH'}; "
+              f"other weightings sharded -> {'PASS' if ok4 else 'MISMATCH'}", flush=True)
+        ok = ok and ok3 and ok4
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
