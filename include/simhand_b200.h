@@ -299,6 +299,51 @@ int smh_transform_bwd(const float *x_dev, int64_t x_row_stride, const float *out
                       const float *save_dev, const float *dout_dev, int64_t dout_row_stride, float *dx_dev,
                       int64_t dx_row_stride, int64_t rows, int32_t d, float eps, void *stream);
 
+/* K5: the projection head fused with the first normalisation (src/models/unsupervised/simclr_model.py:22-39
+ * Linear(in, hidden, bias) -> BatchNorm1d(hidden) in training mode -> ReLU -> Linear(hidden, out, no bias), followed by the
+ * F.normalize of simhand_w_model.py:56-58), 16-bit operands (the reference trains under 16-bit autocast), fp32 accumulation.
+ * smh_head_forward = two tcgen05 kernels: GEMM 1 with the BatchNorm column statistics reduced in its epilogue; GEMM 2 with
+ * BN + ReLU applied in shared memory to its A operand and the row-wise L2 normalisation in its epilogue.
+ * smh_head_backward = normalise-backward + dA = dP W2 (tcgen05) + ReLU mask + BatchNorm-backward reductions in one kernel and
+ * the BatchNorm backward in a second: it produces dP, A = relu(bn(H)) and dH; the three plain GEMMs left
+ * (dW2 = dP^T A, dW1 = dH^T X, dX = dH W1) are library GEMMs on the caller's side.
+ * Shapes: in_dim % 64 == 0, hidden % 256 == 0 (<= 1024), out_dim == 128; 16-bit pointers 16-byte aligned. */
+typedef struct smh_head {
+    int64_t rows;                /* 2B */
+    int32_t in_dim, hidden, out_dim;
+    int32_t fp16;                /* 0: bf16 activations / weights, 1: fp16 */
+    int32_t training;            /* 1: batch statistics (and running estimates updated); 0: eval, running estimates used */
+    int32_t reserved;
+    const void *x_dev;           /* [rows, in_dim] 16-bit encodings */
+    int64_t x_row_stride;        /* elements */
+    const void *w1_dev;          /* [hidden, in_dim] 16-bit */
+    const float *b1_dev;         /* [hidden] fp32 */
+    const float *gamma_dev, *beta_dev;            /* [hidden] fp32 BatchNorm affine */
+    float *running_mean_dev, *running_var_dev;    /* [hidden] fp32, updated in place; NULL = not tracked */
+    float bn_eps, bn_momentum;
+    const void *w2_dev;          /* [out_dim, hidden] 16-bit */
+    void *h_dev;                 /* out: [rows, hidden] 16-bit, Linear-1 output (kept for the backward) */
+    float *colsum_dev;           /* scratch: [2, hidden] fp32 */
+    float *save_mean_dev, *save_rstd_dev;         /* out: [hidden] fp32 batch statistics */
+    float *y_dev;                /* out: [rows, out_dim] fp32 L2-normalised projections */
+    float *norm_dev;             /* out: [rows] fp32 row norms before the normalisation */
+    float norm_eps;              /* F.normalize eps (1e-12) */
+} smh_head_t;
+
+typedef struct smh_head_bwd {
+    const float *dy_dev;         /* [rows, out_dim] fp32 gradient w.r.t. the normalised projections */
+    const void *w2t_dev;         /* [hidden, out_dim] 16-bit: W2 transposed */
+    void *dp_dev;                /* out: [rows, out_dim] 16-bit gradient w.r.t. Linear-2 output */
+    void *a_dev;                 /* out: [rows, hidden] 16-bit relu(bn(H)) (for dW2 = dP^T A) */
+    void *dhn_dev;               /* scratch: [rows, hidden] 16-bit */
+    void *dh_dev;                /* out: [rows, hidden] 16-bit gradient w.r.t. Linear-1 output */
+    float *colsum_dev;           /* scratch: [2, hidden] fp32 */
+    float *dgamma_dev, *dbeta_dev;                /* out: [hidden] fp32 */
+} smh_head_bwd_t;
+
+int smh_head_forward(const smh_head_t *head, void *stream);
+int smh_head_backward(const smh_head_t *head, const smh_head_bwd_t *bwd, void *stream);
+
 /* device self-tests used by tests/ (exhaustive exact-sqrt / exact-division checks, tcgen05 tile
  * checks).  out_dev receives test-specific counters. */
 int smh_selftest(int which, uint64_t *out_dev, int64_t out_words, void *stream);

@@ -9,5 +9,6 @@ from .ops import (LazyWeights, apply_pca, get_weights_linear_with_pca, get_weigh
                   vanila_pos_weights_contrastive_loss, vanila_weights_contrastive_loss, weighted_ntxent)
 
 from .pipeline import HostPipeline  # noqa: F401,E402
+from .head import FusedProjectionHead  # noqa: F401,E402
 
 __version__ = "0.1.0"

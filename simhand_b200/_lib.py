@@ -69,6 +69,22 @@ class Exchange(ctypes.Structure):
                 ("timeout_ms", ctypes.c_uint32)]
 
 
+class Head(ctypes.Structure):
+    _fields_ = [("rows", ctypes.c_int64), ("in_dim", ctypes.c_int32), ("hidden", ctypes.c_int32), ("out_dim", ctypes.c_int32),
+                ("fp16", ctypes.c_int32), ("training", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("x", ctypes.c_void_p), ("x_row_stride", ctypes.c_int64), ("w1", ctypes.c_void_p), ("b1", ctypes.c_void_p),
+                ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("running_mean", ctypes.c_void_p),
+                ("running_var", ctypes.c_void_p), ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float),
+                ("w2", ctypes.c_void_p), ("h", ctypes.c_void_p), ("colsum", ctypes.c_void_p), ("save_mean", ctypes.c_void_p),
+                ("save_rstd", ctypes.c_void_p), ("y", ctypes.c_void_p), ("norm", ctypes.c_void_p), ("norm_eps", ctypes.c_float)]
+
+
+class HeadBwd(ctypes.Structure):
+    _fields_ = [("dy", ctypes.c_void_p), ("w2t", ctypes.c_void_p), ("dp", ctypes.c_void_p), ("a", ctypes.c_void_p),
+                ("dhn", ctypes.c_void_p), ("dh", ctypes.c_void_p), ("colsum", ctypes.c_void_p), ("dgamma", ctypes.c_void_p),
+                ("dbeta", ctypes.c_void_p)]
+
+
 SIGNAL_WORDS = 256
 SIG_EPOCH = 16
 SIG_POISON = 17
@@ -86,7 +102,7 @@ EXPORTS = ("smh_version", "smh_last_error", "smh_layout", "smh_plan_build", "smh
            "smh_forward", "smh_backward", "smh_finalize", "smh_weights_dense", "smh_l2norm_fwd",
            "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params", "smh_push_inputs",
            "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz", "smh_import_weights", "smh_transform_fwd", "smh_transform_bwd",
-           "smh_scale_grads", "smh_shard_prep")
+           "smh_scale_grads", "smh_shard_prep", "smh_head_forward", "smh_head_backward")
 
 _lib = None
 
@@ -120,6 +136,8 @@ def load() -> ctypes.CDLL:
     lib.smh_finalize.argtypes = [pd, pi, vp, vp, f32, f32, vp, vp, vp, i64, ctypes.c_int, ctypes.POINTER(Exchange), vp]
     lib.smh_weights_dense.argtypes = [pd, vp, vp, vp, vp, vp]
     lib.smh_import_weights.argtypes = [pd, vp, vp, vp, i64, vp, vp]
+    lib.smh_head_forward.argtypes = [ctypes.POINTER(Head), vp]
+    lib.smh_head_backward.argtypes = [ctypes.POINTER(Head), ctypes.POINTER(HeadBwd), vp]
     lib.smh_scale_grads.argtypes = [vp, vp, vp, vp, vp, i64, vp]
     lib.smh_l2norm_fwd.argtypes = [vp, vp, vp, i64, i32, f32, vp]
     lib.smh_l2norm_bwd.argtypes = [vp, vp, vp, vp, i64, i32, f32, vp]

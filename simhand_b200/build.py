@@ -18,7 +18,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libsimhand_b200.so")
 
-SOURCES = ["smh_api.cu", "smh_prep.cu", "smh_mpjpe.cu", "smh_sweep_fp32.cu", "smh_sweep_tc.cu", "smh_exchange.cu", "smh_shard.cu", "smh_transform.cu",
+SOURCES = ["smh_api.cu", "smh_prep.cu", "smh_mpjpe.cu", "smh_sweep_fp32.cu", "smh_sweep_tc.cu", "smh_exchange.cu", "smh_shard.cu", "smh_head.cu", "smh_transform.cu",
            "smh_finalize.cu", "smh_selftest.cu"]
 HEADERS = ["smh_common.cuh", "smh_internal.h", os.path.join("..", "..", "include", "simhand_b200.h")]
 

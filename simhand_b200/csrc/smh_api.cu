@@ -678,6 +678,35 @@ int smh_transform_bwd(const float *x_dev, int64_t x_row_stride, const float *out
                                 dx_row_stride, rows, d, eps, (cudaStream_t)stream);
 }
 
+static int check_head(const smh_head_t *h)
+{
+    if (!h) return set_error(SMH_E_ARG, "head is null");
+    if (!h->x_dev || !h->w1_dev || !h->b1_dev || !h->gamma_dev || !h->beta_dev || !h->w2_dev || !h->h_dev || !h->colsum_dev ||
+        !h->save_mean_dev || !h->save_rstd_dev || !h->y_dev || !h->norm_dev)
+        return set_error(SMH_E_ARG, "head: null pointer");
+    if ((h->running_mean_dev == nullptr) != (h->running_var_dev == nullptr))
+        return set_error(SMH_E_ARG, "head: running_mean and running_var go together");
+    if (h->x_row_stride < h->in_dim) return set_error(SMH_E_ARG, "head: x_row_stride < in_dim");
+    return 0;
+}
+
+int smh_head_forward(const smh_head_t *head, void *stream)
+{
+    int rc = check_head(head);
+    if (rc) return rc;
+    return launch_head_fwd(*head, (cudaStream_t)stream);
+}
+
+int smh_head_backward(const smh_head_t *head, const smh_head_bwd_t *bwd, void *stream)
+{
+    int rc = check_head(head);
+    if (rc) return rc;
+    if (!bwd || !bwd->dy_dev || !bwd->w2t_dev || !bwd->dp_dev || !bwd->a_dev || !bwd->dhn_dev || !bwd->dh_dev || !bwd->colsum_dev ||
+        !bwd->dgamma_dev || !bwd->dbeta_dev)
+        return set_error(SMH_E_ARG, "head backward: null pointer");
+    return launch_head_bwd(*head, *bwd, (cudaStream_t)stream);
+}
+
 int smh_selftest(int which, uint64_t *out_dev, int64_t out_words, void *stream)
 {
     if (!out_dev || out_words < 8) return set_error(SMH_E_ARG, "out buffer needs >= 8 words");

@@ -76,6 +76,8 @@ int launch_transform_fwd(const float *x, int64_t x_stride, const float *tx, cons
 int launch_transform_bwd(const float *x, int64_t x_stride, const float *p, int64_t p_stride, const float *save,
                          const float *dp, int64_t dp_stride, float *dx, int64_t dx_stride, int64_t rows, int d,
                          float eps, cudaStream_t stream);
+int launch_head_fwd(const smh_head_t &hd, cudaStream_t stream);
+int launch_head_bwd(const smh_head_t &hd, const smh_head_bwd_t &bw, cudaStream_t stream);
 int launch_selftest(int which, uint64_t *out, int64_t out_words, cudaStream_t stream);
 
 }  // namespace smh

@@ -22,12 +22,13 @@ struct DistCtx {
     uint32_t epoch;
     const Stats *gs;          // scalars the kernel reads (distance bound, domain flags)
 };
+template <bool FUSED>
 __device__ __forceinline__ DistCtx dist_head(Stats *stats, const Peers &peers)
 {
     DistCtx c;
     c.epoch = 0u;
     c.gs = stats;
-    if (peers.fused) {
+    if (FUSED) {
         c.epoch = peers.my_sig()[kSigEpoch];
         stage_wait(peers, 1, c.epoch);
         c.gs = peers.gstats(peers.rank, c.epoch);
@@ -182,7 +183,7 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
 // HALF = false: one CTA per stored tile (thread = row x 64 columns).  HALF = true: one CTA per 64-column half of a
 // stored tile (thread = row x 32 columns) -- twice as many, half as long CTAs, used when a rank has few tiles (sharded
 // runs) so that the last wave of the 2-CTAs-per-SM grid is not mostly empty (1032 tiles = 3.5 waves -> 7.0 waves).
-template <bool HALF, bool Q16>
+template <bool HALF, bool Q16, bool FUSED>
 __global__ void __launch_bounds__(256, Q16 ? 3 : 2)
 mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m,
              Stats *__restrict__ stats, Peers peers, int signal2)
@@ -196,7 +197,7 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
     const int col0 = cs0 + (threadIdx.x >> 7) * kPerThread;
     const int2 ij = tiles[tile_id];
     void *tile_out = reinterpret_cast<unsigned char *>(dist) + (int64_t)tile_id * kTileFloats * (Q16 ? 2 : 4);
-    const DistCtx dc = dist_head(stats, peers);
+    const DistCtx dc = dist_head<FUSED>(stats, peers);
     const float qscale = Q16 ? q16_scale(__uint_as_float(dc.gs->dbound_bits)) * (1.0f / 21.0f) : 0.f;    // applied to the sum
     {
         const float4 *src = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.y * kTile + cs0) * kJP);
@@ -255,7 +256,7 @@ altdist_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, flo
 {
     __shared__ __align__(16) float cs[kTile * kJP];
     __shared__ uint32_t wmax[8];
-    const DistCtx dc = dist_head(stats, peers);
+    const DistCtx dc = peers.fused ? dist_head<true>(stats, peers) : dist_head<false>(stats, peers);
     const int2 ij = tiles[blockIdx.x];
     float *tile_out = dist + (int64_t)blockIdx.x * kTileFloats;
     {
@@ -410,15 +411,21 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
             altdist_kernel<0><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
     } else if (lay.n_stored_tiles < 8 * 2 * kNumCtas) {
         // fewer than ~8 waves of whole tiles (2 CTAs x 148 SMs per wave): cut the tiles in halves
-        if (dims.flags & SMH_DIMS_Q16_TILES)
-            mpjpe_kernel<true, true><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
-        else
-            mpjpe_kernel<true, false><<<2 * lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
+#define SMH_MPJPE(H, Q, G) mpjpe_kernel<H, Q, true><<<G, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2)
+#define SMH_MPJPE_LOCAL(H, Q, G) mpjpe_kernel<H, Q, false><<<G, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2)
+        if (dims.flags & SMH_DIMS_Q16_TILES) {
+            if (peers.fused) SMH_MPJPE(true, true, 2 * lay.n_stored_tiles); else SMH_MPJPE_LOCAL(true, true, 2 * lay.n_stored_tiles);
+        } else {
+            if (peers.fused) SMH_MPJPE(true, false, 2 * lay.n_stored_tiles); else SMH_MPJPE_LOCAL(true, false, 2 * lay.n_stored_tiles);
+        }
     } else {
-        if (dims.flags & SMH_DIMS_Q16_TILES)
-            mpjpe_kernel<false, true><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
-        else
-            mpjpe_kernel<false, false><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
+        if (dims.flags & SMH_DIMS_Q16_TILES) {
+            if (peers.fused) SMH_MPJPE(false, true, lay.n_stored_tiles); else SMH_MPJPE_LOCAL(false, true, lay.n_stored_tiles);
+        } else {
+            if (peers.fused) SMH_MPJPE(false, false, lay.n_stored_tiles); else SMH_MPJPE_LOCAL(false, false, lay.n_stored_tiles);
+        }
+#undef SMH_MPJPE
+#undef SMH_MPJPE_LOCAL
     }
     int rc = check_launch(dims.diff_type != SMH_DIFF_MPJPE ? "altdist_kernel" : "mpjpe_kernel");
     if (rc || !nonlinear) return rc;

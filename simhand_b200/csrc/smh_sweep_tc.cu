@@ -238,7 +238,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
 // BWD: backward sweep (always reads the bf16 image).  SBF16: logits from a 16-bit image `zb` (bf16, or fp16 in the
 // forward sweep of the fp16 engine: the caller passes that image and the matching instruction descriptor idesc1),
 // else from the tf32 image `zt`.
-template <bool BWD, bool SBF16, bool Q16>
+// FUSED: the exchange of the sharded step rides in this kernel's head and tail (smh_shard.cu); a separate instantiation, so
+// the single-GPU kernel carries none of it.
+template <bool BWD, bool SBF16, bool Q16, bool FUSED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const void *__restrict__ dist,
@@ -300,7 +302,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     // already waited for the row sums.  gs: the step's combined scalars.
     uint32_t epoch = 0u;
     const Stats *gs = stats;
-    if (xp.fused) {
+    if (FUSED) {
         epoch = xp.my_sig()[kSigEpoch];
         if (!BWD) stage_wait(xp, 2, epoch);
         gs = xp.gstats(xp.rank, epoch);
@@ -508,7 +510,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         if (sigmoid) {
             // exponent of the sigmoid in base 2: lambda log2(e) (D - mean D), mean over all M^2 ordered pairs
             double dsum = stats->dsum;
-            if (xp.fused) {                  // rank-ordered sum of the parts every rank delivered with stage 2
+            if (FUSED) {                     // rank-ordered sum of the parts every rank delivered with stage 2
                 const double *parts = reinterpret_cast<const double *>(xp.lossparts(xp.rank) + 16);
                 dsum = 0.0;
                 for (int p = 0; p < xp.world; ++p) dsum += __ldcg(parts + p);
@@ -634,10 +636,10 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     }
 
     tc_fence_before();
-    if (xp.fused) __threadfence();               // this thread's row-sum / gradient reductions precede the grid barrier
+    if (FUSED) __threadfence();                  // this thread's row-sum / gradient reductions precede the grid barrier
     __syncthreads();
     if (warp == 2) tc_dealloc(tmem_base, kTmemCols);
-    if (xp.fused) {
+    if (FUSED) {
         // Tail of the fused exchange: once every CTA of the rank has flushed, the CTAs ship the rank's partial results --
         // forward: all-gather of the partial row sums into slot `rank` of every rank's negparts; backward: reduce-scatter
         // payload, rows [p * 2 n_local, (p + 1) * 2 n_local) of the gradient accumulator into slot `rank` of rank p's
@@ -673,7 +675,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     }
 }
 
-template <bool BWD, bool SBF16, bool Q16>
+template <bool BWD, bool SBF16, bool Q16, bool FUSED>
 static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, const smh_dims_t &dims,
                       const smh_layout_t &lay, const PlanView &plan, const WsView &ws, const Peers &peers,
                       const Peers &xp, float temperature, cudaStream_t stream)
@@ -687,9 +689,9 @@ static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, co
     const float inv_k2 = (float)(0.6931471805599453 * (double)temperature);
     const int n_local = dims.n / dims.world;
     constexpr int smem = TcCfg<SBF16, Q16>::kSmem;
-    cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16, Q16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16, Q16, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-    sweep_tc_kernel<BWD, SBF16, Q16><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
+    sweep_tc_kernel<BWD, SBF16, Q16, FUSED><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
                                                                    ws.dist, ws.rn, peers, xp, (Stats *)ws.stats, lay.m,
                                                                    dims.n, n_local, k2, inv_k2, wmode, dims.lambda_neg, idesc1,
                                                                         reinterpret_cast<long long *>(ws.rowloss));
@@ -706,8 +708,10 @@ int launch_sweep_tc(bool backward, int logit_format, int wmode, const smh_dims_t
     const bool q16 = dims.flags & SMH_DIMS_Q16_TILES;
     if (q16 && wmode != 0) return set_error(SMH_E_MODE, "SMH_DIMS_Q16_TILES: linear weights from the joints only");
 #define SMH_SWEEP(B, S, IMG, ID)                                                                                      \
-    (q16 ? launch_one<B, S, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)                \
-         : launch_one<B, S, false>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream))
+    (xp.fused ? (q16 ? launch_one<B, S, true, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)      \
+                     : launch_one<B, S, false, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream))    \
+              : (q16 ? launch_one<B, S, true, false>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)     \
+                     : launch_one<B, S, false, false>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)))
     if (backward) return SMH_SWEEP(true, true, ws.zb, id_bf16);
     if (logit_format == 1) return SMH_SWEEP(false, true, ws.zb, id_bf16);
     if (logit_format == 2) return SMH_SWEEP(false, true, ws.zh, id_f16);

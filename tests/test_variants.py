@@ -79,7 +79,9 @@ def test_materialised_variant_weights(name):
     a, b = _joints(g, cfg, dev)
     hp, hn = _handles(ops, a, b, cfg)
     atol = 4e-6 if "pca" in name else W_ATOL            # PCA coordinates are O(100): fp32 sum of 14 squares
-    assert np.abs(hp.materialize().cpu().numpy() - g["pos_w"]).max() <= atol
+    # the sigmoid amplifies the fp32 rounding of a distance of O(300) (ulp 3e-5) by lambda / 4
+    atol_pos = atol + (1e-5 * abs(cfg["lambda_pos"]) if "pca" in name else 0.0)
+    assert np.abs(hp.materialize().cpu().numpy() - g["pos_w"]).max() <= atol_pos
     _check_neg_w(hn.materialize().cpu().numpy(), g, atol)
 
 
