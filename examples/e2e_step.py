@@ -11,8 +11,12 @@ simhand_w_model.py:122-152) rebuilt as one process per GPU:
 
 The reference's DataParallel computes 8 independent local losses; here the loss is the reference
 function applied to the concatenated global batch.  The loss returned by the op is identical on every rank and its
-autograd hands each rank d(loss)/d(z_local), so the DDP average of the parameter gradients is 1/world of the true
-gradient: the harness scales the loss by `world` before backward.
+autograd hands each rank d(loss)/d(z_local), so the DDP average of the parameter gradients would be 1/world of the true
+gradient: the op is called with `grad_scale=world`.
+
+`--fused-head` swaps the head for simhand_b200.FusedProjectionHead (tcgen05 GEMMs with BatchNorm / ReLU / L2-normalise
+fused; same parameters).  `--dump FILE` saves the first step's projections, joints, loss and d loss / d projections of every
+rank (tests/test_gpu_e2e.py holds them against the CPU oracle).
 
 Synthetic images and joints, random-init weights (no network in this environment).  Prints one line per rank-0 with the
 step time and the share of the loss (transform + loss forward/backward) in it.
@@ -34,12 +38,14 @@ import simhand_b200  # noqa: E402
 from simhand_b200 import synth  # noqa: E402
 
 
-def build_model(out_dim: int = 128):
+def build_model(out_dim: int = 128, fused_head: bool = False):
     import torchvision
     backbone = torchvision.models.resnet50(weights=None)
     backbone.fc = nn.Identity()
     head = nn.Sequential(nn.Linear(2048, 512, bias=True), nn.BatchNorm1d(512), nn.ReLU(),
                          nn.Linear(512, out_dim, bias=False))          # simclr_model.py:22-39
+    if fused_head:
+        head = simhand_b200.FusedProjectionHead(head, act_dtype=torch.bfloat16)
     return nn.Sequential(backbone, head)
 
 
@@ -49,6 +55,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--image", type=int, default=128)
+    ap.add_argument("--fused-head", action="store_true")
+    ap.add_argument("--dump", default=None, help="save the first step's loss inputs / outputs of every rank to FILE.rank")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -60,7 +68,7 @@ def main():
         group = dist.group.WORLD
     b = args.batch // world
     torch.manual_seed(1234 + rank)
-    model = build_model().to(dev).to(memory_format=torch.channels_last)
+    model = build_model(fused_head=args.fused_head).to(dev).to(memory_format=torch.channels_last)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev.index])
     opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-6)
@@ -72,23 +80,28 @@ def main():
     jitter = (torch.randint(0, 16, (2, 2 * b), generator=gen).float() / args.image).to(dev)
     angles = torch.randint(-45, 46, (2 * b,), generator=gen).float().to(dev)
 
-    def step(timers=None):
+    def step(timers=None, dump=None):
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             proj = model(images)                                        # [2b, 128]
         if timers:
             timers[0].record()
         p = simhand_b200.get_transformed_projections(proj.float(), -jitter[0], -jitter[1], -angles)
-        loss = simhand_b200.weighted_ntxent(p[:b], p[b:], joints1, joints2, 0.5, group)
+        if dump:
+            p.retain_grad()
+        loss = simhand_b200.weighted_ntxent(p[:b], p[b:], joints1, joints2, 0.5, group, grad_scale=float(world))
         if timers:
             timers[1].record()
-        (loss * world).backward()
+        loss.backward()
+        if dump:
+            torch.save(dict(p=p.detach().cpu(), dp=p.grad.cpu(), joints1=joints1.cpu(), joints2=joints2.cpu(),
+                            loss=float(loss), world=world, rank=rank), f"{dump}.{rank}")
         opt.step()
         return loss.detach()
 
     losses = []
-    for _ in range(args.warmup):
-        losses.append(float(step()))
+    for it in range(args.warmup):
+        losses.append(float(step(dump=args.dump if it == 0 else None)))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     torch.cuda.synchronize(dev)
     if world > 1:

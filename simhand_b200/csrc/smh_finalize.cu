@@ -50,7 +50,7 @@ finalize_kernel(smh_inputs_t in, int n, int d, int rank, const float *__restrict
                 const float *__restrict__ dzacc_src, int64_t src_row_offset, int n_parts, int64_t part_stride,
                 int pos_mode, float lambda_pos, float inv_tau, float grad_scale,
                 float *__restrict__ loss_out, float *__restrict__ dz1, float *__restrict__ dz2,
-                int64_t dz_row_stride, int phase, Peers peers)
+                int64_t dz_row_stride, int phase, const __grid_constant__ Peers peers)
 {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;

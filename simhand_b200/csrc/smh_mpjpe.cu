@@ -186,7 +186,7 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
 template <bool HALF, bool Q16, bool FUSED>
 __global__ void __launch_bounds__(256, Q16 ? 3 : 2)
 mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m,
-             Stats *__restrict__ stats, Peers peers, int signal2)
+             Stats *__restrict__ stats, const __grid_constant__ Peers peers, int signal2)
 {
     constexpr int kCols = HALF ? 64 : 128;            // columns staged per CTA
     constexpr int kPerThread = kCols / 2;
@@ -252,7 +252,7 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
 template <int MODE>
 __global__ void __launch_bounds__(256, 2)
 altdist_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, float *__restrict__ dist, int m,
-               Stats *__restrict__ stats, Peers peers, int signal2)
+               Stats *__restrict__ stats, const __grid_constant__ Peers peers, int signal2)
 {
     __shared__ __align__(16) float cs[kTile * kJP];
     __shared__ uint32_t wmax[8];
@@ -337,7 +337,7 @@ altdist_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, flo
 // consumers add the parts in rank order) and signals stage 2.
 __global__ void __launch_bounds__(256)
 tile_sum_kernel(const int2 *__restrict__ tiles, const float *__restrict__ dist, int m, Stats *__restrict__ stats,
-                Peers peers)
+                const __grid_constant__ Peers peers)
 {
     __shared__ double part[8];
     const int2 ij = tiles[blockIdx.x];
@@ -379,7 +379,7 @@ tile_sum_kernel(const int2 *__restrict__ tiles, const float *__restrict__ dist, 
 }
 
 // a rank with nothing to do in a stage: wait for the previous stage, signal this one
-__global__ void stage_relay_kernel(Peers pe, int wait_stage, int stage)
+__global__ void stage_relay_kernel(const __grid_constant__ Peers pe, int wait_stage, int stage)
 {
     const uint32_t epoch = pe.my_sig()[kSigEpoch];
     if (wait_stage > 0) stage_wait(pe, wait_stage, epoch);

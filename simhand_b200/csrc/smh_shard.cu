@@ -33,7 +33,7 @@ struct ShardPrepArgs {
     long long zero_off, zero_bytes;   // local accumulators: [off_neg, off_posd)
 };
 
-__global__ void __launch_bounds__(256) shard_prep_kernel(ShardPrepArgs a, Peers pe)
+__global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__ ShardPrepArgs a, const __grid_constant__ Peers pe)
 {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
@@ -222,13 +222,14 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(ShardPrepArgs a, Peers 
         if (d0 >= 0.f && d0 <= 3.0e38f) bound_bits = max(bound_bits, __float_as_uint(d0));
     }
     if (lane == 0) wb[threadIdx.x >> 5] = bound_bits;
-    __threadfence_system();                      // this thread's stores into the peers precede the ticket below
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t b = wb[0];
         for (int w = 1; w < wpb; ++w) b = max(b, wb[w]);
         if (b != 0u) atomicMax_system(&gs->dbound_bits, b);
-        __threadfence();
+        // one system-scope fence per block, after the block barrier: it orders every thread's stores into the peers
+        // (observed through the barrier) before the ticket -- a fence in each of the 65 k threads cost 20-30 us
+        __threadfence_system();
         const unsigned ticket = atomicAdd(&st->counter, 1u);
         if (ticket == gridDim.x - 1) {
             st->counter = 0u;
@@ -277,7 +278,7 @@ int launch_shard_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh
 // neg_i = rank-ordered sum of the partial row sums every rank delivered; 1 / neg_i for the backward sweep.
 // signal4: loss-only step (no backward sweep follows): this launch closes stage 4.
 __global__ void __launch_bounds__(256)
-rn_fused_kernel(Peers pe, float *__restrict__ neg, const float *__restrict__ negparts, float *__restrict__ rn, int m,
+rn_fused_kernel(const __grid_constant__ Peers pe, float *__restrict__ neg, const float *__restrict__ negparts, float *__restrict__ rn, int m,
                 int mp, int signal4)
 {
     uint32_t *sig = pe.my_sig();
@@ -321,7 +322,7 @@ __device__ __forceinline__ double fused_dsum(const Peers &pe)
 
 // Gradients of the own rows and the loss of the global batch.  `in` describes this rank's tensors.
 __global__ void __launch_bounds__(256)
-finalize_fused_kernel(smh_inputs_t in, int n, int d, Peers pe, const float *__restrict__ neg, float *__restrict__ rowloss,
+finalize_fused_kernel(smh_inputs_t in, int n, int d, const __grid_constant__ Peers pe, const float *__restrict__ neg, float *__restrict__ rowloss,
                       const float *__restrict__ dzparts, int pos_mode, float lambda_pos, float inv_tau, float grad_scale,
                       float *__restrict__ loss_out, float *__restrict__ dz1, float *__restrict__ dz2,
                       int64_t dz_row_stride)

@@ -21,7 +21,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(256, 1)
 sweep_fp32_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                   const float *__restrict__ zt, const float *__restrict__ dist, const float *__restrict__ rn,
-                  Peers peers, const Stats *__restrict__ stats, int m, int n, int n_local, float k2, int wmode, float lambda_neg)
+                  const __grid_constant__ Peers peers, const Stats *__restrict__ stats, int m, int n, int n_local, float k2, int wmode, float lambda_neg)
 {
     extern __shared__ __align__(16) float smem[];
     float *As = smem;                         // [128][129]  row block of z

@@ -244,7 +244,7 @@ template <bool BWD, bool SBF16, bool Q16, bool FUSED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const void *__restrict__ dist,
-                const float *__restrict__ rn, Peers peers, Peers xp, Stats *__restrict__ stats, int m, int n, int n_local,
+                const float *__restrict__ rn, const __grid_constant__ Peers peers, const __grid_constant__ Peers xp, Stats *__restrict__ stats, int m, int n, int n_local,
                 float k2, float inv_k2, int wmode, float lambda_neg, uint32_t idesc1, long long *trace)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
@@ -636,7 +636,6 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     }
 
     tc_fence_before();
-    if (FUSED) __threadfence();                  // this thread's row-sum / gradient reductions precede the grid barrier
     __syncthreads();
     if (warp == 2) tc_dealloc(tmem_base, kTmemCols);
     if (FUSED) {
@@ -663,9 +662,9 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 reinterpret_cast<float4 *>(xp.dzparts(p))[(int64_t)xp.rank * block4 + (i - (int64_t)p * block4)] = __ldcg(src + i);
             }
         }
-        __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();              // after the CTA barrier: orders every thread's peer stores before the ticket
             const uint32_t ticket = atomicAdd(sig + kSigTicket, 1u);
             if (ticket == gridDim.x - 1) {
                 sig[kSigTicket] = 0u;

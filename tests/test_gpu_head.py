@@ -88,34 +88,70 @@ def test_eval_mode_uses_running_estimates():
     assert float(torch.nn.functional.cosine_similarity(y, want, dim=1).min()) >= 0.9995
 
 
+def _ste(t, act):
+    """round to the 16-bit activation type in the value, identity in the gradient"""
+    return t + (t.to(act).to(t.dtype) - t).detach()
+
+
 @pytest.mark.parametrize("rows,in_dim,hidden", [(4096, 2048, 512), (300, 512, 256)])
 def test_backward_matches_autograd(rows, in_dim, hidden):
-    """Gradients of a random linear functional of the normalised projections w.r.t. the encodings and every parameter,
-    against fp32 autograd of the plain composition (16-bit operand tolerance: cosine and max error relative to max|g|)."""
+    """Gradients of a random linear functional of the normalised projections w.r.t. the encodings and every parameter.
+    Tight: fp64 autograd of the composition with the SAME two activation roundings (so the ReLU masks coincide; what is left
+    is the 16-bit storage of dP / dH and of the library GEMMs' outputs).  Loose: pure fp32 autograd, where ~0.3 % of the ReLU
+    masks differ because Linear-1's output is rounded to 16 bits -- the eager autocast step the kernels replace differs from
+    fp32 by the same amount, which the test shows beside it."""
     dev = _dev()
+    act = torch.bfloat16
     seq, x = _make(rows, in_dim, hidden, 128, 7, dev)
     cot = torch.randn(rows, 128, device=dev)
-    fused = FusedProjectionHead(seq, act_dtype=torch.bfloat16).train()
+    fused = FusedProjectionHead(seq, act_dtype=act).train()
     xf = x.clone().requires_grad_(True)
     y = fused(xf)
     (y * cot).sum().backward()
     got = dict(x=xf.grad.float(), w1=seq[0].weight.grad.float(), b1=seq[0].bias.grad.float(), g=seq[1].weight.grad.float(),
                b=seq[1].bias.grad.float(), w2=seq[3].weight.grad.float())
     seq.zero_grad()
+
+    # (1) same roundings, fp64
+    lin1, bn, _, lin2 = seq[0], seq[1], seq[2], seq[3]
+    xd = x.to(act).double().requires_grad_(True)
+    w1 = lin1.weight.detach().to(act).double().requires_grad_(True)
+    w2 = lin2.weight.detach().to(act).double().requires_grad_(True)
+    b1 = lin1.bias.detach().double().requires_grad_(True)
+    gam, bet = bn.weight.detach().double().requires_grad_(True), bn.bias.detach().double().requires_grad_(True)
+    h = _ste(xd @ w1.t() + b1, act)
+    hn = (h - h.mean(0)) / torch.sqrt(h.var(0, unbiased=False) + bn.eps) * gam + bet
+    a = _ste(torch.relu(hn), act)
+    p = a @ w2.t()
+    yd = p / p.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    (yd * cot.double()).sum().backward()
+    tight = dict(x=xd.grad, w1=w1.grad, g=gam.grad, b=bet.grad, w2=w2.grad)
+
+    # (2) pure fp32, and the eager autocast composition against it
     seq32 = nn.Sequential(nn.Linear(in_dim, hidden), nn.BatchNorm1d(hidden), nn.ReLU(), nn.Linear(hidden, 128, bias=False)).to(dev)
     seq32.load_state_dict(seq.state_dict())
     seq32.train()
     xr = x.clone().requires_grad_(True)
-    yr = torch.nn.functional.normalize(seq32(xr), dim=1)
-    (yr * cot).sum().backward()
+    (torch.nn.functional.normalize(seq32(xr), dim=1) * cot).sum().backward()
     ref = dict(x=xr.grad, w1=seq32[0].weight.grad, b1=seq32[0].bias.grad, g=seq32[1].weight.grad, b=seq32[1].bias.grad,
                w2=seq32[3].weight.grad)
+    xe = x.clone().requires_grad_(True)
+    (reference_head_forward(seq, xe, act) * cot).sum().backward()
+    eager = dict(x=xe.grad.float(), w1=seq[0].weight.grad.float(), g=seq[1].weight.grad.float(), b=seq[1].bias.grad.float(),
+                 w2=seq[3].weight.grad.float())
+
+    def metrics(u, v):
+        u, v = u.flatten().double(), v.flatten().double()
+        return float(u @ v / (u.norm() * v.norm())), float((u - v).abs().max() / v.abs().max())
+
     for k in ("x", "w1", "g", "b", "w2"):
-        a, b = got[k].flatten().double(), ref[k].flatten().double()
-        cos = float(a @ b / (a.norm() * b.norm()))
-        mx = float((a - b).abs().max() / b.abs().max())
-        print(f"[head bwd rows={rows}] d{k}: cos {cos:.6f} max err {mx:.2e}")
-        assert cos >= 0.999 and mx <= 5e-2, (k, cos, mx)
+        cos_t, mx_t = metrics(got[k], tight[k])
+        cos_l, mx_l = metrics(got[k], ref[k])
+        cos_e, mx_e = metrics(eager[k], ref[k])
+        print(f"[head bwd rows={rows}] d{k}: vs same-rounding fp64 cos {cos_t:.6f} max {mx_t:.2e} | vs fp32 cos {cos_l:.6f} "
+              f"max {mx_l:.2e} (eager autocast vs fp32: cos {cos_e:.6f} max {mx_e:.2e})")
+        assert cos_t >= 0.9995 and mx_t <= 3e-2, (k, cos_t, mx_t)
+        assert cos_l >= min(0.995, cos_e - 2e-3), (k, cos_l, cos_e)
     # BatchNorm in training mode cancels the bias: the reference's own gradient is rounding noise around zero
     assert float(got["b1"].abs().max()) == 0.0
     assert float(ref["b1"].abs().max()) <= 1e-4 * float(ref["b"].abs().max()) + 1e-6
