@@ -34,7 +34,7 @@ def _newer(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False, variant: str = "", defines=()) -> str:
     """trace=True: development build with -DSMH_TRACE (per-role cycle counters in the sweeps, tools/trace_sweeps.py)
     into lib/libsimhand_b200_trace.so; the product library is never built with it."""
     global OBJDIR, LIB
@@ -42,6 +42,11 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
     if trace:
         OBJDIR, LIB = os.path.join(HERE, "build_trace"), os.path.join(LIBDIR, "libsimhand_b200_trace.so")
         flags.append("-DSMH_TRACE")
+    if variant:
+        # experiment builds (python -m simhand_b200.build --variant NAME -DFLAG ...): lib/libsimhand_b200_NAME.so, picked up
+        # through SMH_LIB; never the product library
+        OBJDIR, LIB = os.path.join(HERE, "build_" + variant), os.path.join(LIBDIR, f"libsimhand_b200_{variant}.so")
+        flags.extend(defines)
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
@@ -76,5 +81,7 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose=True, trace="--trace" in sys.argv)
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    path = build(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, trace="--trace" in sys.argv, variant=var,
+                 defines=[a for a in sys.argv if a.startswith("-D")])
     print(path)

@@ -114,7 +114,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane)
 // ----------------------------------------------------------------------------------------------
 // G1: H = X W1^T + b1, column sums of H and H^2
 // ----------------------------------------------------------------------------------------------
-constexpr int kG1Threads = 192;                  // TMA producer, MMA issuer, 4 epilogue warps
+constexpr int kG1Threads = 320;                  // TMA producer, MMA issuer, 8 epilogue warps (2 per TMEM lane quadrant)
 constexpr int kG1Stages = 3;
 constexpr int kG1StageBytes = 2 * 256 * 128;     // A box [256 rows][64] + B box [256 rows][64], 16-bit
 constexpr int kG1Smem = 1024 + kG1Stages * kG1StageBytes + 256;
@@ -186,19 +186,25 @@ head_gemm1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: 4 warps, thread = row of a 128-row half
+        // ------------------------------------------------------------------ epilogue: 8 warps, thread = row of a 128-row
+        // half; the two warps of a TMEM lane quadrant split the 256 columns of the tile
         const int w4 = warp & 3;                       // TMEM lane quadrant this warp may touch
-        const int e = warp - 2;
+        const int qi = (warp - 2) & 3;                 // slot of this warp's partial sums
+        const int chalf = (warp - 2) >> 2;             // which 128 of the 256 columns
         mbar_wait(&bars[6], 0, &fail_s, 3);
         tc_fence_after();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16);
-        for (int c = lane; c < 2 * 256; c += 32) (&part[e][0][0])[c] = 0.f;
+        for (int c = lane; c < 128; c += 32) {
+            part[qi][0][chalf * 128 + c] = 0.f;
+            part[qi][1][chalf * 128 + c] = 0.f;
+        }
         __syncwarp();
         for (int mh = 0; mh < 2; ++mh) {
             const int grow = row0 + mh * 128 + w4 * 32 + lane;
             const bool row_ok = grow < rows;
 #pragma unroll 1
-            for (int ch = 0; ch < 8; ++ch) {
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int ch = chalf * 4 + c4;
                 uint32_t v[32];
                 tc_ld32(lane_addr + mh * 256 + ch * 32, v);
                 tc_wait_ld();
@@ -223,15 +229,15 @@ head_gemm1_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 for (int i = 0; i < 32; ++i) sq[i] = hv[i] * hv[i];
                 const float s1 = warp_transpose_sum(hv, lane);
                 const float s2 = warp_transpose_sum(sq, lane);
-                part[e][0][ch * 32 + lane] += s1;
-                part[e][1][ch * 32 + lane] += s2;
+                part[qi][0][ch * 32 + lane] += s1;
+                part[qi][1][ch * 32 + lane] += s2;
             }
         }
         tc_fence_before();
-        // combine the four warps, one atomic per column and statistic
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // combine the four row quadrants, one atomic per column and statistic
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int t = threadIdx.x - 64;
-        for (int c = t; c < 2 * 256; c += 128) {
+        for (int c = t; c < 2 * 256; c += 256) {
             const int st = c >> 8, col = c & 255;
             const float tot = part[0][st][col] + part[1][st][col] + part[2][st][col] + part[3][st][col];
             atomicAdd(colsum + (int64_t)st * hidden + col0 + col, tot);

@@ -36,12 +36,19 @@ __device__ __forceinline__ DistCtx dist_head(Stats *stats, const Peers &peers)
     return c;
 }
 // thread 0 of every CTA, after the CTA's maximum went into stats->dmax_bits / stats->flags (rank-local)
-__device__ __forceinline__ void dist_tail(Stats *stats, const Peers &peers, const DistCtx &c, bool signal2)
+// persistent: the kernel pulls its work from stats->reserved, which the last CTA resets for the next launch
+__device__ __forceinline__ void dist_tail(Stats *stats, const Peers &peers, const DistCtx &c, bool signal2,
+                                          bool persistent = false)
 {
-    if (peers.world <= 1) return;
+    if (peers.world <= 1 && !persistent) return;
     __threadfence();
     const unsigned ticket = atomicAdd(&stats->ticket2, 1u);
     if (ticket != gridDim.x - 1) return;
+    if (persistent) stats->reserved = 0u;
+    if (peers.world <= 1) {
+        stats->ticket2 = 0u;
+        return;
+    }
     const uint32_t mine = atomicMax(&stats->dmax_bits, 0u);
     if (peers.fused) {
         const uint32_t fl = atomicOr(&stats->flags, 0u);
@@ -180,40 +187,26 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
     }
 }
 
-// HALF = false: one CTA per stored tile (thread = row x 64 columns).  HALF = true: one CTA per 64-column half of a
-// stored tile (thread = row x 32 columns) -- twice as many, half as long CTAs, used when a rank has few tiles (sharded
-// runs) so that the last wave of the 2-CTAs-per-SM grid is not mostly empty (1032 tiles = 3.5 waves -> 7.0 waves).
-template <bool HALF, bool Q16, bool FUSED>
+// Persistent CTAs (one resident set: 3 per SM for the 16-bit image, 2 for the exact form) pull work items from an atomic
+// counter, so the grid has no wave quantisation and no mostly-empty last wave (a rank's 1032 tiles at 8 GPUs used to be
+// 4.65 waves of half-tile CTAs).  An item is one 128 / PARTS-column part of a stored tile: thread = row x (64 / PARTS)
+// columns.  PARTS = 2 when the rank has many tiles, 4 when it has few (sharded runs): the tail of the kernel is at most one
+// item long.  The rank's last CTA resets the counter (and, with a peer exchange, ships Dmax: dist_tail).
+template <int PARTS, bool Q16, bool FUSED>
 __global__ void __launch_bounds__(256, Q16 ? 3 : 2)
-mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m,
+mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m, int n_tiles,
              Stats *__restrict__ stats, const __grid_constant__ Peers peers, int signal2)
 {
-    constexpr int kCols = HALF ? 64 : 128;            // columns staged per CTA
+    constexpr int kCols = kTile / PARTS;              // columns staged per item
     constexpr int kPerThread = kCols / 2;
     __shared__ __align__(16) float cs[kCols * kJP];
     __shared__ uint32_t wmax[8];
-    const int tile_id = HALF ? (blockIdx.x >> 1) : blockIdx.x;
-    const int cs0 = HALF ? (blockIdx.x & 1) * 64 : 0;
-    const int col0 = cs0 + (threadIdx.x >> 7) * kPerThread;
-    const int2 ij = tiles[tile_id];
-    void *tile_out = reinterpret_cast<unsigned char *>(dist) + (int64_t)tile_id * kTileFloats * (Q16 ? 2 : 4);
+    __shared__ int item_s;
     const DistCtx dc = dist_head<FUSED>(stats, peers);
     const float qscale = Q16 ? q16_scale(__uint_as_float(dc.gs->dbound_bits)) * (1.0f / 21.0f) : 0.f;    // applied to the sum
-    {
-        const float4 *src = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.y * kTile + cs0) * kJP);
-        float4 *dst = reinterpret_cast<float4 *>(cs);
-        for (int i = threadIdx.x; i < kCols * kJP / 4; i += 256) dst[i] = src[i];
-    }
-    __syncthreads();
     const uint32_t flags = dc.gs->flags;
     const bool slow = flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE);
-    uint32_t vmax_bits = 0u;
-    if (slow)
-        mpjpe_tile_body<0, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
-    else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
-        mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);   // zero distances
-    else
-        mpjpe_tile_body<2, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+    const int n_items = n_tiles * PARTS;
     auto block_max = [&](uint32_t v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -225,20 +218,53 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
         for (int w = 1; w < 8; ++w) v = max(v, wmax[w]);
         return v;
     };
-    uint32_t bmax = block_max(vmax_bits);
-    if (!slow && bmax > 0x7f800000u) {
-        // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo it guarded
-        vmax_bits = 0u;
-        mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
-        bmax = block_max(vmax_bits);
+    __shared__ uint32_t cta_max_s, cta_bad_s;         // thread 0: maximum / non-finite flag over this CTA's items
+    if (threadIdx.x == 0) cta_max_s = cta_bad_s = 0u;
+    for (;;) {
+        __syncthreads();                              // the previous item's reads of cs / wmax / item_s are done
+        if (threadIdx.x == 0) item_s = (int)atomicAdd(&stats->reserved, 1u);
+        __syncthreads();
+        const int item = item_s;
+        if (item >= n_items) break;
+        const int tile_id = item / PARTS;
+        const int cs0 = (item % PARTS) * kCols;
+        const int col0 = cs0 + (threadIdx.x >> 7) * kPerThread;
+        const int2 ij = tiles[tile_id];
+        void *tile_out = reinterpret_cast<unsigned char *>(dist) + (int64_t)tile_id * kTileFloats * (Q16 ? 2 : 4);
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.y * kTile + cs0) * kJP);
+            float4 *dst = reinterpret_cast<float4 *>(cs);
+            for (int i = threadIdx.x; i < kCols * kJP / 4; i += 256) dst[i] = src[i];
+        }
+        __syncthreads();
+        uint32_t vmax_bits = 0u;
+        if (slow)
+            mpjpe_tile_body<0, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+        else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
+            mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);   // zero distances
+        else
+            mpjpe_tile_body<2, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+        uint32_t bmax = block_max(vmax_bits);
+        if (!slow && bmax > 0x7f800000u) {
+            // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo it guarded
+            vmax_bits = 0u;
+            mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+            bmax = block_max(vmax_bits);
+        }
+        if (threadIdx.x == 0) {
+            if (bmax > 0x7f800000u)
+                cta_bad_s = 1u;                       // non-finite inputs (IEEE path): the loss is NaN
+            else
+                cta_max_s = max(cta_max_s, bmax);
+        }
     }
     if (threadIdx.x == 0) {
-        if (bmax > 0x7f800000u)
-            atomicOr(&stats->flags, SMH_FLAG_NONFINITE);      // non-finite inputs (IEEE path): the loss is NaN
-        else
-            atomicMax(&stats->dmax_bits, Q16 ? __float_as_uint(__fdiv_rn(__uint_as_float(bmax), 21.0f)) : bmax);
-        // fused all-reduce(MAX): the last CTA of this rank pushes the rank's maximum into every peer's stats
-        dist_tail(stats, peers, dc, signal2 != 0);
+        const uint32_t cta_max = cta_max_s;
+        if (cta_bad_s) atomicOr(&stats->flags, SMH_FLAG_NONFINITE);
+        if (cta_max != 0u)
+            atomicMax(&stats->dmax_bits, Q16 ? __float_as_uint(__fdiv_rn(__uint_as_float(cta_max), 21.0f)) : cta_max);
+        // last CTA: resets the work counter; fused all-reduce(MAX): pushes the rank's maximum into every peer's stats
+        dist_tail(stats, peers, dc, signal2 != 0, true);
     }
 }
 
@@ -409,23 +435,22 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
             altdist_kernel<2><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
         else
             altdist_kernel<0><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
-    } else if (lay.n_stored_tiles < 8 * 2 * kNumCtas) {
-        // fewer than ~8 waves of whole tiles (2 CTAs x 148 SMs per wave): cut the tiles in halves
-#define SMH_MPJPE(H, Q, G) mpjpe_kernel<H, Q, true><<<G, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2)
-#define SMH_MPJPE_LOCAL(H, Q, G) mpjpe_kernel<H, Q, false><<<G, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2)
-        if (dims.flags & SMH_DIMS_Q16_TILES) {
-            if (peers.fused) SMH_MPJPE(true, true, 2 * lay.n_stored_tiles); else SMH_MPJPE_LOCAL(true, true, 2 * lay.n_stored_tiles);
-        } else {
-            if (peers.fused) SMH_MPJPE(true, false, 2 * lay.n_stored_tiles); else SMH_MPJPE_LOCAL(true, false, 2 * lay.n_stored_tiles);
-        }
     } else {
-        if (dims.flags & SMH_DIMS_Q16_TILES) {
-            if (peers.fused) SMH_MPJPE(false, true, lay.n_stored_tiles); else SMH_MPJPE_LOCAL(false, true, lay.n_stored_tiles);
+        // few tiles (sharded runs): quarter-tile items, else half-tile items; one resident set of persistent CTAs
+        const bool q16 = dims.flags & SMH_DIMS_Q16_TILES;
+        const bool small = lay.n_stored_tiles < 8 * 2 * kNumCtas;
+        const int resident = kNumCtas * (q16 ? 3 : 2);
+        const int items = lay.n_stored_tiles * (small ? 4 : 2);
+        const int grid = items < resident ? items : resident;
+#define SMH_MPJPE(P, Q, F) mpjpe_kernel<P, Q, F><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, lay.n_stored_tiles, st, peers, signal2)
+        if (small) {
+            if (q16) { if (peers.fused) SMH_MPJPE(4, true, true); else SMH_MPJPE(4, true, false); }
+            else     { if (peers.fused) SMH_MPJPE(4, false, true); else SMH_MPJPE(4, false, false); }
         } else {
-            if (peers.fused) SMH_MPJPE(false, false, lay.n_stored_tiles); else SMH_MPJPE_LOCAL(false, false, lay.n_stored_tiles);
+            if (q16) { if (peers.fused) SMH_MPJPE(2, true, true); else SMH_MPJPE(2, true, false); }
+            else     { if (peers.fused) SMH_MPJPE(2, false, true); else SMH_MPJPE(2, false, false); }
         }
 #undef SMH_MPJPE
-#undef SMH_MPJPE_LOCAL
     }
     int rc = check_launch(dims.diff_type != SMH_DIFF_MPJPE ? "altdist_kernel" : "mpjpe_kernel");
     if (rc || !nonlinear) return rc;

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
     Stats *gs = pe.gstats(pe.rank, epoch);
     Stats *st = pe.stats(pe.rank);
     const smh_inputs_t &in = a.in;
+    PhaseClock clk(pe, 0);
 
     if (blockIdx.x == 0) {
         // rank 0 publishes the joints of global sample 0 first: every rank bounds its rows against them
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
             st->flags = 0u;
             st->fail_site = 0u;
             st->dsum = 0.0;
+            st->reserved = 0u;                             // work counter of the persistent MPJPE kernel
         }
         __syncthreads();
         if (pe.rank == 0 && threadIdx.x == 0) {
@@ -204,8 +206,10 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
     // D(row, global sample 0): by the triangle inequality 2 max_i D_i0 bounds every D_ij (scale of the 16-bit image)
     __shared__ float pivot[42];
     __shared__ uint32_t wb[8];
+    clk.lap();                                   // [0] zeroing + images + positives issued
     if (threadIdx.x == 0) wait_word(pe, sig + kSigPivotFlag, epoch, 120u);
     __syncthreads();
+    clk.lap();                                   // [1] pivot arrived
     if (threadIdx.x < 42) pivot[threadIdx.x] = __uint_as_float(__ldcg(sig + kSigPivot + threadIdx.x));
     __syncthreads();
     uint32_t bound_bits = 0u;
@@ -227,9 +231,11 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
         uint32_t b = wb[0];
         for (int w = 1; w < wpb; ++w) b = max(b, wb[w]);
         if (b != 0u) atomicMax_system(&gs->dbound_bits, b);
-        // one system-scope fence per block, after the block barrier: it orders every thread's stores into the peers
-        // (observed through the barrier) before the ticket -- a fence in each of the 65 k threads cost 20-30 us
-        __threadfence_system();
+        // one fence per block, after the block barrier: it orders every thread's stores into the peers (observed
+        // through the barrier) before the ticket -- a fence in each of the 65 k threads cost 20-30 us
+        clk.lap();                               // [2] bound rows done
+        block_release_fence();
+        clk.lap();                               // [3] fence
         const unsigned ticket = atomicAdd(&st->counter, 1u);
         if (ticket == gridDim.x - 1) {
             st->counter = 0u;
@@ -247,7 +253,9 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
             }
             sig[kSigEpoch] = epoch;
             stage_signal(pe, 1, epoch);
+            sig[kSigClock + 15] = (uint32_t)(global_ns() & 0xffffffffu);       // when the rank's stage 1 went out
         }
+        clk.lap();                               // [4] block 0 done
     }
 }
 

@@ -302,10 +302,13 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     // already waited for the row sums.  gs: the step's combined scalars.
     uint32_t epoch = 0u;
     const Stats *gs = stats;
+    PhaseClock clk(FUSED ? xp : peers, BWD ? 4 : 2);
+    if (!FUSED) clk.dst = nullptr;
     if (FUSED) {
         epoch = xp.my_sig()[kSigEpoch];
         if (!BWD) stage_wait(xp, 2, epoch);
         gs = xp.gstats(xp.rank, epoch);
+        clk.lap();                               // [0] stage wait
     }
 
     if (warp == 0) {
@@ -644,8 +647,10 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         // payload, rows [p * 2 n_local, (p + 1) * 2 n_local) of the gradient accumulator into slot `rank` of rank p's
         // dzparts -- with plain 16-byte stores over NVLink; the rank's last CTA signals the stage.
         uint32_t *sig = xp.my_sig();
+        clk.lap();                               // [1] this CTA's share of the sweep
         if (threadIdx.x == 0) grid_barrier(xp, epoch * 8u + (BWD ? 2u : 1u));
         __syncthreads();
+        clk.lap();                               // [2] every CTA of the rank has flushed
         if (!BWD) {
             const int mp4 = ((m + kTile - 1) / kTile) * kTile / 4;
             const float4 *src = reinterpret_cast<const float4 *>(xp.neg(xp.rank));
@@ -663,8 +668,10 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             }
         }
         __syncthreads();
+        clk.lap();                               // [3] payload stores issued
         if (threadIdx.x == 0) {
-            __threadfence_system();              // after the CTA barrier: orders every thread's peer stores before the ticket
+            block_release_fence();               // after the CTA barrier: orders every thread's peer stores before the ticket
+            clk.lap();                           // [4] fence
             const uint32_t ticket = atomicAdd(sig + kSigTicket, 1u);
             if (ticket == gridDim.x - 1) {
                 sig[kSigTicket] = 0u;
