@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -14,6 +15,7 @@
 namespace smh {
 
 static thread_local char g_err[512] = "";
+constexpr double kStripCost = 4.0;        // cost of opening a strip, in sweep-task times (enumerate_plan)
 
 int set_error(int code, const char *fmt, ...)
 {
@@ -141,13 +143,41 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
         };
         std::sort(tasks.begin(), tasks.end(), [&](const int4 &x, const int4 &y) { return key(x) < key(y); });
     }
+    // The CTAs take contiguous ranges of the ordered list, cut for equal COST: a task costs 1, every strip a CTA opens
+    // (a run of tasks with the same row block; a cut opens one too) costs kStripCost task-times -- the strip's flush of the
+    // row sums / gradient rows and the pipeline drain in front of it.  With ~28 tasks per CTA (8 ranks) a strip more or
+    // less is 10 % of a CTA's time: equal task counts left the slowest CTA 15-20 % behind the first
+    // (profiles/r02_phase_clocks_n2.txt).  SMH_STRIP_COST overrides the weight for experiments.
+    double strip_cost = kStripCost;
+    if (const char *e = getenv("SMH_STRIP_COST")) strip_cost = atof(e);
     const int n_ctas = (int)std::min<size_t>(kNumCtas, std::max<size_t>(tasks.size(), 1));
     std::vector<int2> strips;
     std::vector<int> cta_ptr(kNumCtas + 1, 0);
+    auto opens_strip = [&](size_t j, size_t first) {          // does task j open a new strip in a range starting at `first`?
+        return j == first || tasks[j].x != tasks[j - 1].x;
+    };
+    double remaining = 0.0;
+    for (size_t j = 0; j < tasks.size(); ++j) remaining += 1.0 + (opens_strip(j, 0) ? strip_cost : 0.0);
+    size_t lo = 0;
     for (int c = 0; c < kNumCtas; ++c) {
         cta_ptr[c] = (int)strips.size();
-        if (c >= n_ctas) continue;
-        const size_t lo = tasks.size() * (size_t)c / n_ctas, hi = tasks.size() * (size_t)(c + 1) / n_ctas;
+        if (c >= n_ctas || lo >= tasks.size()) continue;
+        size_t hi = lo;
+        if (c == n_ctas - 1) {
+            hi = tasks.size();
+        } else {
+            // every later CTA pays for the strip its cut opens
+            const double target = (remaining + strip_cost * (n_ctas - 1 - c)) / (double)(n_ctas - c);
+            double acc = 0.0;
+            const size_t must_leave = (size_t)(n_ctas - 1 - c);          // at least one task for every later CTA
+            while (hi < tasks.size() - must_leave) {
+                const double inc = 1.0 + (opens_strip(hi, lo) ? strip_cost : 0.0);
+                if (hi > lo && acc + 0.5 * inc > target) break;
+                acc += inc;
+                ++hi;
+            }
+        }
+        for (size_t j = lo; j < hi; ++j) remaining -= 1.0 + (opens_strip(j, 0) ? strip_cost : 0.0);
         size_t i = lo;
         while (i < hi) {
             size_t j = i;
@@ -157,6 +187,7 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
             tasks[j - 1].w |= kTaskLast;
             i = j;
         }
+        lo = hi;
     }
     cta_ptr[kNumCtas] = (int)strips.size();
     *n_stored = (int)tiles.size();

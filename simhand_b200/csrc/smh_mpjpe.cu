@@ -10,6 +10,8 @@
 //
 // CUDA-core kernel: per ordered pair 21 MUFU.RSQ and ~190 FMA-pipe lane-operations; the packed
 // FADD2/FMUL2/FFMA2 forms halve the issue slots.  This is the kernel the roofline in bench.py is quoted on.
+#include <cstdlib>
+
 #include "smh_common.cuh"
 #include "smh_internal.h"
 
@@ -187,15 +189,18 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
     }
 }
 
-// Persistent CTAs (one resident set: 3 per SM for the 16-bit image, 2 for the exact form) pull work items from an atomic
-// counter, so the grid has no wave quantisation and no mostly-empty last wave (a rank's 1032 tiles at 8 GPUs used to be
-// 4.65 waves of half-tile CTAs).  An item is one 128 / PARTS-column part of a stored tile: thread = row x (64 / PARTS)
-// columns.  PARTS = 2 when the rank has many tiles, 4 when it has few (sharded runs): the tail of the kernel is at most one
-// item long.  The rank's last CTA resets the counter (and, with a peer exchange, ships Dmax: dist_tail).
+// A work item is one 128 / PARTS-column part of a stored tile: thread = row x (64 / PARTS) columns.
+//   dynamic = 0: one CTA per item (grid = items).  PARTS = 1 when the rank has many tiles; PARTS = 2 when it has few
+//                (sharded runs), so that the last wave of the resident CTAs is not mostly empty.
+//   dynamic = 1: one resident set of persistent CTAs (3 per SM for the 16-bit image, 2 for the exact form) pulls items from
+//                an atomic counter: no wave quantisation, and the cross-rank stage wait / ticket are paid once per resident
+//                CTA instead of once per item.  The price is one atomic round trip and an un-overlapped operand load per
+//                item, which only pays for short kernels (measured: profiles/r02_mpjpe_modes.txt).
+// The rank's last CTA resets the counter (and, with a peer exchange, ships Dmax: dist_tail).
 template <int PARTS, bool Q16, bool FUSED>
 __global__ void __launch_bounds__(256, Q16 ? 3 : 2)
 mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m, int n_tiles,
-             Stats *__restrict__ stats, const __grid_constant__ Peers peers, int signal2)
+             Stats *__restrict__ stats, const __grid_constant__ Peers peers, int signal2, int dynamic)
 {
     constexpr int kCols = kTile / PARTS;              // columns staged per item
     constexpr int kPerThread = kCols / 2;
@@ -220,9 +225,9 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
     };
     __shared__ uint32_t cta_max_s, cta_bad_s;         // thread 0: maximum / non-finite flag over this CTA's items
     if (threadIdx.x == 0) cta_max_s = cta_bad_s = 0u;
-    for (;;) {
+    for (int round = 0;; ++round) {
         __syncthreads();                              // the previous item's reads of cs / wmax / item_s are done
-        if (threadIdx.x == 0) item_s = (int)atomicAdd(&stats->reserved, 1u);
+        if (threadIdx.x == 0) item_s = dynamic ? (int)atomicAdd(&stats->reserved, 1u) : (round == 0 ? (int)blockIdx.x : n_items);
         __syncthreads();
         const int item = item_s;
         if (item >= n_items) break;
@@ -436,20 +441,27 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
         else
             altdist_kernel<0><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
     } else {
-        // few tiles (sharded runs): quarter-tile items, else half-tile items; one resident set of persistent CTAs
+        // work-item size and scheduling: see mpjpe_kernel.  SMH_MPJPE_MODE = "<parts><s|d>" (e.g. "2s", "4d") overrides the
+        // choice for experiments.
         const bool q16 = dims.flags & SMH_DIMS_Q16_TILES;
         const bool small = lay.n_stored_tiles < 8 * 2 * kNumCtas;
-        const int resident = kNumCtas * (q16 ? 3 : 2);
-        const int items = lay.n_stored_tiles * (small ? 4 : 2);
-        const int grid = items < resident ? items : resident;
-#define SMH_MPJPE(P, Q, F) mpjpe_kernel<P, Q, F><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, lay.n_stored_tiles, st, peers, signal2)
-        if (small) {
-            if (q16) { if (peers.fused) SMH_MPJPE(4, true, true); else SMH_MPJPE(4, true, false); }
-            else     { if (peers.fused) SMH_MPJPE(4, false, true); else SMH_MPJPE(4, false, false); }
-        } else {
-            if (q16) { if (peers.fused) SMH_MPJPE(2, true, true); else SMH_MPJPE(2, true, false); }
-            else     { if (peers.fused) SMH_MPJPE(2, false, true); else SMH_MPJPE(2, false, false); }
+        // full-tile items, one CTA each, won every size measured (8256 / 4128 / 1032 tiles: profiles/r02_mpjpe_modes.txt);
+        // half-tile items only when there are too few tiles to fill the machine once
+        (void)small;
+        int parts = lay.n_stored_tiles < kNumCtas * (q16 ? 3 : 2) ? 2 : 1, dynamic = 0;
+        if (const char *mode = getenv("SMH_MPJPE_MODE")) {
+            if (mode[0] == '1' || mode[0] == '2') parts = mode[0] - '0';
+            if (mode[0] && (mode[1] == 'd' || mode[1] == 's')) dynamic = mode[1] == 'd';
         }
+        const int resident = kNumCtas * (q16 ? 3 : 2);
+        const int items = lay.n_stored_tiles * parts;
+        const int grid = dynamic ? (items < resident ? items : resident) : items;
+#define SMH_MPJPE(P, Q, F) mpjpe_kernel<P, Q, F><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, lay.n_stored_tiles, st, peers, signal2, dynamic)
+#define SMH_MPJPE_P(P)                                                                                     \
+        if (q16) { if (peers.fused) SMH_MPJPE(P, true, true); else SMH_MPJPE(P, true, false); }            \
+        else     { if (peers.fused) SMH_MPJPE(P, false, true); else SMH_MPJPE(P, false, false); }
+        if (parts == 1) { SMH_MPJPE_P(1) } else { SMH_MPJPE_P(2) }
+#undef SMH_MPJPE_P
 #undef SMH_MPJPE
     }
     int rc = check_launch(dims.diff_type != SMH_DIFF_MPJPE ? "altdist_kernel" : "mpjpe_kernel");

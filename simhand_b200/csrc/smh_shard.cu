@@ -18,6 +18,8 @@
 // poisons the whole group (sticky) and every later loss is NaN.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "smh_common.cuh"
 #include "smh_internal.h"
 
@@ -45,10 +47,14 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
     PhaseClock clk(pe, 0);
 
     if (blockIdx.x == 0) {
-        // rank 0 publishes the joints of global sample 0 first: every rank bounds its rows against them
+        // rank 0 publishes the joints of global sample 0 first: every rank bounds its rows against them.  Each coordinate
+        // travels as one 8-byte word {bits, epoch}: the store is atomic, the tag is its own "valid" flag (no fence, no
+        // separate flag: one NVLink latency)
         if (pe.rank == 0 && threadIdx.x < 42) {
             const float v = in.j1_dev[(int64_t)(threadIdx.x >> 1) * in.j_joint_stride + (threadIdx.x & 1) * in.j_coord_stride];
-            for (int p = 0; p < pe.world; ++p) pe.sig[p][kSigPivot + threadIdx.x] = __float_as_uint(v);
+            const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(v);
+            for (int p = 0; p < pe.world; ++p)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long *>(pe.sig[p] + kSigPivot) + threadIdx.x), "l"(w) : "memory");
         }
         // the scalars of the NEXT step (same slot as the previous one, which this rank has finished reading; peers
         // write it only after they have seen this rank's stage 4 of the current step)
@@ -59,11 +65,6 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
             st->fail_site = 0u;
             st->dsum = 0.0;
             st->reserved = 0u;                             // work counter of the persistent MPJPE kernel
-        }
-        __syncthreads();
-        if (pe.rank == 0 && threadIdx.x == 0) {
-            __threadfence_system();
-            for (int p = 0; p < pe.world; ++p) st_release_sys(pe.sig[p] + kSigPivotFlag, epoch);
         }
     }
 
@@ -207,11 +208,27 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
     __shared__ float pivot[42];
     __shared__ uint32_t wb[8];
     clk.lap();                                   // [0] zeroing + images + positives issued
-    if (threadIdx.x == 0) wait_word(pe, sig + kSigPivotFlag, epoch, 120u);
+    if (threadIdx.x < 42) {
+        // poll this coordinate's tagged word (bounded like every cross-rank wait)
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(sig + kSigPivot) + threadIdx.x;
+        unsigned long long w;
+        const unsigned long long t0 = global_ns();
+        const unsigned long long limit = (unsigned long long)(pe.timeout_ms ? pe.timeout_ms : 30000u) * 1000000ull;
+        for (uint32_t spin = 1;; ++spin) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+            if ((uint32_t)(w >> 32) == epoch) break;
+            if ((spin & 63u) == 0u) {
+                if (global_ns() - t0 > limit) {
+                    poison_group(pe, 120u);
+                    break;
+                }
+                __nanosleep(64);
+            }
+        }
+        pivot[threadIdx.x] = __uint_as_float((uint32_t)w);
+    }
     __syncthreads();
     clk.lap();                                   // [1] pivot arrived
-    if (threadIdx.x < 42) pivot[threadIdx.x] = __uint_as_float(__ldcg(sig + kSigPivot + threadIdx.x));
-    __syncthreads();
     uint32_t bound_bits = 0u;
     for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < rows; w += gridDim.x * wpb) {
         const int v = w >= a.n_local ? 1 : 0;
@@ -349,7 +366,7 @@ finalize_fused_kernel(smh_inputs_t in, int n, int d, const __grid_constant__ Pee
     const float pmin = __uint_as_float(0x7fffffffu - __ldcg(&gs->pmin_inv));
     const float pden = __fsub_rn(pmax, pmin);
     const int n_local = in.n_local;
-    const int k_lo = pe.rank * n_local, k_hi = k_lo + n_local;
+    const int k_lo = pe.rank * n_local;
     const float gsf = grad_scale * inv_tau / (float)m;
     const int64_t part_stride = (int64_t)2 * n_local * kD;
     __shared__ float pos_mean_s;
@@ -368,19 +385,27 @@ finalize_fused_kernel(smh_inputs_t in, int n, int d, const __grid_constant__ Pee
     }
     const float pos_mean = pos_mode == 3 ? pos_mean_s : 0.f;
 
-    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < m; row += gridDim.x * wpb) {
-        const int v = row >= n ? 1 : 0;
-        const int k = row - v * n;
+    auto pos_weight = [&](int k) {
         const float pd = __ldcg(posd + k);
         float wp = pos_mode == 1 ? 1.0f : __fdiv_rn(__fsub_rn(pmax, pd), pden);
         if (pos_mode == 3) wp = __fdiv_rn(1.0f, 1.0f + expf(lambda_pos * (pd - pos_mean)));
-        if (lane == 0) rowloss[row] = logf(__ldcg(neg + row)) - __ldcg(dots + k) * wp * inv_tau;      // utils.py:420-426
-        if (dz1 != nullptr && k >= k_lo && k < k_hi) {
-            const int kl = k - k_lo;
+        return wp;
+    };
+    // loss terms of ALL rows, one thread per row (every rank evaluates the global loss from the delivered row sums and
+    // positives: no further exchange)                                                               utils.py:420-426
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < m; row += gridDim.x * blockDim.x) {
+        const int k = row >= n ? row - n : row;
+        rowloss[row] = logf(__ldcg(neg + row)) - __ldcg(dots + k) * pos_weight(k) * inv_tau;
+    }
+    // gradients of the OWN rows, one warp per row: rank-ordered sum of the delivered partials minus the positive term
+    if (dz1 != nullptr) {
+        for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < 2 * n_local; w += gridDim.x * wpb) {
+            const int v = w >= n_local ? 1 : 0;
+            const int kl = w - v * n_local;
+            const float two_wp = 2.f * pos_weight(k_lo + kl);
             const float *zp = (v ? in.z1_dev : in.z2_dev) + (int64_t)kl * in.z_row_stride;        // the partner's row
-            const float *src = dzparts + ((int64_t)v * n_local + kl) * kD;
+            const float *src = dzparts + (int64_t)w * kD;
             float *dst = (v ? dz2 : dz1) + (int64_t)kl * dz_row_stride;
-            const float two_wp = 2.f * wp;
             for (int c = lane; c < d; c += 32) {
                 float acc = __ldcg(src + c);
                 for (int p = 1; p < pe.world; ++p) acc += __ldcg(src + (int64_t)p * part_stride + c);   // rank order
@@ -422,7 +447,9 @@ int launch_finalize_fused(const smh_dims_t &dims, const smh_layout_t &lay, const
                           int pos_mode, float temperature, float grad_scale, float *loss, float *dz1, float *dz2,
                           int64_t dz_row_stride, const Peers &peers, cudaStream_t stream)
 {
-    const int blocks = (lay.m + 7) / 8 < 4 * kNumCtas ? (lay.m + 7) / 8 : 4 * kNumCtas;
+    const int n_local = dims.n / dims.world;
+    int blocks = std::max((lay.m + 255) / 256, (2 * n_local + 7) / 8);           // a thread per loss row, a warp per own row
+    if (blocks > 2 * kNumCtas) blocks = 2 * kNumCtas;
     finalize_fused_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, peers, ws.neg, ws.rowloss, ws.dzparts, pos_mode,
                                                       dims.lambda_pos, 1.0f / temperature, grad_scale, loss, dz1, dz2,
                                                       dz_row_stride);

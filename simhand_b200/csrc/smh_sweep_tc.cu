@@ -50,7 +50,7 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps + 64;     // 640: tile producer, 
 constexpr int kSBufs = 4;                                // S / G buffers in TMEM (64 columns each)
 constexpr int kMaxBStages = 4;                           // z blocks come from L2
 constexpr int kMaxDStages = 8;                           // MPJPE tile pieces come from HBM: deeper prefetch
-constexpr int kNumBars = 56;
+constexpr int kNumBars = 58;
 constexpr int kCtlBytes = kNumBars * 8 + kMaxDStages * 16 + 16;   // barriers, staged task records, TMEM base
 
 // Q16: the distance tiles are the 16-bit image (SMH_DIMS_Q16_TILES): half the bytes per task, twice the stages in flight
@@ -73,7 +73,7 @@ struct TcBars {
     uint64_t full_d[kMaxDStages][kEpiGroups];
     uint64_t a_full, a_empty;
     uint64_t sg_full[kSBufs], sg_empty[kSBufs], g_ready[kSBufs];
-    uint64_t dz_full, dz_empty;
+    uint64_t dz_full[2], dz_empty[2];        // two gradient accumulators in TMEM: strip k uses k % 2
 };
 static_assert(sizeof(TcBars) <= kNumBars * 8, "barrier block too small");
 
@@ -285,8 +285,10 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             mbar_init(&bars->sg_empty[i], BWD ? 1 : kGroupWarps);
             mbar_init(&bars->g_ready[i], kGroupWarps);
         }
-        mbar_init(&bars->dz_full, 1);
-        mbar_init(&bars->dz_empty, kEpiWarps);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->dz_full[i], 1);
+            mbar_init(&bars->dz_empty[i], kEpiWarps);
+        }
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -467,17 +469,17 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         // dependency between the two streams goes through an mbarrier, so they need no ordering between them.
         constexpr uint32_t idesc2 = umma_idesc_bf16(kTile, kD, 0, 1);
         const uint32_t sB_u = smem_u32(sB);
-        uint32_t q = 0, dz_ph = 0;
+        uint32_t q = 0;
         for (int s = s_begin; s < s_end; ++s) {
             const int2 strip = strips[s];
+            // gradient accumulator of this strip: the epilogue drains the other one while this strip's MMAs run
+            const uint32_t sk = (uint32_t)(s - s_begin), acc = sk & 1u;
+            const uint32_t dz_tmem = tmem_base + kDzCol + acc * (uint32_t)kD;
             for (int ti = strip.x; ti < strip.y; ++ti, ++q) {
                 const uint32_t sbq = q % kSBufs, bstq = q % kBStages;
                 const bool first = ti == strip.x, last = ti + 1 == strip.y;
                 mbar_wait(&bars->g_ready[sbq], (q / kSBufs) & 1u, fail, 4);
-                if (first) {
-                    mbar_wait(&bars->dz_empty, dz_ph ^ 1u, fail, 5);
-                    dz_ph ^= 1u;
-                }
+                if (first) mbar_wait(&bars->dz_empty[acc], ((sk >> 1) & 1u) ^ 1u, fail, 5);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
@@ -487,12 +489,12 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                         // columns [32,48) hold task columns 32..63 (each epilogue half overwrites its own S columns).
                         const uint64_t bdesc = umma_desc_sw128(sB_u + bstq * kBBytes + ks * 2048, 8192, 1024);
                         const uint32_t a_col = (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u;
-                        tc_mma_ts_f16(tmem_base + kDzCol, tmem_base + sbq * kTaskN + a_col, bdesc, idesc2,
+                        tc_mma_ts_f16(dz_tmem, tmem_base + sbq * kTaskN + a_col, bdesc, idesc2,
                                       (first && ks == 0) ? 0u : 1u);
                     }
                     tc_commit(&bars->sg_empty[sbq]);
                     tc_commit(&bars->empty_b[bstq]);
-                    if (last) tc_commit(&bars->dz_full);
+                    if (last) tc_commit(&bars->dz_full[acc]);
                 }
                 __syncwarp();
             }
@@ -529,8 +531,37 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         }
         const f2 negc2 = pack2(negc, negc), k2c2 = pack2(addc, addc);
         const uint32_t sD_s = smem_u32(sD);
-        uint32_t seq = 0, dz_ph = 0;
+        uint32_t seq = 0;
         f2 rowsum[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
+        // Backward: the flush of a strip's gradient accumulator is DEFERRED by one strip.  Waiting for the strip's last value
+        // MMA right after its last task drained the whole pipeline at every strip boundary (a strip cost ~4 task times:
+        // profiles/r02_strip_cost.txt); with two accumulators the epilogue goes straight on to the next strip and drains
+        // the finished accumulator after that strip's tasks, when its MMAs have long completed.
+        int pend_row = -1;                            // first row of the strip whose accumulator is still to be drained
+        uint32_t pend_k = 0;                          // its index among this CTA's strips
+        auto flush_dz = [&](int row_first, uint32_t sk) {
+            const uint32_t acc = sk & 1u;
+            mbar_wait(&bars->dz_full[acc], (sk >> 1) & 1u, fail, 11);
+            tc_fence_after();
+            const int gi2 = row_first + r;
+            const bool ok2 = gi2 < m;
+            // fused reduce-scatter: the gradient rows are added straight into the owning rank's accumulator
+            float *orow = dz_row_ptr(peers, ok2 ? gi2 : 0, n, n_local);
+            const int chunk = group * 2 + half;       // every epilogue warp drains 32 of the 128 columns of its lane quadrant
+            uint32_t dv[32];
+            tc_ld32(lane_addr + kDzCol + acc * (uint32_t)kD + chunk * 32, dv);
+            tc_wait_ld();
+            if (ok2) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    red_add_v4(orow + chunk * 32 + q * 4, inv_k2 * __uint_as_float(dv[4 * q]),
+                               inv_k2 * __uint_as_float(dv[4 * q + 1]), inv_k2 * __uint_as_float(dv[4 * q + 2]),
+                               inv_k2 * __uint_as_float(dv[4 * q + 3]));        // the accumulator holds k2 * dz
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->dz_empty[acc]);
+        };
         TR_DECL(7);
         for (int s = s_begin; s < s_end; ++s) {
             const int2 strip = strips[s];
@@ -610,31 +641,13 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 }
                 rowsum[0] = rowsum[1] = pack2(0.f, 0.f);
             } else {
-                // every epilogue warp drains 32 of the 128 gradient columns of its lane quadrant
-                mbar_wait(&bars->dz_full, dz_ph, fail, 11);
-                dz_ph ^= 1u;
-                tc_fence_after();
-                const int gi2 = tasks[strip.x].x * kTile + r;
-                const bool ok2 = gi2 < m;
-                // fused reduce-scatter: the gradient rows are added straight into the owning rank's accumulator
-                float *orow = dz_row_ptr(peers, ok2 ? gi2 : 0, n, n_local);
-                const int chunk = group * 2 + half;
-                uint32_t dv[32];
-                tc_ld32(lane_addr + kDzCol + chunk * 32, dv);
-                tc_wait_ld();
-                if (ok2) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        red_add_v4(orow + chunk * 32 + q * 4, inv_k2 * __uint_as_float(dv[4 * q]),
-                                   inv_k2 * __uint_as_float(dv[4 * q + 1]), inv_k2 * __uint_as_float(dv[4 * q + 2]),
-                                   inv_k2 * __uint_as_float(dv[4 * q + 3]));        // the accumulator holds k2 * dz
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->dz_empty);
+                if (pend_row >= 0) flush_dz(pend_row, pend_k);       // the PREVIOUS strip's accumulator
+                pend_row = tasks[strip.x].x * kTile;
+                pend_k = (uint32_t)(s - s_begin);
             }
             TR_LAP(5);                                                              // [5] strip flush
         }
+        if (BWD && pend_row >= 0) flush_dz(pend_row, pend_k);         // the CTA's last strip
         if (e == 0 && lane == 0) TR_STORE(3, 7);
     }
 

@@ -70,7 +70,7 @@ def main():
         if it >= 2:
             for i, stage in enumerate(sd.FUSED_STAGES):
                 acc[stage] += evs[i].elapsed_time(evs[i + 1])
-            clocks += ex.signal[128:128 + 96].cpu().view(torch.int32).to(torch.int64).bitwise_and(0xffffffff).double().view(6, 16)
+            clocks += ex.signal[160:160 + 96].cpu().view(torch.int32).to(torch.int64).bitwise_and(0xffffffff).double().view(6, 16)
     clocks /= iters
     line = f"rank {rank}/{world} exact={int(exact)} poisoned={ex.poisoned()} | " + " ".join(
         f"{s} {acc[s] / iters * 1e3:.1f}us" for s in sd.FUSED_STAGES) + f" | total {sum(acc.values()) / iters * 1e3:.1f}us"
