@@ -56,6 +56,15 @@ def _ncu_traffic(kernel: str):
     return None
 
 
+def _mufu_peak():
+    """Measured special-function throughput (tools/mufu_peak.cu, run on this pool's B200: profiles/r02_mufu_peak.json)."""
+    p = os.path.join(ROOT, "profiles", "r02_mufu_peak.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            return json.load(fh)
+    return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -368,11 +377,22 @@ def run_ours(args):
                 gpu_launches=launches * steps)
     if kernels is not None:
         f_clk = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
-        xu_peak = NUM_SMS * MUFU_LANES_PER_SM * f_clk * 1e6 / 1e9          # G special-function ops / s
+        xu_nominal = NUM_SMS * MUFU_LANES_PER_SM * f_clk * 1e6 / 1e9       # G special-function ops / s
+        mufu = _mufu_peak()
         tiles_total = (m // 128) * (m // 128 + 1) // 2                     # stored (upper-triangular) MPJPE tiles
         tiles = tiles_total / world                                        # per rank (balanced to +-1 tile)
 
         def roofline_of(kern, exact):
+            # denominator: the MUFU rate of the instruction the kernel issues, measured on this pool (scaled to the SM
+            # clock seen during this run); the nominal 16 lanes / clk / SM when the measurement file is absent
+            if mufu:
+                xu_peak = mufu["mufu_rsq_gops" if exact else "mufu_sqrt_gops"] * f_clk / mufu["clock_rate_mhz"]
+                src = (f"measured {'MUFU.RSQ' if exact else 'MUFU.SQRT'} throughput (tools/mufu_peak.cu -> profiles/r02_mufu_peak.json, "
+                       f"{mufu['clock_rate_mhz']:.0f} MHz) scaled to the {f_clk:.0f} MHz seen under load; nominal 148 x 16 lanes/clk = "
+                       f"{xu_nominal:.0f} Gop/s")
+            else:
+                xu_peak = xu_nominal
+                src = f"nominal: 148 SMs x 16 MUFU lanes/clk x {f_clk:.0f} MHz (median SM clock under load)"
             t_mpjpe = kern["mpjpe_kernel"] * 1e-3
             traffic = _ncu_traffic("mpjpe_kernel")
             executed = 21.0 * tiles * 128 * 128 / t_mpjpe / 1e9            # sqrt one rank's launch evaluates / its duration
@@ -385,8 +405,7 @@ def run_ours(args):
                       "Gop/s per GPU: approximate sqrt (one MUFU.SQRT, no correction: relaxed-weights mode), 21 per pair the launch evaluates"),
                 frac=executed / xu_peak, traffic=(traffic or {}).get("bytes") if (world == 1 and not exact) else None,
                 traffic_source=(traffic or {}).get("source") if (world == 1 and not exact) else None,
-                peak_source=f"148 SMs x 16 MUFU lanes/clk x {f_clk:.0f} MHz (median SM clock under load); nominal issue rate, "
-                            "tools/microbench.cu measures it",
+                peak_source=src,
                 units_per_launch=f"{tiles:.0f} tiles x 16384 unordered pairs per rank (symmetry: D_ij == D_ji bitwise)",
                 algorithmic_frac=(21.0 * m * m / world / t_mpjpe / 1e9) / xu_peak,
                 step_frac=(22.0 * m * m / world / (step_ms * 1e-3) / 1e9) / xu_peak,

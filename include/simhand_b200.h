@@ -134,8 +134,10 @@ typedef struct smh_layout {
     int32_t tiles_per_side;      /* Tp = ceil(M / 128) */
     int32_t n_stored_tiles;      /* upper-triangular 128x128 tiles assigned to this rank */
     int32_t n_tasks;             /* 128x64 sweep tasks of this rank */
-    int32_t n_strips;            /* groups of consecutive tasks sharing a row block */
+    int32_t n_strips;            /* groups of consecutive tasks sharing a row block (backward sweep's cuts) */
     int32_t strip_len;           /* max tasks per strip */
+    int32_t n_strips_fwd;        /* the same for the forward sweep's cuts of the task list */
+    int32_t reserved;
 } smh_layout_t;
 
 /* device-resident scalars.  The first three words are order-preserving integer images of the

@@ -48,7 +48,8 @@ class Layout(ctypes.Structure):
                 ("off_dzacc", ctypes.c_int64), ("off_negparts", ctypes.c_int64), ("off_dzparts", ctypes.c_int64),
                 ("off_dist", ctypes.c_int64), ("off_posinfo", ctypes.c_int64),
                 ("m", ctypes.c_int32), ("tiles_per_side", ctypes.c_int32), ("n_stored_tiles", ctypes.c_int32),
-                ("n_tasks", ctypes.c_int32), ("n_strips", ctypes.c_int32), ("strip_len", ctypes.c_int32)]
+                ("n_tasks", ctypes.c_int32), ("n_strips", ctypes.c_int32), ("strip_len", ctypes.c_int32),
+                ("n_strips_fwd", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class Inputs(ctypes.Structure):

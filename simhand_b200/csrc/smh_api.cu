@@ -15,7 +15,9 @@
 namespace smh {
 
 static thread_local char g_err[512] = "";
-constexpr double kStripCost = 4.0;        // cost of opening a strip, in sweep-task times (enumerate_plan)
+// cost of opening a strip in sweep-task times (enumerate_plan): backward (gradient-accumulator flush, row-block reload,
+// pipeline restart) and forward (128 atomics)
+constexpr double kStripCostBwd = 4.0, kStripCostFwd = 0.5;
 
 int set_error(int code, const char *fmt, ...)
 {
@@ -70,12 +72,63 @@ static inline int row_owner(int I, int tp, int world) { return std::min(I, tp - 
 struct HostPlan {
     std::vector<int2> tiles;
     std::vector<int4> tasks;
-    std::vector<int2> strips;
-    std::vector<int> cta_ptr;          // kNumCtas + 1 offsets into strips
+    // the CTA ranges are cut separately for the two sweeps (a strip costs the backward sweep ~4 task times, the forward
+    // sweep next to nothing): [0] backward, [1] forward
+    std::vector<int2> strips[2];
+    std::vector<int> cta_ptr[2];       // kNumCtas + 1 offsets into strips
 };
 
+// Contiguous ranges of the ordered task list for the kNumCtas sweep CTAs, cut for equal COST: a task costs 1, every strip a
+// CTA opens (a run of tasks with the same row block; a cut opens one too) costs `strip_cost` task times.  With ~28 tasks per
+// CTA (8 ranks) a strip more or less is 10 % of a CTA's time: equal task counts left the slowest CTA of the backward sweep
+// 15-20 % behind the first (profiles/r02_strip_cost*.txt).
+static void cut_ranges(const std::vector<int4> &tasks, double strip_cost, int strip_len, std::vector<int2> *strips_out,
+                       std::vector<int> *cta_ptr_out)
+{
+    const int n_ctas = (int)std::min<size_t>(kNumCtas, std::max<size_t>(tasks.size(), 1));
+    std::vector<int2> strips;
+    std::vector<int> cta_ptr(kNumCtas + 1, 0);
+    auto opens_strip = [&](size_t j, size_t first) {          // does task j open a new strip in a range starting at `first`?
+        return j == first || tasks[j].x != tasks[j - 1].x;
+    };
+    double remaining = 0.0;
+    for (size_t j = 0; j < tasks.size(); ++j) remaining += 1.0 + (opens_strip(j, 0) ? strip_cost : 0.0);
+    size_t lo = 0;
+    for (int c = 0; c < kNumCtas; ++c) {
+        cta_ptr[c] = (int)strips.size();
+        if (c >= n_ctas || lo >= tasks.size()) continue;
+        size_t hi = lo;
+        if (c == n_ctas - 1) {
+            hi = tasks.size();
+        } else {
+            // every later CTA pays for the strip its cut opens
+            const double target = (remaining + strip_cost * (n_ctas - 1 - c)) / (double)(n_ctas - c);
+            double acc = 0.0;
+            const size_t must_leave = (size_t)(n_ctas - 1 - c);          // at least one task for every later CTA
+            while (hi < tasks.size() - must_leave) {
+                const double inc = 1.0 + (opens_strip(hi, lo) ? strip_cost : 0.0);
+                if (hi > lo && acc + 0.5 * inc > target) break;
+                acc += inc;
+                ++hi;
+            }
+        }
+        for (size_t j = lo; j < hi; ++j) remaining -= 1.0 + (opens_strip(j, 0) ? strip_cost : 0.0);
+        size_t i = lo;
+        while (i < hi) {
+            size_t j = i;
+            while (j < hi && tasks[j].x == tasks[i].x && (int)(j - i) < strip_len) ++j;
+            strips.push_back(make_int2((int)i, (int)j));
+            i = j;
+        }
+        lo = hi;
+    }
+    cta_ptr[kNumCtas] = (int)strips.size();
+    strips_out->swap(strips);
+    cta_ptr_out->swap(cta_ptr);
+}
+
 static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out, int *n_stored, int *n_tasks,
-                           int *n_strips)
+                           int *n_strips, int *n_strips_fwd)
 {
     const int m = 2 * dims.n;
     const int tp = (m + kTile - 1) / kTile;
@@ -143,61 +196,25 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
         };
         std::sort(tasks.begin(), tasks.end(), [&](const int4 &x, const int4 &y) { return key(x) < key(y); });
     }
-    // The CTAs take contiguous ranges of the ordered list, cut for equal COST: a task costs 1, every strip a CTA opens
-    // (a run of tasks with the same row block; a cut opens one too) costs kStripCost task-times -- the strip's flush of the
-    // row sums / gradient rows and the pipeline drain in front of it.  With ~28 tasks per CTA (8 ranks) a strip more or
-    // less is 10 % of a CTA's time: equal task counts left the slowest CTA 15-20 % behind the first
-    // (profiles/r02_phase_clocks_n2.txt).  SMH_STRIP_COST overrides the weight for experiments.
-    double strip_cost = kStripCost;
-    if (const char *e = getenv("SMH_STRIP_COST")) strip_cost = atof(e);
-    const int n_ctas = (int)std::min<size_t>(kNumCtas, std::max<size_t>(tasks.size(), 1));
-    std::vector<int2> strips;
-    std::vector<int> cta_ptr(kNumCtas + 1, 0);
-    auto opens_strip = [&](size_t j, size_t first) {          // does task j open a new strip in a range starting at `first`?
-        return j == first || tasks[j].x != tasks[j - 1].x;
-    };
-    double remaining = 0.0;
-    for (size_t j = 0; j < tasks.size(); ++j) remaining += 1.0 + (opens_strip(j, 0) ? strip_cost : 0.0);
-    size_t lo = 0;
-    for (int c = 0; c < kNumCtas; ++c) {
-        cta_ptr[c] = (int)strips.size();
-        if (c >= n_ctas || lo >= tasks.size()) continue;
-        size_t hi = lo;
-        if (c == n_ctas - 1) {
-            hi = tasks.size();
-        } else {
-            // every later CTA pays for the strip its cut opens
-            const double target = (remaining + strip_cost * (n_ctas - 1 - c)) / (double)(n_ctas - c);
-            double acc = 0.0;
-            const size_t must_leave = (size_t)(n_ctas - 1 - c);          // at least one task for every later CTA
-            while (hi < tasks.size() - must_leave) {
-                const double inc = 1.0 + (opens_strip(hi, lo) ? strip_cost : 0.0);
-                if (hi > lo && acc + 0.5 * inc > target) break;
-                acc += inc;
-                ++hi;
-            }
-        }
-        for (size_t j = lo; j < hi; ++j) remaining -= 1.0 + (opens_strip(j, 0) ? strip_cost : 0.0);
-        size_t i = lo;
-        while (i < hi) {
-            size_t j = i;
-            while (j < hi && tasks[j].x == tasks[i].x && (int)(j - i) < strip_len) ++j;
-            strips.push_back(make_int2((int)i, (int)j));
-            tasks[i].w |= kTaskFirst;
-            tasks[j - 1].w |= kTaskLast;
-            i = j;
-        }
-        lo = hi;
-    }
-    cta_ptr[kNumCtas] = (int)strips.size();
+    // SMH_STRIP_COST / SMH_STRIP_COST_FWD override the weights for experiments
+    double cost_bwd = kStripCostBwd, cost_fwd = kStripCostFwd;
+    if (const char *e = getenv("SMH_STRIP_COST")) cost_bwd = atof(e);
+    if (const char *e = getenv("SMH_STRIP_COST_FWD")) cost_fwd = atof(e);
+    std::vector<int2> strips[2];
+    std::vector<int> cta_ptr[2];
+    cut_ranges(tasks, cost_bwd, strip_len, &strips[0], &cta_ptr[0]);
+    cut_ranges(tasks, cost_fwd, strip_len, &strips[1], &cta_ptr[1]);
     *n_stored = (int)tiles.size();
     *n_tasks = (int)tasks.size();
-    *n_strips = (int)strips.size();
+    *n_strips = (int)strips[0].size();
+    *n_strips_fwd = (int)strips[1].size();
     if (out) {
         out->tiles.swap(tiles);
         out->tasks.swap(tasks);
-        out->strips.swap(strips);
-        out->cta_ptr.swap(cta_ptr);
+        for (int k = 0; k < 2; ++k) {
+            out->strips[k].swap(strips[k]);
+            out->cta_ptr[k].swap(cta_ptr[k]);
+        }
     }
 }
 
@@ -223,7 +240,7 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     lay->m = m;
     lay->tiles_per_side = tp;
     lay->strip_len = dims.strip_len > 0 ? dims.strip_len : 4096;
-    enumerate_plan(dims, lay->strip_len, plan, &lay->n_stored_tiles, &lay->n_tasks, &lay->n_strips);
+    enumerate_plan(dims, lay->strip_len, plan, &lay->n_stored_tiles, &lay->n_tasks, &lay->n_strips, &lay->n_strips_fwd);
     int64_t off = 0;
     auto take = [&](int64_t bytes) {
         int64_t o = off;
@@ -250,7 +267,7 @@ static int compute_layout(const smh_dims_t &dims, smh_layout_t *lay, HostPlan *p
     lay->ws_bytes = off;
     lay->plan_bytes = align_up((int64_t)sizeof(PlanHeader), 16) + align_up((int64_t)lay->n_stored_tiles * 8, 16) +
                       (int64_t)lay->n_tasks * 16 + align_up((int64_t)lay->n_strips * 8, 16) +
-                      align_up((int64_t)(kNumCtas + 1) * 4, 16);
+                      align_up((int64_t)lay->n_strips_fwd * 8, 16) + 2 * align_up((int64_t)(kNumCtas + 1) * 4, 16);
     g_memo.dims = dims;
     g_memo.lay = *lay;
     g_memo.valid = true;
@@ -289,6 +306,10 @@ static PlanView carve_plan(const void *plan, const smh_layout_t &lay)
     v.strips = (const int2 *)(b + o);
     o += align_up((int64_t)lay.n_strips * 8, 16);
     v.cta_ptr = (const int *)(b + o);
+    o += align_up((int64_t)(kNumCtas + 1) * 4, 16);
+    v.strips_fwd = (const int2 *)(b + o);
+    o += align_up((int64_t)lay.n_strips_fwd * 8, 16);
+    v.cta_ptr_fwd = (const int *)(b + o);
     return v;
 }
 
@@ -423,10 +444,17 @@ int smh_plan_build(const smh_dims_t *dims, void *plan_host, int64_t plan_bytes)
     if (!hp.tasks.empty()) memcpy(b + o, hp.tasks.data(), hp.tasks.size() * 16);
     o += (int64_t)lay.n_tasks * 16;
     h.off_strips = (uint32_t)o;
-    if (!hp.strips.empty()) memcpy(b + o, hp.strips.data(), hp.strips.size() * 8);
+    if (!hp.strips[0].empty()) memcpy(b + o, hp.strips[0].data(), hp.strips[0].size() * 8);
     o += align_up((int64_t)lay.n_strips * 8, 16);
     h.off_cta = (uint32_t)o;
-    memcpy(b + o, hp.cta_ptr.data(), hp.cta_ptr.size() * 4);
+    memcpy(b + o, hp.cta_ptr[0].data(), hp.cta_ptr[0].size() * 4);
+    o += align_up((int64_t)(kNumCtas + 1) * 4, 16);
+    h.off_strips_fwd = (uint32_t)o;
+    h.n_strips_fwd = (uint32_t)lay.n_strips_fwd;
+    if (!hp.strips[1].empty()) memcpy(b + o, hp.strips[1].data(), hp.strips[1].size() * 8);
+    o += align_up((int64_t)lay.n_strips_fwd * 8, 16);
+    h.off_cta_fwd = (uint32_t)o;
+    memcpy(b + o, hp.cta_ptr[1].data(), hp.cta_ptr[1].size() * 4);
     memcpy(b, &h, sizeof(h));
     return 0;
 }

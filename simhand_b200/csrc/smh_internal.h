@@ -28,8 +28,10 @@ struct WsView {                 // device pointers carved out of the caller's wo
 struct PlanView {               // device pointers into the caller's plan blob
     const int2 *tiles;          // (I, J) of each stored tile of this rank
     const int4 *tasks;          // (row block, 64-col tile, stored tile, flags)
-    const int2 *strips;         // (first task, one-past-last task)
+    const int2 *strips;         // backward sweep: (first task, one-past-last task)
     const int *cta_ptr;         // strips of sweep CTA c: [cta_ptr[c], cta_ptr[c + 1])
+    const int2 *strips_fwd;     // the forward sweep's own cuts of the same task list
+    const int *cta_ptr_fwd;
 };
 
 int set_error(int code, const char *fmt, ...);

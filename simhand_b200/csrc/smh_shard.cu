@@ -425,8 +425,19 @@ finalize_fused_kernel(smh_inputs_t in, int n, int d, const __grid_constant__ Pee
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < m; i += 256) acc += __ldcg(rowloss + i);
+    // fixed order (thread t owns rows t, t + 256, ...; four independent partial sums keep 8 loads in flight)
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int i = threadIdx.x;
+    for (; i + 768 < m; i += 1024) {
+        const float v0 = __ldcg(rowloss + i), v1 = __ldcg(rowloss + i + 256), v2 = __ldcg(rowloss + i + 512),
+                    v3 = __ldcg(rowloss + i + 768);
+        a0 += v0;
+        a1 += v1;
+        a2 += v2;
+        a3 += v3;
+    }
+    for (; i < m; i += 256) a0 += __ldcg(rowloss + i);
+    const float acc = (a0 + a1) + (a2 + a3);
     red[threadIdx.x] = acc;
     __syncthreads();
     for (int s2 = 128; s2 > 0; s2 >>= 1) {

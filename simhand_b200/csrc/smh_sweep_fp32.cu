@@ -177,7 +177,7 @@ int launch_sweep_fp32(bool backward, int wmode, const smh_dims_t &dims, const sm
     } else {
         e = cudaFuncSetAttribute(sweep_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32Smem);
         if (e != cudaSuccess) return set_error((int)e, "fp32 sweep smem attr: %s", cudaGetErrorString(e));
-        sweep_fp32_kernel<false><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt,
+        sweep_fp32_kernel<false><<<grid, 256, kFp32Smem, stream>>>(plan.tasks, plan.strips_fwd, plan.cta_ptr_fwd, ws.zt,
                                                                   ws.dist, ws.rn, peers,
                                                                   (const Stats *)ws.stats, lay.m, dims.n, n_local, k2, wmode, dims.lambda_neg);
     }

@@ -710,7 +710,8 @@ static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, co
     constexpr int smem = TcCfg<SBF16, Q16>::kSmem;
     cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16, Q16, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-    sweep_tc_kernel<BWD, SBF16, Q16, FUSED><<<grid, kTcThreads, smem, stream>>>(plan.tasks, plan.strips, plan.cta_ptr, ws.zt, half_image,
+    sweep_tc_kernel<BWD, SBF16, Q16, FUSED><<<grid, kTcThreads, smem, stream>>>(plan.tasks, BWD ? plan.strips : plan.strips_fwd,
+                                                                   BWD ? plan.cta_ptr : plan.cta_ptr_fwd, ws.zt, half_image,
                                                                    ws.dist, ws.rn, peers, xp, (Stats *)ws.stats, lay.m,
                                                                    dims.n, n_local, k2, inv_k2, wmode, dims.lambda_neg, idesc1,
                                                                         reinterpret_cast<long long *>(ws.rowloss));

@@ -19,7 +19,7 @@ BLOCK_FLOATS = BLOCK_ROWS * 128
 JP = 44
 STAGE_FLOATS = 8192              # floats of a stored tile staged per task (32 KiB, no padding)
 
-TASK_TRANSPOSED, TASK_DIAGONAL, TASK_RAGGED, TASK_FIRST, TASK_LAST = 1, 2, 4, 8, 16
+TASK_TRANSPOSED, TASK_DIAGONAL, TASK_RAGGED = 1, 2, 4
 
 
 def zt_index(row, col):
@@ -49,13 +49,16 @@ def parse_plan(plan_bytes: np.ndarray):
     """Decodes a plan blob built by smh_plan_build into (header dict, tiles[n,2], tasks[n,4], strips[n,2])."""
     hdr = np.frombuffer(plan_bytes[:64].tobytes(), dtype=np.uint32)
     names = ("magic", "m", "world", "rank", "tiles_per_side", "n_stored", "n_tasks", "n_strips", "strip_len",
-             "off_tiles", "off_tasks", "off_strips", "off_cta")
+             "off_tiles", "off_tasks", "off_strips", "off_cta", "off_strips_fwd", "off_cta_fwd", "n_strips_fwd")
     h = {k: int(v) for k, v in zip(names, hdr)}
     raw = plan_bytes.tobytes()
     tiles = np.frombuffer(raw, np.int32, h["n_stored"] * 2, h["off_tiles"]).reshape(-1, 2)
     tasks = np.frombuffer(raw, np.int32, h["n_tasks"] * 4, h["off_tasks"]).reshape(-1, 4)
     strips = np.frombuffer(raw, np.int32, h["n_strips"] * 2, h["off_strips"]).reshape(-1, 2)
     h["cta_ptr"] = np.frombuffer(raw, np.int32, NUM_CTAS + 1, h["off_cta"])
+    # the forward sweep's own cuts of the same task list
+    h["strips_fwd"] = np.frombuffer(raw, np.int32, h["n_strips_fwd"] * 2, h["off_strips_fwd"]).reshape(-1, 2)
+    h["cta_ptr_fwd"] = np.frombuffer(raw, np.int32, NUM_CTAS + 1, h["off_cta_fwd"])
     return h, tiles, tasks, strips
 
 
