@@ -445,9 +445,19 @@ head_bwd1_kernel(const __grid_constant__ CUtensorMap map_w2t, const __grid_const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 12);
     __shared__ uint32_t fail_s;
     __shared__ float part[4][2][128];
+    // per-column BatchNorm constants: hn = h * sc + sh (sc = gamma rstd, sh = beta - mean sc); hhat = h * rs + nm
+    __shared__ float sc_s[1024], sh_s[1024], rs_s[1024], nm_s[1024];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * 128;
     const int chunks = hidden / 128;
+    for (int c = threadIdx.x; c < hidden; c += kB1Threads) {
+        const float mean = save_mean[c], rstd = save_rstd[c];
+        const float sc = gamma[c] * rstd;
+        sc_s[c] = sc;
+        sh_s[c] = beta[c] - mean * sc;
+        rs_s[c] = rstd;
+        nm_s[c] = -mean * rstd;
+    }
     if (threadIdx.x == 0) {
         fail_s = 0u;
         for (int i = 0; i < 2; ++i) {
@@ -562,8 +572,8 @@ head_bwd1_kernel(const __grid_constant__ CUtensorMap map_w2t, const __grid_const
                             const int i = j * 8 + u * 2 + hf;
                             const int c = kc * 128 + ch * 32 + i;
                             const float hval = unpack16(w[u], hf, fp16 != 0);
-                            const float hhat = (hval - __ldg(save_mean + c)) * __ldg(save_rstd + c);
-                            const float hn = fmaf(hhat, __ldg(gamma + c), __ldg(beta + c));
+                            const float hhat = fmaf(hval, rs_s[c], nm_s[c]);
+                            const float hn = fmaf(hval, sc_s[c], sh_s[c]);
                             const float da = __uint_as_float(v[i]);
                             const float dh = (hn > 0.f && row_ok) ? da : 0.f;
                             g[i] = dh;
@@ -612,32 +622,38 @@ head_bwd1_kernel(const __grid_constant__ CUtensorMap map_w2t, const __grid_const
     if (threadIdx.x == 0 && fail_s != 0u) colsum[0] = CUDART_NAN_F;
 }
 
-// backward 2: BatchNorm backward, dH = gamma rstd (dHn - mean(dHn) - Hhat mean(dHn Hhat)); dgamma, dbeta from the column sums
+// backward 2: BatchNorm backward, dH = gamma rstd (dHn - mean(dHn) - Hhat mean(dHn Hhat)) = a_c dHn + b_c H + d_c per column
+// (the three coefficients per column sit in shared memory; a pure 48 MB stream); dgamma, dbeta from the column sums
 __global__ void __launch_bounds__(256)
 head_bwd2_kernel(const uint16_t *__restrict__ dhn, const uint16_t *__restrict__ h, const float *__restrict__ colsum,
                  const float *__restrict__ gamma, const float *__restrict__ save_mean, const float *__restrict__ save_rstd,
                  uint16_t *__restrict__ dh_out, float *__restrict__ dgamma, float *__restrict__ dbeta, int64_t rows, int hidden,
                  int fp16)
 {
-    const int64_t total8 = rows * hidden / 8;
+    __shared__ float ca[1024], cb[1024], cd[1024];
     const float inv_r = 1.0f / (float)rows;
+    for (int c = threadIdx.x; c < hidden; c += blockDim.x) {
+        const float rstd = save_rstd[c], mean = save_mean[c], g = gamma[c];
+        const float m1 = colsum[c] * inv_r, m2 = colsum[hidden + c] * inv_r;
+        // Hhat = (H - mean) rstd
+        ca[c] = g * rstd;
+        cb[c] = -g * rstd * rstd * m2;
+        cd[c] = g * rstd * (mean * rstd * m2 - m1);
+    }
+    __syncthreads();
+    const int groups = hidden / 8;                       // 16-byte groups per row
+    const int64_t total8 = rows * groups;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c0 = (int)((i * 8) % hidden);
-        const uint4 qg = reinterpret_cast<const uint4 *>(dhn)[i], qh = reinterpret_cast<const uint4 *>(h)[i];
+        const int c0 = (int)(i % groups) * 8;
+        const uint4 qg = __ldcs(reinterpret_cast<const uint4 *>(dhn) + i), qh = __ldg(reinterpret_cast<const uint4 *>(h) + i);
         const uint32_t wg[4] = {qg.x, qg.y, qg.z, qg.w}, wh[4] = {qh.x, qh.y, qh.z, qh.w};
         uint32_t o[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            float r2[2];
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                const int c = c0 + 2 * u + hf;
-                const float rstd = __ldg(save_rstd + c);
-                const float hhat = (unpack16(wh[u], hf, fp16 != 0) - __ldg(save_mean + c)) * rstd;
-                const float m1 = __ldg(colsum + c) * inv_r, m2 = __ldg(colsum + hidden + c) * inv_r;
-                r2[hf] = __ldg(gamma + c) * rstd * (unpack16(wg[u], hf, fp16 != 0) - m1 - hhat * m2);
-            }
-            o[u] = pack16x2(r2[0], r2[1], fp16 != 0);
+            const int c = c0 + 2 * u;
+            const float r0 = fmaf(ca[c], unpack16(wg[u], 0, fp16 != 0), fmaf(cb[c], unpack16(wh[u], 0, fp16 != 0), cd[c]));
+            const float r1 = fmaf(ca[c + 1], unpack16(wg[u], 1, fp16 != 0), fmaf(cb[c + 1], unpack16(wh[u], 1, fp16 != 0), cd[c + 1]));
+            o[u] = pack16x2(r0, r1, fp16 != 0);
         }
         reinterpret_cast<uint4 *>(dh_out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }

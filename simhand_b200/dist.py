@@ -3,6 +3,10 @@
 One process per GPU (`torch.distributed`, NCCL over NVLink).  Every rank holds `n_local` samples of each
 view; the loss is the reference's loss on the concatenation of all local batches (global 2N samples).
 
+Three transports (run_step_sharded): "fused" (default: run_step_fused, the exchange rides in the kernels' heads and tails,
+csrc/smh_shard.cu), "peer" (the same exchange as separate push / barrier kernels) and "nccl".  EmulatedGroup runs all ranks
+of the fused step on one device (tests).  The collective pattern, spelled out for the NCCL transport --
+
 Per step and rank:
   1. all-gather of one packed buffer [z1 | z2 | joints1 | joints2] (the autograd transpose of step 5)
   2. smh_prep on the gathered batch, smh_mpjpe on this rank's share of the upper-triangular tiles
@@ -132,7 +136,9 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
     """Sharded step with the collectives done by the library over peer memory (NVLink): push-gather of the inputs,
     Dmax pushed by the MPJPE kernel's last CTA, partial row sums / gradient rows stored into the peers' partial
     buffers and reduced in rank order by their consumers; device-side barriers separate the phases.  No NCCL call
-    on the data path; the whole step is a fixed kernel sequence (CUDA-graph capturable) and bitwise reproducible."""
+    on the data path; the whole step is a fixed kernel sequence (CUDA-graph capturable).  The cross-rank sums are taken in
+    rank order (every rank returns the same loss bits); inside a rank the sweeps' strip flushes use floating-point atomics,
+    so a step is not bitwise reproducible from run to run (differences at the 1e-7 level)."""
     lib = _lib.load()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = z1.device

@@ -1,18 +1,22 @@
 #!/bin/bash
-# Round-end style scaling measurement on one 8-GPU box (run via `gpurun --gpus 8`): bench.py at N = 1, 2, 4, 8 back to
-# back, the sharded parity checks, the per-stage breakdown at N = 8 and the end-to-end example.  Outputs: gpurun_out/.
+# One 8-GPU box: sharded parity at full size, phase clocks, bench at 8 / 4 / 2 GPUs (fused exchange; the unfused one at 8 for
+# comparison).   gpurun --gpus 8 -- bash tools/scaling_run.sh
+run() { timeout "$1" python -m torch.distributed.run --nnodes=1 --nproc-per-node "$2" --master-addr 127.0.0.1 --master-port "$3" "${@:4}"; }
 mkdir -p gpurun_out
-run() { # N port
-  if [ "$1" = 1 ]; then timeout 300 python bench.py --gpus 1 > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err
-  else timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$1" --master-addr 127.0.0.1 --master-port "$2" \
-       bench.py --gpus "$1" > gpurun_out/scale_n$1.json 2> gpurun_out/scale_n$1.err; fi
-  echo "N=$1 rc=$?"; cut -c1-260 gpurun_out/scale_n$1.json
-}
-run 1 0; run 2 29701; run 4 29702; run 8 29703
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29704 \
-    tools/dist_check.py 8192 > gpurun_out/dist_check_n8.log 2>&1; grep -E "rank [0-9]/8" gpurun_out/dist_check_n8.log | head -16
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29705 \
-    tools/dist_profile.py > gpurun_out/dist_profile_n8.log 2>&1; grep -E "^rank 0" gpurun_out/dist_profile_n8.log
-timeout 300 python -m pytest tests/test_gpu_dist.py tests/test_gpu_e2e.py -m gpu -x -q > gpurun_out/dist_tests_n8.log 2>&1; tail -3 gpurun_out/dist_tests_n8.log
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29706 \
-    examples/e2e_step.py --batch 8192 --steps 5 > gpurun_out/e2e_n8.log 2>&1; grep -E "^\{" gpurun_out/e2e_n8.log | cut -c1-400
+run 300 8 29721 tools/dist_check.py 8192 fused 2>&1 | grep -E "rank|Error|error" | tee gpurun_out/r02_dist_check_n8.log
+run 200 8 29722 tools/shard_phase_times.py 2>&1 | grep -v "^\*\*\*\|OMP_NUM\|^$" | sed "s/\\\\n/\n/g" | tee gpurun_out/r02_phase_clocks_n8.txt
+for cfg in "8 fused" "8 peer" "4 fused" "2 fused"; do
+  set -- $cfg
+  run 300 $1 29723 bench.py --gpus $1 --steps 300 --warmup 5 --transport $2 > gpurun_out/r02_bench_n$1_$2.json 2> gpurun_out/r02_bench_n$1_$2.err
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/r02_bench_n$1_$2.json"))
+    print("n$1 $2", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "exact", round(d["exact_weights"]["value"], 1), d.get("kernels_ms"), d.get("clocks"))
+except Exception as e:
+    print("n$1 $2 FAILED", e)
+PY
+done
+timeout 300 python bench.py --steps 300 > gpurun_out/r02_bench_n1_box8.json 2>/dev/null
+python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_n1_box8.json')); print('n1', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'exact', round(d['exact_weights']['value'],1))"
