@@ -245,6 +245,13 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
  * step. */
 int smh_shard_prep(const smh_dims_t *dims, const smh_inputs_t *local_in, void *ws_dev, const smh_exchange_t *exch,
                    int engine, void *stream);
+/* OR into smh_shard_prep's engine: the operand images of z are NOT shipped by smh_shard_prep but by smh_shard_push_z, which
+ * the caller launches on a second stream right after smh_shard_prep (a parallel branch of the step's CUDA graph): its
+ * NVLink transfer (3/4 of the bytes a rank ships) then runs under the MPJPE kernel, which needs only the joints.  The
+ * forward sweep waits for it (stage 5); the caller joins the streams before smh_forward. */
+#define SMH_SHARD_PREP_NO_IMAGES 0x10000
+int smh_shard_push_z(const smh_dims_t *dims, const smh_inputs_t *local_in, void *ws_dev, const smh_exchange_t *exch,
+                     int engine, void *stream);
 
 /* peer exchange: pack this rank's local inputs (n_local samples per view, described like smh_inputs_t with
  * rank strides ignored) as [z1|z2|joints1|joints2] into slot `rank` of every peer's gathered-input buffer

@@ -24,6 +24,7 @@ UNIT_POS_WEIGHTS = 0x800
 DENSE_WEIGHTS = 0x2000
 FINALIZE_LOSS_PART = 0x4000
 FINALIZE_GRAD = 0x8000
+SHARD_PREP_NO_IMAGES = 0x10000
 DIMS_DENSE_WEIGHTS = 1
 DIMS_DENSE_BACKWARD = 2
 DIMS_Q16_TILES = 4
@@ -103,7 +104,7 @@ EXPORTS = ("smh_version", "smh_last_error", "smh_layout", "smh_plan_build", "smh
            "smh_forward", "smh_backward", "smh_finalize", "smh_weights_dense", "smh_l2norm_fwd",
            "smh_l2norm_bwd", "smh_selftest", "smh_tc_probe", "smh_tc_default_params", "smh_push_inputs",
            "smh_barrier", "smh_prep_zero", "smh_exchange_neg", "smh_exchange_dz", "smh_import_weights", "smh_transform_fwd", "smh_transform_bwd",
-           "smh_scale_grads", "smh_shard_prep", "smh_head_forward", "smh_head_backward")
+           "smh_scale_grads", "smh_shard_prep", "smh_shard_push_z", "smh_head_forward", "smh_head_backward")
 
 _lib = None
 
@@ -131,6 +132,7 @@ def load() -> ctypes.CDLL:
     lib.smh_push_inputs.argtypes = [px, pi, i32, i32, vp]
     lib.smh_barrier.argtypes = [px, vp]
     lib.smh_shard_prep.argtypes = [pd, pi, vp, px, ctypes.c_int, vp]
+    lib.smh_shard_push_z.argtypes = [pd, pi, vp, px, ctypes.c_int, vp]
     lib.smh_exchange_neg.argtypes = [pd, vp, px, vp]
     lib.smh_exchange_dz.argtypes = [pd, vp, px, vp]
     lib.smh_prep_zero.argtypes = [pd, vp, vp]

@@ -556,7 +556,9 @@ int smh_backward(const smh_dims_t *dims, const void *plan_dev, void *ws_dev, flo
     if ((rc = make_peers(*dims, lay, ws_dev, (exch && exch->fused) ? exch : nullptr, &xp))) return rc;
     // peer exchange: the row sums are the rank-ordered sum of the partials every rank delivered
     if (xp.fused) {
-        if ((rc = launch_rn_fused(lay, ws, xp, (engine & SMH_BACKWARD_RN_ONLY) != 0, st))) return rc;
+        // loss-only step: the row sums are reduced by a small kernel that also closes stage 4; otherwise the backward
+        // sweep's CTAs reduce them in its head (one launch less)
+        if ((engine & SMH_BACKWARD_RN_ONLY) && (rc = launch_rn_fused(lay, ws, xp, true, st))) return rc;
     } else if ((rc = launch_rn(lay, ws, exch ? dims->world : 1, st))) {
         return rc;
     }
@@ -637,11 +639,29 @@ int smh_shard_prep(const smh_dims_t *dims, const smh_inputs_t *local_in, void *w
         return set_error(SMH_E_ARG, "shard_prep: null input pointer");
     if (local_in->z_row_stride < dims->d) return set_error(SMH_E_ARG, "z_row_stride < d");
     if (dims->world < 2) return set_error(SMH_E_DIM, "shard_prep: world must be >= 2");
+    const int eng = engine & ~SMH_SHARD_PREP_NO_IMAGES;
+    if (eng != SMH_ENGINE_TC_TF32 && eng != SMH_ENGINE_TC_BF16 && eng != SMH_ENGINE_TC_FP16)
+        return set_error(SMH_E_MODE, "the fused exchange runs the tensor-core engines only (got %d)", eng);
+    Peers peers;
+    if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
+    return launch_shard_prep(*dims, lay, *local_in, engine, peers, st);
+}
+
+int smh_shard_push_z(const smh_dims_t *dims, const smh_inputs_t *local_in, void *ws_dev, const smh_exchange_t *exch,
+                     int engine, void *stream)
+{
+    const void *plan_dev = nullptr;
+    SMH_COMMON_PROLOGUE(false)
+    (void)plan_dev;
+    (void)ws;
+    if (!exch || !exch->fused) return set_error(SMH_E_ARG, "shard_push_z needs an exchange with fused = 1");
+    if (!local_in || !local_in->z1_dev || !local_in->z2_dev) return set_error(SMH_E_ARG, "shard_push_z: null input pointer");
+    if (local_in->z_row_stride < dims->d) return set_error(SMH_E_ARG, "z_row_stride < d");
     if (engine != SMH_ENGINE_TC_TF32 && engine != SMH_ENGINE_TC_BF16 && engine != SMH_ENGINE_TC_FP16)
         return set_error(SMH_E_MODE, "the fused exchange runs the tensor-core engines only (got %d)", engine);
     Peers peers;
     if ((rc = make_peers(*dims, lay, ws_dev, exch, &peers))) return rc;
-    return launch_shard_prep(*dims, lay, *local_in, engine, peers, st);
+    return launch_shard_push_z(*dims, lay, *local_in, engine, peers, st);
 }
 
 int smh_push_inputs(const smh_exchange_t *exch, const smh_inputs_t *local_in, int32_t n_local, int32_t d, void *stream)

@@ -49,6 +49,8 @@ int launch_sweep_tc(bool backward, int logit_format /* 0 tf32, 1 bf16, 2 fp16 */
                     float temperature, cudaStream_t stream);
 int launch_shard_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, int engine,
                       const Peers &peers, cudaStream_t stream);
+int launch_shard_push_z(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, int engine,
+                        const Peers &peers, cudaStream_t stream);
 int launch_rn_fused(const smh_layout_t &lay, const WsView &ws, const Peers &peers, bool signal4, cudaStream_t stream);
 int launch_finalize_fused(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, const WsView &ws,
                           int pos_mode, float temperature, float grad_scale, float *loss, float *dz1, float *dz2,

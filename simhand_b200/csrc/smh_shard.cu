@@ -33,6 +33,7 @@ struct ShardPrepArgs {
     int diff;
     long long off_zt, off_zb, off_zh, off_jp;
     long long zero_off, zero_bytes;   // local accumulators: [off_neg, off_posd)
+    int push_images;            // 0: smh_shard_push_z ships the z images on a parallel branch
 };
 
 __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__ ShardPrepArgs a, const __grid_constant__ Peers pe)
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
         }
         const uint2 b16 = make_uint2(pack_bf16x2(zv.x, zv.y), pack_bf16x2(zv.z, zv.w));
         const uint2 h16 = make_uint2(pack_f16x2(zv.x, zv.y), pack_f16x2(zv.z, zv.w));
+        const int images = a.push_images ? a.images : 0;
         // packed joints: lane L < 10 holds (x_2L, x_2L+1, y_2L, y_2L+1), lane 10 holds (x_20, y_20, 0, 0)
         float4 jq;
         {
@@ -122,9 +124,9 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
         const int64_t i_zt = zt_index(grow, 4 * lane), i_zb = zb_index(grow, 4 * lane);
         for (int p = 0; p < pe.world; ++p) {
             unsigned char *w8 = pe.ws[p];
-            if (a.images & 1) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(w8 + a.off_zt) + i_zt) = zv;
-            if (a.images & 2) *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(w8 + a.off_zb) + i_zb) = b16;
-            if (a.images & 4) *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(w8 + a.off_zh) + i_zb) = h16;
+            if (images & 1) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(w8 + a.off_zt) + i_zt) = zv;
+            if (images & 2) *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(w8 + a.off_zb) + i_zb) = b16;
+            if (images & 4) *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(w8 + a.off_zh) + i_zb) = h16;
             if (lane < 11) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(w8 + a.off_jp) + grow * kJP + 4 * lane) = jq;
         }
         // domain of the branch-free exact sqrt (as smh_prep.cu)
@@ -276,8 +278,74 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
     }
 }
 
-int launch_shard_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, int engine,
-                      const Peers &peers, cudaStream_t stream)
+// The z-image part of the all-gather on its own: own rows -> operand images of the engine -> every rank's workspace; the
+// rank's last block signals stage 5.  Launched on a second stream next to the MPJPE kernel (which needs only the joints):
+// the transfer, 3/4 of the bytes a rank ships per step, leaves the critical path.
+__global__ void __launch_bounds__(256)
+shard_push_z_kernel(const __grid_constant__ ShardPrepArgs a, const __grid_constant__ Peers pe)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    uint32_t *sig = pe.my_sig();
+    const uint32_t epoch = sig[kSigEpoch];                 // shard_prep of this step has completed (stream order)
+    const smh_inputs_t &in = a.in;
+    const int rows = 2 * a.n_local;
+    for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < rows; w += gridDim.x * wpb) {
+        const int v = w >= a.n_local ? 1 : 0;
+        const int kl = w - v * a.n_local;
+        const int64_t grow = (int64_t)v * a.n + (int64_t)pe.rank * a.n_local + kl;
+        const float *zp = (v ? in.z2_dev : in.z1_dev) + (int64_t)kl * in.z_row_stride;
+        float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = 4 * lane;
+        if (c + 3 < a.d && ((reinterpret_cast<uintptr_t>(zp + c) & 15) == 0)) {
+            zv = *reinterpret_cast<const float4 *>(zp + c);
+        } else {
+            if (c + 0 < a.d) zv.x = zp[c + 0];
+            if (c + 1 < a.d) zv.y = zp[c + 1];
+            if (c + 2 < a.d) zv.z = zp[c + 2];
+            if (c + 3 < a.d) zv.w = zp[c + 3];
+        }
+        if (a.round_tf32) {
+            zv.x = to_tf32(zv.x);
+            zv.y = to_tf32(zv.y);
+            zv.z = to_tf32(zv.z);
+            zv.w = to_tf32(zv.w);
+        }
+        const uint2 b16 = make_uint2(pack_bf16x2(zv.x, zv.y), pack_bf16x2(zv.z, zv.w));
+        const uint2 h16 = make_uint2(pack_f16x2(zv.x, zv.y), pack_f16x2(zv.z, zv.w));
+        const int64_t i_zt = zt_index(grow, 4 * lane), i_zb = zb_index(grow, 4 * lane);
+        for (int p = 0; p < pe.world; ++p) {
+            unsigned char *w8 = pe.ws[p];
+            if (a.images & 1) *reinterpret_cast<float4 *>(reinterpret_cast<float *>(w8 + a.off_zt) + i_zt) = zv;
+            if (a.images & 2) *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(w8 + a.off_zb) + i_zb) = b16;
+            if (a.images & 4) *reinterpret_cast<uint2 *>(reinterpret_cast<uint16_t *>(w8 + a.off_zh) + i_zb) = h16;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        block_release_fence();
+        const unsigned ticket = atomicAdd(sig + kSigTicketZ, 1u);
+        if (ticket == gridDim.x - 1) {
+            sig[kSigTicketZ] = 0u;
+            stage_signal(pe, kStageZ, epoch);
+        }
+    }
+}
+
+static ShardPrepArgs make_prep_args(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, int engine);
+
+int launch_shard_push_z(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, int engine,
+                        const Peers &peers, cudaStream_t stream)
+{
+    const ShardPrepArgs a = make_prep_args(dims, lay, in, engine);
+    // a modest grid: the kernel shares the SMs with the MPJPE kernel and is bound by NVLink, not by its own parallelism
+    int blocks = (2 * a.n_local + 7) / 8;
+    if (blocks > kNumCtas * 2) blocks = kNumCtas * 2;
+    shard_push_z_kernel<<<blocks, 256, 0, stream>>>(a, peers);
+    return check_launch("shard_push_z_kernel");
+}
+
+static ShardPrepArgs make_prep_args(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, int engine)
 {
     ShardPrepArgs a;
     a.in = in;
@@ -294,6 +362,16 @@ int launch_shard_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh
     a.off_jp = lay.off_jp;
     a.zero_off = lay.off_neg;
     a.zero_bytes = lay.off_posd - lay.off_neg;
+    a.push_images = 1;
+    return a;
+}
+
+int launch_shard_prep(const smh_dims_t &dims, const smh_layout_t &lay, const smh_inputs_t &in, int engine,
+                      const Peers &peers, cudaStream_t stream)
+{
+    const bool no_images = (engine & SMH_SHARD_PREP_NO_IMAGES) != 0;
+    ShardPrepArgs a = make_prep_args(dims, lay, in, engine & ~SMH_SHARD_PREP_NO_IMAGES);
+    a.push_images = no_images ? 0 : 1;
     int blocks = (2 * a.n_local + 7) / 8;
     if (blocks > kNumCtas * 8) blocks = kNumCtas * 8;
     shard_prep_kernel<<<blocks, 256, 0, stream>>>(a, peers);

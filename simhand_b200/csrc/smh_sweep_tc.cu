@@ -244,7 +244,7 @@ template <bool BWD, bool SBF16, bool Q16, bool FUSED>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const void *__restrict__ dist,
-                const float *__restrict__ rn, const __grid_constant__ Peers peers, const __grid_constant__ Peers xp, Stats *__restrict__ stats, int m, int n, int n_local,
+                float *__restrict__ rn, const __grid_constant__ Peers peers, const __grid_constant__ Peers xp, Stats *__restrict__ stats, int m, int n, int n_local,
                 float k2, float inv_k2, int wmode, float lambda_neg, uint32_t idesc1, long long *trace)
 {
     static_assert(!BWD || SBF16, "the backward sweep stages only the bf16 image");
@@ -308,9 +308,28 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     if (!FUSED) clk.dst = nullptr;
     if (FUSED) {
         epoch = xp.my_sig()[kSigEpoch];
-        if (!BWD) stage_wait(xp, 2, epoch);
+        if (!BWD) {
+            stage_wait(xp, 2, epoch);            // Dmax of every rank
+            stage_wait(xp, kStageZ, epoch);      // z images of every rank (shipped on a parallel branch under the MPJPE kernel)
+        } else {
+            // the row sums: neg_i = rank-ordered sum of the partials every rank delivered (stage 3), 1 / neg_i.  Every CTA
+            // reduces a slice, a grid barrier publishes the vector (this used to be a launch of its own)
+            stage_wait(xp, 3, epoch);
+            const int mp = ((m + kTile - 1) / kTile) * kTile;
+            float *neg_tot = xp.neg(xp.rank);
+            const float *parts = xp.negparts(xp.rank);
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < mp; i += gridDim.x * blockDim.x) {
+                float v = 0.f;
+                for (int p = 0; p < xp.world; ++p) v += __ldcg(parts + (int64_t)p * mp + i);
+                neg_tot[i] = v;
+                rn[i] = (i < m) ? __frcp_rn(v) : 0.f;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) grid_barrier(xp, epoch * 8u + 2u);       // tags grow: fwd tail 1, bwd head 2, bwd tail 3
+            __syncthreads();
+        }
         gs = xp.gstats(xp.rank, epoch);
-        clk.lap();                               // [0] stage wait
+        clk.lap();                               // [0] stage wait (+ row-sum reduction)
     }
 
     if (warp == 0) {
@@ -661,7 +680,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         // dzparts -- with plain 16-byte stores over NVLink; the rank's last CTA signals the stage.
         uint32_t *sig = xp.my_sig();
         clk.lap();                               // [1] this CTA's share of the sweep
-        if (threadIdx.x == 0) grid_barrier(xp, epoch * 8u + (BWD ? 2u : 1u));
+        if (threadIdx.x == 0) grid_barrier(xp, epoch * 8u + (BWD ? 3u : 1u));
         __syncthreads();
         clk.lap();                               // [2] every CTA of the rank has flushed
         if (!BWD) {

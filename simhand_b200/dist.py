@@ -197,10 +197,21 @@ def run_step_peer(z1, z2, joints1, joints2, temperature: float, engine: str, wan
     return loss, dz1, dz2
 
 
+_side_streams = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device)
+    return _side_streams[key]
+
+
 def _fused_launches(lib, ctx, exch_struct, ws_ptr, local, temperature, eng, want_grad, grad_scale, outs, st,
-                    pos_weighted=True, neg_weighted=True, stages=None):
-    """The six launches of one rank's fused step (smh_shard.cu).  `stages`: subset to issue (the single-GPU emulation
-    runs the ranks stage by stage)."""
+                    pos_weighted=True, neg_weighted=True, stages=None, overlap_push: bool = True):
+    """The launches of one rank's fused step (smh_shard.cu).  `stages`: subset to issue (the single-GPU emulation runs the
+    ranks stage by stage, on one stream).  overlap_push: the z images travel on a second stream next to the MPJPE kernel
+    (a parallel branch when the step is captured into a CUDA graph)."""
     dims = ctx.dims
     pd, pl, px = ctypes.byref(dims), ctypes.byref(local), ctypes.byref(exch_struct)
     plan = ctx.plan_dev.data_ptr()
@@ -209,7 +220,8 @@ def _fused_launches(lib, ctx, exch_struct, ws_ptr, local, temperature, eng, want
     sweep_eng = eng | (0 if neg_weighted else _lib.UNIT_NEG_WEIGHTS)
     fin_flags = 0 if pos_weighted else _lib.UNIT_POS_WEIGHTS
     table = {
-        "prep": lambda: check(lib.smh_shard_prep(pd, pl, ws_ptr, px, eng, st), "smh_shard_prep"),
+        "prep": lambda: check(lib.smh_shard_prep(pd, pl, ws_ptr, px, eng | _lib.SHARD_PREP_NO_IMAGES, st), "smh_shard_prep"),
+        "zpush": lambda: check(lib.smh_shard_push_z(pd, pl, ws_ptr, px, eng, st), "smh_shard_push_z"),
         "mpjpe": lambda: check(lib.smh_mpjpe(pd, plan, ws_ptr, px, st), "smh_mpjpe"),
         "fwd": lambda: check(lib.smh_forward(pd, plan, ws_ptr, temperature, sweep_eng, px, st), "smh_forward"),
         "bwd": lambda: check(lib.smh_backward(pd, plan, ws_ptr, temperature,
@@ -218,11 +230,25 @@ def _fused_launches(lib, ctx, exch_struct, ws_ptr, local, temperature, eng, want
                                               dz1.data_ptr() if want_grad else None, dz2.data_ptr() if want_grad else None,
                                               d, fin_flags, px, st), "smh_finalize"),
     }
+    if stages is None and overlap_push:
+        # prep -> { z push on the side stream | MPJPE on the main stream } -> join -> forward sweep ...
+        dev = ctx.device
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        table["prep"]()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            check(lib.smh_shard_push_z(pd, pl, ws_ptr, px, eng, side.cuda_stream), "smh_shard_push_z")
+        table["mpjpe"]()
+        main.wait_stream(side)
+        for name in ("fwd", "bwd", "fin"):
+            table[name]()
+        return
     for name in (stages or FUSED_STAGES):
         table[name]()
 
 
-FUSED_STAGES = ("prep", "mpjpe", "fwd", "bwd", "fin")
+FUSED_STAGES = ("prep", "zpush", "mpjpe", "fwd", "bwd", "fin")
 
 
 def run_step_fused(z1, z2, joints1, joints2, temperature: float, engine: str, want_grad: bool, group,
