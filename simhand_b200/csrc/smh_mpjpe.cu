@@ -32,25 +32,20 @@ __device__ __forceinline__ DistCtx dist_head(Stats *stats, const Peers &peers)
     c.gs = stats;
     if (FUSED) {
         c.epoch = peers.my_sig()[kSigEpoch];
+        PhaseClock clk(peers, 1);
         stage_wait(peers, 1, c.epoch);
+        clk.lap();                               // [0] stage wait
         c.gs = peers.gstats(peers.rank, c.epoch);
     }
     return c;
 }
 // thread 0 of every CTA, after the CTA's maximum went into stats->dmax_bits / stats->flags (rank-local)
-// persistent: the kernel pulls its work from stats->reserved, which the last CTA resets for the next launch
-__device__ __forceinline__ void dist_tail(Stats *stats, const Peers &peers, const DistCtx &c, bool signal2,
-                                          bool persistent = false)
+__device__ __forceinline__ void dist_tail(Stats *stats, const Peers &peers, const DistCtx &c, bool signal2)
 {
-    if (peers.world <= 1 && !persistent) return;
+    if (peers.world <= 1) return;
     __threadfence();
     const unsigned ticket = atomicAdd(&stats->ticket2, 1u);
     if (ticket != gridDim.x - 1) return;
-    if (persistent) stats->reserved = 0u;
-    if (peers.world <= 1) {
-        stats->ticket2 = 0u;
-        return;
-    }
     const uint32_t mine = atomicMax(&stats->dmax_bits, 0u);
     if (peers.fused) {
         const uint32_t fl = atomicOr(&stats->flags, 0u);
@@ -189,29 +184,25 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
     }
 }
 
-// A work item is one 128 / PARTS-column part of a stored tile: thread = row x (64 / PARTS) columns.
-//   dynamic = 0: one CTA per item (grid = items).  PARTS = 1 when the rank has many tiles; PARTS = 2 when it has few
-//                (sharded runs), so that the last wave of the resident CTAs is not mostly empty.
-//   dynamic = 1: one resident set of persistent CTAs (3 per SM for the 16-bit image, 2 for the exact form) pulls items from
-//                an atomic counter: no wave quantisation, and the cross-rank stage wait / ticket are paid once per resident
-//                CTA instead of once per item.  The price is one atomic round trip and an un-overlapped operand load per
-//                item, which only pays for short kernels (measured: profiles/r02_mpjpe_modes.txt).
-// The rank's last CTA resets the counter (and, with a peer exchange, ships Dmax: dist_tail).
-template <int PARTS, bool Q16, bool FUSED>
-__global__ void __launch_bounds__(256, Q16 ? 3 : 2)
-mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m, int n_tiles,
-             Stats *__restrict__ stats, const __grid_constant__ Peers peers, int signal2, int dynamic)
+// One work item = one 128 / PARTS-column part of a stored tile: thread = row x (64 / PARTS) columns.  Returns the block
+// maximum of the integer image of the item's values (of D, or of the 21-term sum for the 16-bit image); NaN sorts on top.
+template <int PARTS, bool Q16>
+__device__ __forceinline__ uint32_t mpjpe_item(const int2 *__restrict__ tiles, const float *__restrict__ jp,
+                                               void *__restrict__ dist, int m, int tile_id, int part, bool slow, float qscale,
+                                               float *cs, uint32_t *wmax)
 {
     constexpr int kCols = kTile / PARTS;              // columns staged per item
     constexpr int kPerThread = kCols / 2;
-    __shared__ __align__(16) float cs[kCols * kJP];
-    __shared__ uint32_t wmax[8];
-    __shared__ int item_s;
-    const DistCtx dc = dist_head<FUSED>(stats, peers);
-    const float qscale = Q16 ? q16_scale(__uint_as_float(dc.gs->dbound_bits)) * (1.0f / 21.0f) : 0.f;    // applied to the sum
-    const uint32_t flags = dc.gs->flags;
-    const bool slow = flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE);
-    const int n_items = n_tiles * PARTS;
+    const int cs0 = part * kCols;
+    const int col0 = cs0 + (threadIdx.x >> 7) * kPerThread;
+    const int2 ij = tiles[tile_id];
+    void *tile_out = reinterpret_cast<unsigned char *>(dist) + (int64_t)tile_id * kTileFloats * (Q16 ? 2 : 4);
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.y * kTile + cs0) * kJP);
+        float4 *dst = reinterpret_cast<float4 *>(cs);
+        for (int i = threadIdx.x; i < kCols * kJP / 4; i += 256) dst[i] = src[i];
+    }
+    __syncthreads();
     auto block_max = [&](uint32_t v) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -223,53 +214,53 @@ mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void 
         for (int w = 1; w < 8; ++w) v = max(v, wmax[w]);
         return v;
     };
-    __shared__ uint32_t cta_max_s, cta_bad_s;         // thread 0: maximum / non-finite flag over this CTA's items
-    if (threadIdx.x == 0) cta_max_s = cta_bad_s = 0u;
-    for (int round = 0;; ++round) {
-        __syncthreads();                              // the previous item's reads of cs / wmax / item_s are done
-        if (threadIdx.x == 0) item_s = dynamic ? (int)atomicAdd(&stats->reserved, 1u) : (round == 0 ? (int)blockIdx.x : n_items);
-        __syncthreads();
-        const int item = item_s;
-        if (item >= n_items) break;
-        const int tile_id = item / PARTS;
-        const int cs0 = (item % PARTS) * kCols;
-        const int col0 = cs0 + (threadIdx.x >> 7) * kPerThread;
-        const int2 ij = tiles[tile_id];
-        void *tile_out = reinterpret_cast<unsigned char *>(dist) + (int64_t)tile_id * kTileFloats * (Q16 ? 2 : 4);
-        {
-            const float4 *src = reinterpret_cast<const float4 *>(jp + ((int64_t)ij.y * kTile + cs0) * kJP);
-            float4 *dst = reinterpret_cast<float4 *>(cs);
-            for (int i = threadIdx.x; i < kCols * kJP / 4; i += 256) dst[i] = src[i];
-        }
-        __syncthreads();
-        uint32_t vmax_bits = 0u;
-        if (slow)
-            mpjpe_tile_body<0, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
-        else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
-            mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);   // zero distances
-        else
-            mpjpe_tile_body<2, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
-        uint32_t bmax = block_max(vmax_bits);
-        if (!slow && bmax > 0x7f800000u) {
-            // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo it guarded
-            vmax_bits = 0u;
-            mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
-            bmax = block_max(vmax_bits);
-        }
-        if (threadIdx.x == 0) {
-            if (bmax > 0x7f800000u)
-                cta_bad_s = 1u;                       // non-finite inputs (IEEE path): the loss is NaN
-            else
-                cta_max_s = max(cta_max_s, bmax);
-        }
+    uint32_t vmax_bits = 0u;
+    if (slow)
+        mpjpe_tile_body<0, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+    else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
+        mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);   // zero distances
+    else
+        mpjpe_tile_body<2, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+    uint32_t bmax = block_max(vmax_bits);
+    if (!slow && bmax > 0x7f800000u) {
+        // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo it guarded
+        vmax_bits = 0u;
+        mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+        bmax = block_max(vmax_bits);
+    }
+    return bmax;
+}
+
+// One CTA per work item.  The first n_full tiles (whole waves of the resident CTAs: 3 per SM for the 16-bit image, 2 for the
+// exact form) are full-tile items; the tiles of an under-filled last wave are cut in halves, two CTAs each, so that the SMs
+// are not left with a single CTA for the length of a full tile (a rank's 1032 tiles at 8 GPUs: 888 full + 144 x 2 halves).
+// Measured alternatives, all slower: half / quarter items throughout, and a persistent grid pulling items from an atomic
+// counter (profiles/r02_mpjpe_modes.txt) -- the per-item operand loads are not overlapped with the arithmetic.
+template <bool Q16, bool FUSED>
+__global__ void __launch_bounds__(256, Q16 ? 3 : 2)
+mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m, int n_full,
+             Stats *__restrict__ stats, const __grid_constant__ Peers peers, int signal2)
+{
+    __shared__ __align__(16) float cs[kTile * kJP];
+    __shared__ uint32_t wmax[8];
+    const DistCtx dc = dist_head<FUSED>(stats, peers);
+    const float qscale = Q16 ? q16_scale(__uint_as_float(dc.gs->dbound_bits)) * (1.0f / 21.0f) : 0.f;    // applied to the sum
+    const uint32_t flags = dc.gs->flags;
+    const bool slow = flags & (SMH_FLAG_SLOW_DOMAIN | SMH_FLAG_NONFINITE);
+    uint32_t bmax;
+    if ((int)blockIdx.x < n_full) {
+        bmax = mpjpe_item<1, Q16>(tiles, jp, dist, m, (int)blockIdx.x, 0, slow, qscale, cs, wmax);
+    } else {
+        const int j = (int)blockIdx.x - n_full;
+        bmax = mpjpe_item<2, Q16>(tiles, jp, dist, m, n_full + (j >> 1), j & 1, slow, qscale, cs, wmax);
     }
     if (threadIdx.x == 0) {
-        const uint32_t cta_max = cta_max_s;
-        if (cta_bad_s) atomicOr(&stats->flags, SMH_FLAG_NONFINITE);
-        if (cta_max != 0u)
-            atomicMax(&stats->dmax_bits, Q16 ? __float_as_uint(__fdiv_rn(__uint_as_float(cta_max), 21.0f)) : cta_max);
-        // last CTA: resets the work counter; fused all-reduce(MAX): pushes the rank's maximum into every peer's stats
-        dist_tail(stats, peers, dc, signal2 != 0, true);
+        if (bmax > 0x7f800000u)
+            atomicOr(&stats->flags, SMH_FLAG_NONFINITE);      // non-finite inputs (IEEE path): the loss is NaN
+        else
+            atomicMax(&stats->dmax_bits, Q16 ? __float_as_uint(__fdiv_rn(__uint_as_float(bmax), 21.0f)) : bmax);
+        // fused all-reduce(MAX): the last CTA of this rank pushes the rank's maximum into every peer's stats
+        dist_tail(stats, peers, dc, signal2 != 0);
     }
 }
 
@@ -441,27 +432,16 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
         else
             altdist_kernel<0><<<lay.n_stored_tiles, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, st, peers, signal2);
     } else {
-        // work-item size and scheduling: see mpjpe_kernel.  SMH_MPJPE_MODE = "<parts><s|d>" (e.g. "2s", "4d") overrides the
-        // choice for experiments.
+        // full-tile items for whole waves of the resident CTAs; an under-filled last wave (less than half) in half tiles
         const bool q16 = dims.flags & SMH_DIMS_Q16_TILES;
-        const bool small = lay.n_stored_tiles < 8 * 2 * kNumCtas;
-        // full-tile items, one CTA each, won every size measured (8256 / 4128 / 1032 tiles: profiles/r02_mpjpe_modes.txt);
-        // half-tile items only when there are too few tiles to fill the machine once
-        (void)small;
-        int parts = lay.n_stored_tiles < kNumCtas * (q16 ? 3 : 2) ? 2 : 1, dynamic = 0;
-        if (const char *mode = getenv("SMH_MPJPE_MODE")) {
-            if (mode[0] == '1' || mode[0] == '2') parts = mode[0] - '0';
-            if (mode[0] && (mode[1] == 'd' || mode[1] == 's')) dynamic = mode[1] == 'd';
-        }
         const int resident = kNumCtas * (q16 ? 3 : 2);
-        const int items = lay.n_stored_tiles * parts;
-        const int grid = dynamic ? (items < resident ? items : resident) : items;
-#define SMH_MPJPE(P, Q, F) mpjpe_kernel<P, Q, F><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, lay.n_stored_tiles, st, peers, signal2, dynamic)
-#define SMH_MPJPE_P(P)                                                                                     \
-        if (q16) { if (peers.fused) SMH_MPJPE(P, true, true); else SMH_MPJPE(P, true, false); }            \
-        else     { if (peers.fused) SMH_MPJPE(P, false, true); else SMH_MPJPE(P, false, false); }
-        if (parts == 1) { SMH_MPJPE_P(1) } else { SMH_MPJPE_P(2) }
-#undef SMH_MPJPE_P
+        const int rem = lay.n_stored_tiles % resident;
+        int n_full = (2 * rem <= resident) ? lay.n_stored_tiles - rem : lay.n_stored_tiles;
+        if (const char *mode = getenv("SMH_MPJPE_HALVES")) n_full = atoi(mode) ? n_full : lay.n_stored_tiles;   // experiments
+        const int grid = n_full + 2 * (lay.n_stored_tiles - n_full);
+#define SMH_MPJPE(Q, F) mpjpe_kernel<Q, F><<<grid, 256, 0, stream>>>(plan.tiles, ws.jp, ws.dist, lay.m, n_full, st, peers, signal2)
+        if (q16) { if (peers.fused) SMH_MPJPE(true, true); else SMH_MPJPE(true, false); }
+        else     { if (peers.fused) SMH_MPJPE(false, true); else SMH_MPJPE(false, false); }
 #undef SMH_MPJPE
     }
     int rc = check_launch(dims.diff_type != SMH_DIFF_MPJPE ? "altdist_kernel" : "mpjpe_kernel");

@@ -272,7 +272,6 @@ __global__ void __launch_bounds__(256) shard_prep_kernel(const __grid_constant__
             }
             sig[kSigEpoch] = epoch;
             stage_signal(pe, 1, epoch);
-            sig[kSigClock + 15] = (uint32_t)(global_ns() & 0xffffffffu);       // when the rank's stage 1 went out
         }
         clk.lap();                               // [4] block 0 done
     }
@@ -434,7 +433,9 @@ finalize_fused_kernel(smh_inputs_t in, int n, int d, const __grid_constant__ Pee
     const int wpb = blockDim.x >> 5;
     uint32_t *sig = pe.my_sig();
     const uint32_t epoch = sig[kSigEpoch];
+    PhaseClock clk(pe, 5);
     stage_wait(pe, 4, epoch);
+    clk.lap();                                   // [0] stage wait
     Stats *st = pe.stats(pe.rank);
     const Stats *gs = pe.gstats(pe.rank, epoch);
     const float *posd = pe.posinfo(pe.rank, epoch);

@@ -72,8 +72,45 @@ def main():
                 acc[stage] += evs[i].elapsed_time(evs[i + 1])
             clocks += ex.signal[160:160 + 96].cpu().view(torch.int32).to(torch.int64).bitwise_and(0xffffffff).double().view(6, 16)
     clocks /= iters
+    # the real step: one CUDA graph (z push on its parallel branch); intervals between the kernels' absolute start stamps
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            sd._fused_launches(lib, ctx, ex.struct, ex.ws.data_ptr(), local_in, 0.5, eng, True, 1.0, (loss, g1, g2),
+                               torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        gstep = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gstep, stream=side):
+            sd._fused_launches(lib, ctx, ex.struct, ex.ws.data_ptr(), local_in, 0.5, eng, True, 1.0, (loss, g1, g2),
+                               torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    order = [0, 1, 2, 4, 5]                     # prep, mpjpe, fwd, bwd, finalize
+    gaps = torch.zeros(len(order), dtype=torch.float64)
+    reps = 30
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for it in range(reps + 3):
+        if it == 3:
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+        gstep.replay()
+        gstep.replay()
+        torch.cuda.synchronize()
+        if it >= 3:
+            stamps = ex.signal[160:160 + 96].cpu().view(torch.int32).to(torch.int64).bitwise_and(0xffffffff).view(6, 16)[:, 15]
+            for i, k in enumerate(order):
+                nxt = order[(i + 1) % len(order)]
+                gaps[i] += float((int(stamps[nxt]) - int(stamps[k])) % (1 << 32))
+    e1.record()
+    torch.cuda.synchronize()
+    gaps /= reps * 1e3
+    step_us = e0.elapsed_time(e1) / (2 * reps) * 1e3
+    names5 = ["prep", "mpjpe", "fwd", "bwd", "fin"]
+    graph_line = " ".join(f"{n}->next {gaps[i]:.1f}us" for i, n in enumerate(names5))
     line = f"rank {rank}/{world} exact={int(exact)} poisoned={ex.poisoned()} | " + " ".join(
         f"{s} {acc[s] / iters * 1e3:.1f}us" for s in sd.FUSED_STAGES) + f" | total {sum(acc.values()) / iters * 1e3:.1f}us"
+    line += f"\n    whole-step graph (includes host sync every 2 steps): ~{step_us:.1f}us/step; start-to-start: {graph_line} (fin->next wraps to the next step's prep)"
     for k, (name, phases) in PHASES.items():
         line += f"\\n    {name}: " + " ".join(f"{p}@{clocks[k][i] / 1e3:.1f}us" for i, p in enumerate(phases))
     for r in range(world):
