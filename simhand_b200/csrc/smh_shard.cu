@@ -476,6 +476,7 @@ finalize_fused_kernel(smh_inputs_t in, int n, int d, const __grid_constant__ Pee
         const int k = row >= n ? row - n : row;
         rowloss[row] = logf(__ldcg(neg + row)) - __ldcg(dots + k) * pos_weight(k) * inv_tau;
     }
+    clk.lap();                                   // [1] loss rows
     // gradients of the OWN rows, one warp per row: rank-ordered sum of the delivered partials minus the positive term
     if (dz1 != nullptr) {
         for (int w = blockIdx.x * wpb + (threadIdx.x >> 5); w < 2 * n_local; w += gridDim.x * wpb) {
@@ -485,14 +486,39 @@ finalize_fused_kernel(smh_inputs_t in, int n, int d, const __grid_constant__ Pee
             const float *zp = (v ? in.z1_dev : in.z2_dev) + (int64_t)kl * in.z_row_stride;        // the partner's row
             const float *src = dzparts + (int64_t)w * kD;
             float *dst = (v ? dz2 : dz1) + (int64_t)kl * dz_row_stride;
-            for (int c = lane; c < d; c += 32) {
-                float acc = __ldcg(src + c);
-                for (int p = 1; p < pe.world; ++p) acc += __ldcg(src + (int64_t)p * part_stride + c);   // rank order
-                dst[c] = gsf * (acc - two_wp * zp[c]);
+            if (d == kD && ((reinterpret_cast<uintptr_t>(zp) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+                // one 16-byte load per partial and lane, four of them in flight before the first add; rank order
+                const float4 zq = *(reinterpret_cast<const float4 *>(zp) + lane);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int p0 = 0; p0 < pe.world; p0 += 4) {
+                    float4 part[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (p0 + q < pe.world)
+                            part[q] = __ldcg(reinterpret_cast<const float4 *>(src + (int64_t)(p0 + q) * part_stride) + lane);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (p0 + q < pe.world) {
+                            acc.x += part[q].x;
+                            acc.y += part[q].y;
+                            acc.z += part[q].z;
+                            acc.w += part[q].w;
+                        }
+                }
+                *(reinterpret_cast<float4 *>(dst) + lane) =
+                    make_float4(gsf * (acc.x - two_wp * zq.x), gsf * (acc.y - two_wp * zq.y), gsf * (acc.z - two_wp * zq.z),
+                                gsf * (acc.w - two_wp * zq.w));
+            } else {
+                for (int c = lane; c < d; c += 32) {
+                    float acc = __ldcg(src + c);
+                    for (int p = 1; p < pe.world; ++p) acc += __ldcg(src + (int64_t)p * part_stride + c);   // rank order
+                    dst[c] = gsf * (acc - two_wp * zp[c]);
+                }
             }
         }
     }
 
+    clk.lap();                                   // [2] own-row gradients
     // last block: the row terms in a fixed order (the same on every rank)
     __shared__ bool is_last;
     __threadfence();
@@ -539,7 +565,7 @@ int launch_finalize_fused(const smh_dims_t &dims, const smh_layout_t &lay, const
 {
     const int n_local = dims.n / dims.world;
     int blocks = std::max((lay.m + 255) / 256, (2 * n_local + 7) / 8);           // a thread per loss row, a warp per own row
-    if (blocks > 2 * kNumCtas) blocks = 2 * kNumCtas;
+    if (blocks > 4 * kNumCtas) blocks = 4 * kNumCtas;
     finalize_fused_kernel<<<blocks, 256, 0, stream>>>(in, dims.n, dims.d, peers, ws.neg, ws.rowloss, ws.dzparts, pos_mode,
                                                       dims.lambda_pos, 1.0f / temperature, grad_scale, loss, dz1, dz2,
                                                       dz_row_stride);

@@ -304,8 +304,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     // already waited for the row sums.  gs: the step's combined scalars.
     uint32_t epoch = 0u;
     const Stats *gs = stats;
-    PhaseClock clk(FUSED ? xp : peers, BWD ? 4 : 2);
-    if (!FUSED) clk.dst = nullptr;
+    PhaseClock clk(xp, BWD ? 4 : 2, FUSED);
     if (FUSED) {
         epoch = xp.my_sig()[kSigEpoch];
         if (!BWD) {

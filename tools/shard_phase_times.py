@@ -16,7 +16,9 @@ from simhand_b200 import dist as sd  # noqa: E402
 PHASES = {
     0: ("prep", ["issue", "pivot", "bound", "fence", "end"]),
     2: ("fwd", ["wait", "sweep", "gridbar", "copy", "fence"]),
-    4: ("bwd", ["-", "sweep", "gridbar", "copy", "fence"]),
+    4: ("bwd", ["head", "sweep", "gridbar", "copy", "fence"]),
+    1: ("mpjpe", ["wait"]),
+    5: ("fin", ["wait", "loss", "grads"]),
 }
 
 
@@ -99,18 +101,17 @@ def main():
         torch.cuda.synchronize()
         if it >= 3:
             stamps = ex.signal[160:160 + 96].cpu().view(torch.int32).to(torch.int64).bitwise_and(0xffffffff).view(6, 16)[:, 15]
-            for i, k in enumerate(order):
-                nxt = order[(i + 1) % len(order)]
-                gaps[i] += float((int(stamps[nxt]) - int(stamps[k])) % (1 << 32))
+            for i, k in enumerate(order[:-1]):
+                gaps[i] += float((int(stamps[order[i + 1]]) - int(stamps[k])) % (1 << 32))
     e1.record()
     torch.cuda.synchronize()
     gaps /= reps * 1e3
     step_us = e0.elapsed_time(e1) / (2 * reps) * 1e3
-    names5 = ["prep", "mpjpe", "fwd", "bwd", "fin"]
+    names5 = ["prep", "mpjpe", "fwd", "bwd"]
     graph_line = " ".join(f"{n}->next {gaps[i]:.1f}us" for i, n in enumerate(names5))
     line = f"rank {rank}/{world} exact={int(exact)} poisoned={ex.poisoned()} | " + " ".join(
         f"{s} {acc[s] / iters * 1e3:.1f}us" for s in sd.FUSED_STAGES) + f" | total {sum(acc.values()) / iters * 1e3:.1f}us"
-    line += f"\n    whole-step graph (includes host sync every 2 steps): ~{step_us:.1f}us/step; start-to-start: {graph_line} (fin->next wraps to the next step's prep)"
+    line += f"\n    whole-step graph (includes host sync every 2 steps): ~{step_us:.1f}us/step; start-to-start: {graph_line} "
     for k, (name, phases) in PHASES.items():
         line += f"\\n    {name}: " + " ".join(f"{p}@{clocks[k][i] / 1e3:.1f}us" for i, p in enumerate(phases))
     for r in range(world):
