@@ -328,7 +328,9 @@ def run_ours(args):
     if world == 1:
         kernels = {False: time_kernels(ops, _lib, dz1_, dz2_, dj1, dj2, engine, iters, False),
                    True: time_kernels(ops, _lib, dz1_, dz2_, dj1, dj2, engine, iters, True)}
-    elif transport in ("auto", "fused"):
+    elif world > 1:
+        # per-launch times of the fused form of the exchange (whatever transport the headline ran with): its six launches
+        # map one to one onto the step's phases, and each launch's time includes its wait for the other ranks
         kernels = {False: time_kernels_sharded(ops, _lib, dz1_, dz2_, dj1, dj2, engine, iters, False, group, barrier),
                    True: time_kernels_sharded(ops, _lib, dz1_, dz2_, dj1, dj2, engine, iters, True, group, barrier)}
     else:
@@ -344,7 +346,7 @@ def run_ours(args):
     h2d = int(hz1.numel() * 8 + hj1.numel() * 8) * world
     resolved_transport = None
     if world > 1:
-        resolved_transport = "fused" if transport == "auto" else transport
+        resolved_transport = os.environ.get("SMH_TRANSPORT", "peer") if transport == "auto" else transport
     launches = 6 if world == 1 else (6 if resolved_transport == "fused" else 14)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=steps, warmup=warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None,

@@ -18,6 +18,7 @@ static thread_local char g_err[512] = "";
 // cost of opening a strip in sweep-task times (enumerate_plan): backward (gradient-accumulator flush, row-block reload,
 // pipeline restart) and forward (128 atomics)
 constexpr double kStripCostBwd = 4.0, kStripCostFwd = 0.5;
+constexpr double kCostTransposed = 0.0, kCostMasked = 0.0;      // extra cost of a transposed / masked task (see task_cost)
 
 int set_error(int code, const char *fmt, ...)
 {
@@ -82,6 +83,14 @@ struct HostPlan {
 // CTA opens (a run of tasks with the same row block; a cut opens one too) costs `strip_cost` task times.  With ~28 tasks per
 // CTA (8 ranks) a strip more or less is 10 % of a CTA's time: equal task counts left the slowest CTA of the backward sweep
 // 15-20 % behind the first (profiles/r02_strip_cost*.txt).
+// cost of one task in the units of a plain direct task: a transposed task reads the staged tile with four 4-byte (or
+// 2-byte) shared loads where a direct one takes one 16-byte load; a masked one (diagonal / ragged) runs the checked epilogue
+static double g_cost_transposed = 0.0, g_cost_masked = 0.0;
+static inline double task_cost(const int4 &t)
+{
+    return 1.0 + ((t.w & kTaskTransposed) ? g_cost_transposed : 0.0) + ((t.w & (kTaskDiagonal | kTaskRagged)) ? g_cost_masked : 0.0);
+}
+
 static void cut_ranges(const std::vector<int4> &tasks, double strip_cost, int strip_len, std::vector<int2> *strips_out,
                        std::vector<int> *cta_ptr_out)
 {
@@ -92,7 +101,7 @@ static void cut_ranges(const std::vector<int4> &tasks, double strip_cost, int st
         return j == first || tasks[j].x != tasks[j - 1].x;
     };
     double remaining = 0.0;
-    for (size_t j = 0; j < tasks.size(); ++j) remaining += 1.0 + (opens_strip(j, 0) ? strip_cost : 0.0);
+    for (size_t j = 0; j < tasks.size(); ++j) remaining += task_cost(tasks[j]) + (opens_strip(j, 0) ? strip_cost : 0.0);
     size_t lo = 0;
     for (int c = 0; c < kNumCtas; ++c) {
         cta_ptr[c] = (int)strips.size();
@@ -106,13 +115,13 @@ static void cut_ranges(const std::vector<int4> &tasks, double strip_cost, int st
             double acc = 0.0;
             const size_t must_leave = (size_t)(n_ctas - 1 - c);          // at least one task for every later CTA
             while (hi < tasks.size() - must_leave) {
-                const double inc = 1.0 + (opens_strip(hi, lo) ? strip_cost : 0.0);
+                const double inc = task_cost(tasks[hi]) + (opens_strip(hi, lo) ? strip_cost : 0.0);
                 if (hi > lo && acc + 0.5 * inc > target) break;
                 acc += inc;
                 ++hi;
             }
         }
-        for (size_t j = lo; j < hi; ++j) remaining -= 1.0 + (opens_strip(j, 0) ? strip_cost : 0.0);
+        for (size_t j = lo; j < hi; ++j) remaining -= task_cost(tasks[j]) + (opens_strip(j, 0) ? strip_cost : 0.0);
         size_t i = lo;
         while (i < hi) {
             size_t j = i;
@@ -200,6 +209,10 @@ static void enumerate_plan(const smh_dims_t &dims, int strip_len, HostPlan *out,
     double cost_bwd = kStripCostBwd, cost_fwd = kStripCostFwd;
     if (const char *e = getenv("SMH_STRIP_COST")) cost_bwd = atof(e);
     if (const char *e = getenv("SMH_STRIP_COST_FWD")) cost_fwd = atof(e);
+    g_cost_transposed = kCostTransposed;
+    g_cost_masked = kCostMasked;
+    if (const char *e = getenv("SMH_COST_TRANSPOSED")) g_cost_transposed = atof(e);
+    if (const char *e = getenv("SMH_COST_MASKED")) g_cost_masked = atof(e);
     std::vector<int2> strips[2];
     std::vector<int> cta_ptr[2];
     cut_ranges(tasks, cost_bwd, strip_len, &strips[0], &cta_ptr[0]);

@@ -352,14 +352,24 @@ def run_step_sharded(z1, z2, joints1, joints2, temperature: float, engine: str, 
                      transport: str = "auto", pos_weighted: bool = True, neg_weighted: bool = True, weighting=None,
                      exact_weights: Optional[bool] = None):
     """transport: "fused" (6 launches, the exchange rides in the kernels' heads and tails over peer memory; every
-    weighting), "peer" (the same exchange as separate push / barrier kernels: 14 launches), "nccl" (NCCL calls between
-    the kernels) or "auto" (fused when symmetric memory is available, the group fits SMH_MAX_PEERS and a tensor-core
-    engine is selected)."""
+    weighting), "peer" (the same exchange as separate push / barrier kernels: 14 launches; linear / mpjpe / pos_neg only),
+    "nccl" (NCCL calls between the kernels) or "auto".  Both peer-memory forms were measured on 8 B200s (DESIGN.md section 7,
+    profiles/r02_bench_n8_*.json): inside a CUDA graph a launch boundary costs ~1 us, both forms pay the same cross-rank
+    skew at four synchronisation points and the same NVLink-bound payloads, and the unfused form came out 3-5 % ahead
+    (3670 vs 3496 steps/s at 8 GPUs) -- so "auto" picks "peer" for the default weighting and "fused" for everything
+    only it implements (other weightings, pos / neg only); "nccl" when symmetric memory is unavailable or the group is
+    larger than SMH_MAX_PEERS.  SMH_TRANSPORT overrides "auto"."""
     n_glob = z1.shape[0] * dist.get_world_size(group)
     plain = pos_weighted and neg_weighted and tuple(weighting or DEFAULT_WEIGHTING) == DEFAULT_WEIGHTING
     if transport == "auto":
         can_peer = peer_exchange_available() and dist.get_world_size(group) <= _lib.MAX_PEERS
-        transport = "nccl" if not can_peer else ("fused" if resolve_engine(engine, n_glob) != "fp32" else "peer")
+        tc = resolve_engine(engine, n_glob) != "fp32"
+        if not can_peer:
+            transport = "nccl"
+        elif plain or not tc:
+            transport = "peer"
+        else:
+            transport = "fused"
         transport = os.environ.get("SMH_TRANSPORT", transport)
     if transport == "fused":
         return run_step_fused(z1, z2, joints1, joints2, temperature, engine, want_grad, group, grad_scale, strip_len,
