@@ -8,8 +8,8 @@
 // stored tile directly for (I, J) and transposed for (J, I).  The global max (utils.py:255) is folded in
 // with an integer atomicMax (D >= 0).  The global min is the diagonal, +0 (utils.py:256).
 //
-// CUDA-core kernel: per ordered pair 21 MUFU.RSQ and ~190 FMA-pipe lane-operations; the packed
-// FADD2/FMUL2/FFMA2 forms halve the issue slots.  This is the kernel the roofline in bench.py is quoted on.
+// CUDA-core kernel: per pair 21 MUFU and ~190 FMA-pipe lane-operations; the packed FADD2/FMUL2/FFMA2 forms halve the
+// instruction count (not the dispatch cycles: see joint_pair).  This is the kernel the roofline in bench.py is quoted on.
 #include <cstdlib>
 
 #include "smh_common.cuh"
@@ -68,9 +68,36 @@ __device__ __forceinline__ void dist_tail(Stats *stats, const Peers &peers, cons
 // guard (a coincident joint gives NaN; the caller repairs that pair with MODE 1).
 // distances of joints (2p, 2p+1) of one pair of samples
 // APPROX (16-bit tile image only): one MUFU.SQRT per joint and no correction step -- the value is about to be rounded to
-// 16 bits, so the ~2^-22 relative error of the approximation is invisible, and sqrt(+0) = +0 needs no guard.  This takes
-// the two Newton FFMAs, the x * rsqrt(x) FMUL and the exponent decrement (3 of 8 FMA-pipe operations per joint) out of
-// the kernel: the XU pipe alone binds it.  The exact forms stay for the fp32 tiles (weights API, fp32 engine).
+// 16 bits, so the ~2^-22 relative error of the approximation is invisible, and sqrt(+0) = +0 needs no guard.  The exact
+// forms stay for the fp32 tiles (weights API, fp32 engine, exact_weights=True).
+//
+// What bounds the 16-bit-image kernel (ncu: profiles/r02_ncu_mpjpe_pipes.txt).  Per pair of samples and warp the XU pipe
+// needs 8 cycles per MUFU: 168 for 21 joints.  The rest of the pair (differences, squares, sums, 11 broadcast LDS) is ~100
+// instructions, half of them packed FADD2 / FMUL2 / FFMA2 -- and a packed instruction holds the SMSP's dispatch port for TWO
+// cycles (its pipe time, sm__pipe_fma_cycles_active, is exactly 2 x the packed count + the scalar count), so the pair costs
+// ~147 dispatch cycles.  The kernel runs at 190 cycles per pair and warp: XU 89 % busy, dispatch 75 %.
+// Bit p of kFmaSqrtMask (p = 0..9: joints 2p, 2p+1; bit 10: joint 20) sends that square root through sqrt2_fma_pipe (integer
+// seed + 6 packed FMA-pipe operations, +-7.2e-7 relative) instead of MUFU.SQRT: 8 XU cycles less, 9 dispatch cycles more per
+// joint.  The two limits cross between one and two joints; measured (profiles/r02_mpjpe_fma_sqrt.txt, 8256 tiles):
+// 0 joints 691 us, 2 joints 679 us, 3: 697, 4: 702, 5: 726, 6: 748, 8: 801.  With 4 joints moved ncu shows XU 71 %, FMA 67 %,
+// issue 62 % + the packed instructions once more = 90 % of the dispatch cycles: neither pipe binds any more, the port does.
+// Also measured, not faster: scalar FFMA for the moved joints (730 us), 2 CTAs per SM at 126 registers (689 / 680 us with 0 / 4
+// joints moved), two rows per thread sharing every LDS (mpjpe_tile_body_2r: 703 us -- the shared-memory instructions are
+// not what holds the MUFU queue back).
+#ifndef SMH_MPJPE_FMA_SQRT_MASK
+#define SMH_MPJPE_FMA_SQRT_MASK 0x040
+#endif
+constexpr unsigned kFmaSqrtMask = SMH_MPJPE_FMA_SQRT_MASK;
+#ifndef SMH_MPJPE_Q16_CTAS
+#define SMH_MPJPE_Q16_CTAS 3                    // resident CTAs per SM of the 16-bit-image form (80 registers)
+#endif
+#ifndef SMH_MPJPE_Q16_ROWS
+#define SMH_MPJPE_Q16_ROWS 1                    // rows per thread of the 16-bit-image form (2: mpjpe_tile_body_2r, needs 2 CTAs)
+#endif
+#ifndef SMH_MPJPE_EXACT_CTAS
+#define SMH_MPJPE_EXACT_CTAS 2                  // resident CTAs per SM of the exact form (124 registers)
+#endif
+
 template <int MODE, bool APPROX = false>
 __device__ __forceinline__ f2 joint_pair(const f2 ax, const f2 ay, const float *__restrict__ col, int p)
 {
@@ -79,6 +106,7 @@ __device__ __forceinline__ f2 joint_pair(const f2 ax, const f2 ay, const float *
     f2 dy = sub2(ay, pack2(b.z, b.w));
     f2 x = fma2(dy, dy, mul2(dx, dx));
     if (APPROX) {
+        if ((kFmaSqrtMask >> p) & 1u) return sqrt2_fma_pipe(x);
         float x0, x1;
         unpack2(x, x0, x1);
         return pack2(sqrt_approx(x0), sqrt_approx(x1));
@@ -100,6 +128,18 @@ __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10
 {
     constexpr bool FAST = MODE != 0;
     float a, b;
+    if (SUM) {
+        // the image is rounded to 16 bits: the ATen summation order buys nothing here, so the 21 terms are added as packed
+        // pairs (9 FADD2 + 2 FADD instead of 4 FADD2 + 14 FADD: the kernel is as much issue- as pipe-bound)
+        f2 acc = joint_pair<MODE, true>(ax[0], ay[0], col, 0);
+#pragma unroll
+        for (int p = 1; p < 10; ++p) acc = add2(acc, joint_pair<MODE, true>(ax[p], ay[p], col, p));
+        const float2 b20 = *reinterpret_cast<const float2 *>(col + 40);
+        const float dx20 = __fsub_rn(ax20, b20.x), dy20 = __fsub_rn(ay20, b20.y);
+        const float x20 = __fmaf_rn(dy20, dy20, __fmul_rn(dx20, dx20));
+        unpack2(acc, a, b);
+        return __fadd_rn(__fadd_rn(a, b), ((kFmaSqrtMask >> 10) & 1u) ? sqrt_fma_pipe(x20) : sqrt_approx(x20));
+    }
     unpack2(joint_pair<MODE, SUM>(ax[8], ay[8], col, 8), a, b);          // (n16, n17)
     float s = __fadd_rn(a, b);
     unpack2(joint_pair<MODE, SUM>(ax[9], ay[9], col, 9), a, b);          // (n18, n19)
@@ -184,6 +224,61 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
     }
 }
 
+// 16-bit image, two rows per thread (r and r + 64) x NCOLS columns: every broadcast LDS of a column's joints serves two pairs,
+// which halves the shared-memory instructions queued on the MIO path next to the MUFU.SQRT (ncu: mio_throttle is the top
+// stall of the one-row form).  84 registers of row data: 2 CTAs per SM.
+template <int NCOLS>
+__device__ __forceinline__ void mpjpe_tile_body_2r(const float *__restrict__ jp, void *__restrict__ tile_out, int I, int J,
+                                                   int m, const float *cs, int cs0, int col0, uint32_t &vmax_bits,
+                                                   float qscale)
+{
+    const int r = threadIdx.x & 63;
+    f2 ax[2][10], ay[2][10];
+    float ax20[2], ay20[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float4 *rowp = reinterpret_cast<const float4 *>(jp + ((int64_t)I * kTile + r + 64 * h) * kJP);
+#pragma unroll
+        for (int p = 0; p < 10; ++p) {
+            float4 v = rowp[p];
+            ax[h][p] = pack2(v.x, v.y);
+            ay[h][p] = pack2(v.z, v.w);
+        }
+        float4 v = rowp[10];
+        ax20[h] = v.x;
+        ay20[h] = v.y;
+    }
+    const DivConst div21 = make_div(21.0f);
+    const bool row_ok[2] = {(I * kTile + r) < m, (I * kTile + r + 64) < m};
+    const int col_limit = m - J * kTile;
+    uint2 qprev[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+#pragma unroll 1
+    for (int cq = 0; cq < NCOLS / 4; ++cq) {
+        const int c0 = col0 + cq * 4;
+        float dv[2][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float *col = cs + (c0 - cs0 + u) * kJP;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {          // same column pointer: the loads are shared between the two rows
+                dv[h][u] = mpjpe_one<2, true>(ax[h], ay[h], ax20[h], ay20[h], col, div21);
+                if (row_ok[h] && (c0 + u) < col_limit) vmax_bits = max(vmax_bits, __float_as_uint(dv[h][u]));
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t q[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) q[t] = __float_as_uint(__fmaf_rn(dv[h][t], qscale, 8388608.0f));
+            const uint2 pk = make_uint2(__byte_perm(q[0], q[1], 0x5410), __byte_perm(q[2], q[3], 0x5410));
+            if (cq & 1)
+                *reinterpret_cast<uint4 *>(reinterpret_cast<uint16_t *>(tile_out) + distq_index(r + 64 * h, c0 - 4)) =
+                    make_uint4(qprev[h].x, qprev[h].y, pk.x, pk.y);
+            qprev[h] = pk;
+        }
+    }
+}
+
 // One work item = one 128 / PARTS-column part of a stored tile: thread = row x (64 / PARTS) columns.  Returns the block
 // maximum of the integer image of the item's values (of D, or of the 21-term sum for the 16-bit image); NaN sorts on top.
 template <int PARTS, bool Q16>
@@ -215,6 +310,17 @@ __device__ __forceinline__ uint32_t mpjpe_item(const int2 *__restrict__ tiles, c
         return v;
     };
     uint32_t vmax_bits = 0u;
+    if (Q16 && SMH_MPJPE_Q16_ROWS == 2) {
+        constexpr int kPer2 = kCols / 4;              // thread = rows (r, r + 64) x a quarter of the item's columns
+        mpjpe_tile_body_2r<kPer2>(jp, tile_out, ij.x, ij.y, m, cs, cs0, cs0 + (threadIdx.x >> 6) * kPer2, vmax_bits, qscale);
+        return block_max(vmax_bits);
+    }
+    if (Q16) {
+        // one body: the approximate square roots take any input (sqrt(+0) = +0, non-finite values end up as NaN / inf in
+        // the maximum and flag the step), so neither the IEEE path nor the guarded redo exists for the 16-bit image
+        mpjpe_tile_body<2, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+        return block_max(vmax_bits);
+    }
     if (slow)
         mpjpe_tile_body<0, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
     else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
@@ -237,7 +343,7 @@ __device__ __forceinline__ uint32_t mpjpe_item(const int2 *__restrict__ tiles, c
 // Measured alternatives, all slower: half / quarter items throughout, and a persistent grid pulling items from an atomic
 // counter (profiles/r02_mpjpe_modes.txt) -- the per-item operand loads are not overlapped with the arithmetic.
 template <bool Q16, bool FUSED>
-__global__ void __launch_bounds__(256, Q16 ? 3 : 2)
+__global__ void __launch_bounds__(256, Q16 ? SMH_MPJPE_Q16_CTAS : SMH_MPJPE_EXACT_CTAS)
 mpjpe_kernel(const int2 *__restrict__ tiles, const float *__restrict__ jp, void *__restrict__ dist, int m, int n_full,
              Stats *__restrict__ stats, const __grid_constant__ Peers peers, int signal2)
 {
@@ -434,7 +540,7 @@ int launch_mpjpe(const smh_dims_t &dims, const smh_layout_t &lay, const PlanView
     } else {
         // full-tile items for whole waves of the resident CTAs; an under-filled last wave (less than half) in half tiles
         const bool q16 = dims.flags & SMH_DIMS_Q16_TILES;
-        const int resident = kNumCtas * (q16 ? 3 : 2);
+        const int resident = kNumCtas * (q16 ? SMH_MPJPE_Q16_CTAS : SMH_MPJPE_EXACT_CTAS);
         const int rem = lay.n_stored_tiles % resident;
         int n_full = (2 * rem <= resident) ? lay.n_stored_tiles - rem : lay.n_stored_tiles;
         if (const char *mode = getenv("SMH_MPJPE_HALVES")) n_full = atoi(mode) ? n_full : lay.n_stored_tiles;   // experiments

@@ -125,6 +125,36 @@ __global__ void selftest_divw(uint64_t *out)
     report(out, tested, bad, first, mx);
 }
 
+// 4: sqrt_fma_pipe / sqrt2_fma_pipe (the MUFU-free square root of the 16-bit tile image) against the correctly rounded
+// double sqrt for x = 0 and every float in [2^-101, FLT_MAX]: out[1] = values off by more than 7.5e-7 relative (or a
+// non-zero result for x = 0, or the two forms disagreeing), out[3] = largest relative error in units of 1e-9
+__global__ void selftest_sqrt_fma_pipe(uint64_t *out)
+{
+    const uint64_t lo = 0x0d000000ull, hi = 0x7f7fffffull;
+    uint64_t tested = 0, bad = 0, first = ~0ull, mx = 0;
+    for (uint64_t b = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= hi + 1; b += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = (b == hi + 1) ? 0.f : __uint_as_float((uint32_t)b);
+        const float a = sqrt_fma_pipe(x);
+        float p0, p1;
+        unpack2(sqrt2_fma_pipe(pack2(x, x)), p0, p1);
+        const double r = sqrt((double)x);
+        const double rel = r > 0.0 ? fabs((double)a - r) / r : (a == 0.f ? 0.0 : 1.0);
+        const uint64_t u = (uint64_t)(rel * 1e9);
+        ++tested;
+        if (u > mx) mx = u;
+        if (rel > 7.5e-7 || __float_as_uint(p0) != __float_as_uint(a) || __float_as_uint(p1) != __float_as_uint(a)) {
+            ++bad;
+            if (b < first) first = b;
+        }
+    }
+    if (tested) atomicAdd((unsigned long long *)&out[0], (unsigned long long)tested);
+    if (bad) {
+        atomicAdd((unsigned long long *)&out[1], (unsigned long long)bad);
+        atomicMin((unsigned long long *)&out[2], (unsigned long long)first);
+    }
+    atomicMax((unsigned long long *)&out[3], (unsigned long long)mx);
+}
+
 int launch_selftest(int which, uint64_t *out, int64_t out_words, cudaStream_t stream)
 {
     (void)out_words;
@@ -136,6 +166,7 @@ int launch_selftest(int which, uint64_t *out, int64_t out_words, cudaStream_t st
         case 1: selftest_sqrt2<<<148 * 16, 256, 0, stream>>>(out); break;
         case 2: selftest_div21<<<148 * 16, 256, 0, stream>>>(out); break;
         case 3: selftest_divw<<<148 * 16, 256, 0, stream>>>(out); break;
+        case 4: selftest_sqrt_fma_pipe<<<148 * 16, 256, 0, stream>>>(out); break;
         default: return set_error(SMH_E_MODE, "unknown selftest %d", which);
     }
     return check_launch("selftest");

@@ -45,6 +45,18 @@ def test_exact_math_selftests(which, name):
     assert bad == 0, f"{name}: {bad} mismatches of {tested}, first input bits {first:#x}, max {max_ulp} ulp"
 
 
+def test_fma_pipe_sqrt_selftest():
+    """The MUFU-free square root of the 16-bit tile image (sqrt2_fma_pipe) stays within 7.5e-7 relative of the true square
+    root for x = 0 and every float of the kernel's domain; packed and scalar forms agree bit for bit."""
+    lib = _lib.load()
+    out = torch.zeros(8, dtype=torch.int64, device=_dev())
+    _lib.check(lib.smh_selftest(4, out.data_ptr(), 8, torch.cuda.current_stream().cuda_stream), "sqrt_fma_pipe")
+    tested, bad, first, max_rel_e9 = out.cpu().tolist()[:4]
+    print(f"sqrt_fma_pipe: {tested} values, max relative error {max_rel_e9 * 1e-9:.3e}")
+    assert tested > 1_000_000_000
+    assert bad == 0, f"{bad} of {tested} outside the bound, first input bits {first:#x}, max rel {max_rel_e9 * 1e-9:.3e}"
+
+
 def test_weights_match_reference_bitwise(golden):
     z1, z2, a, b = _to_dev(golden)
     pos_w, neg_w = ops.mpjpe_weights(a, b)
