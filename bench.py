@@ -404,14 +404,17 @@ def run_ours(args):
                 achieved=executed, peak=xu_peak,
                 unit=("Gop/s per GPU: correctly rounded sqrt (MUFU.RSQ + Newton step on the FMA pipe), 21 per pair the launch evaluates"
                       if exact else
-                      "Gop/s per GPU: approximate sqrt (one MUFU.SQRT, no correction: relaxed-weights mode), 21 per pair the launch evaluates"),
-                frac=executed / xu_peak, traffic=(traffic or {}).get("bytes") if (world == 1 and not exact) else None,
+                      "Gop/s per GPU: approximate sqrt (relaxed-weights mode), 21 per pair the launch evaluates -- 19 of them one "
+                      "MUFU.SQRT each, 2 on the FMA pipe (sqrt2_fma_pipe)"),
+                frac=executed / xu_peak,
+                xu_pipe_frac=(executed if exact else executed * 19.0 / 21.0) / xu_peak, traffic=(traffic or {}).get("bytes") if (world == 1 and not exact) else None,
                 traffic_source=(traffic or {}).get("source") if (world == 1 and not exact) else None,
                 peak_source=src,
                 units_per_launch=f"{tiles:.0f} tiles x 16384 unordered pairs per rank (symmetry: D_ij == D_ji bitwise)",
                 algorithmic_frac=(21.0 * m * m / world / t_mpjpe / 1e9) / xu_peak,
                 step_frac=(22.0 * m * m / world / (step_ms * 1e-3) / 1e9) / xu_peak,
-                note="frac counts the sqrt the kernel executes.  algorithmic_frac counts 21 per ORDERED pair (M^2 / P per rank, "
+                note="frac counts the sqrt the kernel executes over the MUFU rate; xu_pipe_frac counts only those that are MUFU "
+                     "instructions (what ncu's sm__inst_executed_pipe_xu shows).  algorithmic_frac counts 21 per ORDERED pair (M^2 / P per rank, "
                      "as the reference evaluates them) over the same launch time and step_frac is SURVEY 8d's figure, "
                      "(21 sqrt + 1 exp) M^2 / (P x whole step time) over the MUFU peak: both exceed frac because symmetry "
                      "halves the executed count.")

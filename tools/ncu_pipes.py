@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Pipe / dispatch / stall summary of one kernel from `ncu --set full --import-source on` reports (read here with ncu -i).
 
-    python tools/ncu_pipes.py LABEL=report.ncu-rep [LABEL=report.ncu-rep ...] > profiles/rNN_ncu_..._pipes.txt
+    python tools/ncu_pipes.py LABEL=report.ncu-rep[@N] [LABEL=report.ncu-rep[@N] ...] > profiles/rNN_ncu_..._pipes.txt
 
 For every report: duration, pipe utilisation, instructions per warp, and the stall samples aggregated by opcode and reason
 (the source page), which is what tells a pipe-bound kernel from a dispatch-bound one."""
@@ -18,11 +18,16 @@ METRICS = ["gpu__time_duration.sum", "launch__registers_per_thread", "sm__warps_
            "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
            "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smsp__warps_eligible.avg.per_cycle_active",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
            "dram__bytes_read.sum", "dram__bytes_write.sum"]
 
 
 def page(rep, name):
-    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    sel = []
+    if "@" in rep:                         # report@N: the N-th kernel of a report with several
+        rep, n = rep.rsplit("@", 1)
+        sel = ["--launch-skip", n, "--launch-count", "1"]
+    out = subprocess.run(["ncu", "-i", rep, *sel, "--page", name, "--csv"], capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
@@ -42,6 +47,10 @@ def main():
         top = sorted(stalls.items(), key=lambda kv: -kv[1])[:7]
         print("   stalls per issue: " + ", ".join(f"{k} {v:.2f}" for k, v in top))
         src = page(rep, "source")
+        # one table per kernel: a "Kernel Name" row, a header row, then one row per instruction
+        starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"] + [len(src)]
+        want = int(rep.rsplit("@", 1)[1]) if "@" in rep and len(starts) > 2 else 0
+        src = src[starts[want]:starts[want + 1]]
         h = src[1]
         ix = {n: i for i, n in enumerate(h)}
         reasons = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
@@ -59,7 +68,7 @@ def main():
         print(f"   warp instructions executed {n_exec}, of them packed fp32x2 {packed} ({100.0 * packed / max(n_exec, 1):.1f} %): "
               f"dispatch cycles ~ executed + packed = {n_exec + packed}")
         print("   stall samples by opcode (share of all samples; top reasons):")
-        for op, n in samples.most_common(8):
+        for op, n in samples.most_common(14):
             rs = ", ".join(f"{k} {100.0 * x / total:.1f}" for k, x in by_op[op].most_common(4))
             print(f"      {op:12s} {100.0 * n / total:5.1f} %   executed {execd[op]:>11d}   {rs}")
 

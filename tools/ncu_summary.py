@@ -40,11 +40,27 @@ def launches(path):
         per.setdefault(short(r[4]), []).append(float(r[14]))
     print("== launch list: %s (%d launches; gpu__time_duration.sum, ns)" % (path, len(rows)))
     ours = {k: v for k, v in per.items() if not k.startswith("at::")}
-    step = sum(sum(v) / len(v) for v in ours.values())
-    for k, v in ours.items():
-        avg = sum(v) / len(v)
-        print("  %-28s n=%-3d avg %10.0f ns   share of step %5.1f %%" % (k, len(v), avg, 100 * avg / step))
-    print("  %-28s       sum %10.0f ns" % ("one step (serialised)", step))
+    # bench.py runs the step in both weight modes: kernels of the exact-weights step are the <.., 0, ..> (Q16 = false)
+    # instantiations of mpjpe_kernel<Q16, FUSED> / sweep_tc_kernel<BWD, SBF16, Q16, FUSED>; the small kernels are shared
+    def is_exact(k):
+        if k.startswith("mpjpe_kernel<"):
+            return k.split("<")[1].split(",")[0].strip() == "0"
+        if k.startswith("sweep_tc_kernel<"):
+            return k.split("<")[1].split(",")[2].strip() == "0"
+        return False
+    shared = {k: v for k, v in ours.items() if not k.startswith(("mpjpe_kernel<", "sweep_tc_kernel<"))}
+    for title, pick in (("relaxed-weights step (default)", lambda k: not is_exact(k)), ("exact-weights step", is_exact)):
+        mine = {k: v for k, v in ours.items() if k not in shared and pick(k)}
+        if not mine:
+            continue
+        group = dict(shared)
+        group.update(mine)
+        step = sum(sum(v) / len(v) for v in group.values())
+        print("  -- %s" % title)
+        for k, v in group.items():
+            avg = sum(v) / len(v)
+            print("  %-28s n=%-3d avg %10.0f ns   share of step %5.1f %%" % (k, len(v), avg, 100 * avg / step))
+        print("  %-28s       sum %10.0f ns" % ("one step (serialised)", step))
 
 
 def full(path):
