@@ -83,12 +83,14 @@ __device__ __forceinline__ void lds_f2x2(uint32_t addr, f2 &a, f2 &b)
 {
     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
-// one 16-bit fixed-point distance as the float 2^23 + q (the caller subtracts 2^23)
+// one 16-bit fixed-point distance as a float: LDS.U16 zero-extends, I2FP.F32.U32 converts on the integer pipe (one
+// instruction, where "or 2^23's exponent, then subtract 2^23" costs an integer instruction plus half a packed FADD2 = two
+// dispatch cycles: the sweeps are bound by the dispatch port)
 __device__ __forceinline__ float lds_q16(uint32_t addr)
 {
     uint32_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
-    return __uint_as_float(v | 0x4B000000u);
+    return __uint2float_rn(v);
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr)
 {
@@ -97,15 +99,6 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
     return v;
 }
 
-// The 32 columns [chunk * 32, chunk * 32 + 32) of one task for one row; v[] holds S on entry.
-//   forward : rowsum += E,  E = 2^(S * wk),  wk = W * k2 = k2 - D * (k2 / Dmax)      (one FFMA per weight)
-//   backward: pk[] = bf16x2 of G' = wk * E * (1/neg_i + 1/neg_j) = k2 * G; the strip flush multiplies by 1 / k2
-// The tensor-core engines do not need the correctly rounded W of the fp32 engine (the logits carry 2^-11 operand
-// rounding): the fused form is within 1 ulp of k2 in absolute terms.  Packed f32x2 arithmetic throughout.
-// negc2 = (-k2 / Dmax) x2, k2c2 = k2 x2.  Unit weights: negc2 = 0 and the tile is not read.  Materialised weights
-// (the tile holds W itself): negc2 = k2, k2c2 = 0, and, W not being symmetric in general, the backward visits a tile
-// once for the row term (cs2 = 0: G = W_ij E_ij / neg_i) and once transposed for the column term (rni = 0, cs2 = 1:
-// G = W_ji E_ji / neg_j).
 // The 32 columns [chunk * 32, chunk * 32 + 32) of one task for one row; v[] holds S on entry.
 //   forward : rowsum += E,  E = 2^(S * wk),  wk = W * k2 = k2 - D * (k2 / Dmax)      (one FFMA per weight)
 //   backward: pk[] = bf16x2 of G' = wk * E * (1/neg_i + 1/neg_j) = k2 * G; the strip flush multiplies by 1 / k2
@@ -179,8 +172,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
                 d01 = pack2(lds_f32(ta[k0] + off), lds_f32(ta[k0 + 1] + off));
                 d23 = pack2(lds_f32(ta[k0 + 2] + off), lds_f32(ta[k0 + 3] + off));
             } else {
-                d01 = sub2(pack2(lds_q16(ta[k0] + off), lds_q16(ta[k0 + 1] + off)), magic2);
-                d23 = sub2(pack2(lds_q16(ta[k0 + 2] + off), lds_q16(ta[k0 + 3] + off)), magic2);
+                d01 = pack2(lds_q16(ta[k0] + off), lds_q16(ta[k0 + 1] + off));
+                d23 = pack2(lds_q16(ta[k0 + 2] + off), lds_q16(ta[k0 + 3] + off));
             }
         }
         f2 wk01 = fma2(d01, negc2, k2c2), wk23 = fma2(d23, negc2, k2c2);
@@ -240,7 +233,9 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], uint32_t
 // else from the tf32 image `zt`.
 // FUSED: the exchange of the sharded step rides in this kernel's head and tail (smh_shard.cu); a separate instantiation, so
 // the single-GPU kernel carries none of it.
-template <bool BWD, bool SBF16, bool Q16, bool FUSED>
+// PLAIN: linear weights from the joints (wmode 0), the default; the other weightings (unit, materialised, non_linear) share
+// the !PLAIN instantiation and tell each other apart at run time.
+template <bool BWD, bool SBF16, bool Q16, bool FUSED, bool PLAIN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips, const int *__restrict__ cta_ptr,
                 const float *__restrict__ zt, const uint16_t *__restrict__ zb, const void *__restrict__ dist,
@@ -527,7 +522,11 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16);
         const float dmax = __uint_as_float(gs->dmax_bits);
         // wk = W * k2 = k2 - D * (k2 / Dmax)  (Dmin = +0, the diagonal); unit weights: wk = k2
-        const bool no_tile = wmode == 1, dense = wmode == 2, sigmoid = wmode == 3;
+        // Compile-time false for the default weighting: as run-time flags these three put a branch and two register-pair
+        // clears into every 4-element step of the epilogue (CS2R 0.53, BSSY + BSYNC 0.4 instructions per element in the ncu
+        // counts) -- on a kernel bound by the dispatch port: forward 146 -> 128 us, backward 206 -> 188 us at 2N = 16384.
+        static_assert(PLAIN || !Q16, "the 16-bit image exists for the linear weights from the joints only");
+        const bool no_tile = !PLAIN && wmode == 1, dense = !PLAIN && wmode == 2, sigmoid = !PLAIN && wmode == 3;
         float negc = no_tile ? 0.f : (dense ? k2 : -__fdiv_rn(k2, dmax));
         float addc = dense ? 0.f : k2;
         if (sigmoid) {
@@ -712,7 +711,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
     }
 }
 
-template <bool BWD, bool SBF16, bool Q16, bool FUSED>
+template <bool BWD, bool SBF16, bool Q16, bool FUSED, bool PLAIN>
 static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, const smh_dims_t &dims,
                       const smh_layout_t &lay, const PlanView &plan, const WsView &ws, const Peers &peers,
                       const Peers &xp, float temperature, cudaStream_t stream)
@@ -726,9 +725,9 @@ static int launch_one(int wmode, const uint16_t *half_image, uint32_t idesc1, co
     const float inv_k2 = (float)(0.6931471805599453 * (double)temperature);
     const int n_local = dims.n / dims.world;
     constexpr int smem = TcCfg<SBF16, Q16>::kSmem;
-    cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16, Q16, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(sweep_tc_kernel<BWD, SBF16, Q16, FUSED, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error((int)e, "tc sweep smem attr: %s", cudaGetErrorString(e));
-    sweep_tc_kernel<BWD, SBF16, Q16, FUSED><<<grid, kTcThreads, smem, stream>>>(plan.tasks, BWD ? plan.strips : plan.strips_fwd,
+    sweep_tc_kernel<BWD, SBF16, Q16, FUSED, PLAIN><<<grid, kTcThreads, smem, stream>>>(plan.tasks, BWD ? plan.strips : plan.strips_fwd,
                                                                    BWD ? plan.cta_ptr : plan.cta_ptr_fwd, ws.zt, half_image,
                                                                    ws.dist, ws.rn, peers, xp, (Stats *)ws.stats, lay.m,
                                                                    dims.n, n_local, k2, inv_k2, wmode, dims.lambda_neg, idesc1,
@@ -745,16 +744,17 @@ int launch_sweep_tc(bool backward, int logit_format, int wmode, const smh_dims_t
                    id_tf32 = umma_idesc_tf32(kTile, kTaskN, 0, 0);
     const bool q16 = dims.flags & SMH_DIMS_Q16_TILES;
     if (q16 && wmode != 0) return set_error(SMH_E_MODE, "SMH_DIMS_Q16_TILES: linear weights from the joints only");
-#define SMH_SWEEP(B, S, IMG, ID)                                                                                      \
-    (xp.fused ? (q16 ? launch_one<B, S, true, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)      \
-                     : launch_one<B, S, false, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream))    \
-              : (q16 ? launch_one<B, S, true, false>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)     \
-                     : launch_one<B, S, false, false>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)))
+#define SMH_SWEEP_F(B, S, F, IMG, ID)                                                                                  \
+    (q16 ? launch_one<B, S, true, F, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)                \
+         : (wmode == 0 ? launch_one<B, S, false, F, true>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream) \
+                       : launch_one<B, S, false, F, false>(wmode, IMG, ID, dims, lay, plan, ws, peers, xp, temperature, stream)))
+#define SMH_SWEEP(B, S, IMG, ID) (xp.fused ? SMH_SWEEP_F(B, S, true, IMG, ID) : SMH_SWEEP_F(B, S, false, IMG, ID))
     if (backward) return SMH_SWEEP(true, true, ws.zb, id_bf16);
     if (logit_format == 1) return SMH_SWEEP(false, true, ws.zb, id_bf16);
     if (logit_format == 2) return SMH_SWEEP(false, true, ws.zh, id_f16);
     return SMH_SWEEP(false, false, ws.zb, id_tf32);
 #undef SMH_SWEEP
+#undef SMH_SWEEP_F
 }
 
 }  // namespace smh
