@@ -418,12 +418,15 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         // control flow and every operand stay warp-uniform, see elect_one)
         {
             const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+            // descriptors = base + (byte offset / 16) in the start-address field (umma_desc_lo): one add per MMA operand
+            const uint32_t a_lo = umma_desc_lo(sA_u, 16), b_lo0 = umma_desc_lo(sB_u, 16), d_hi = umma_desc_hi_sw128(1024);
             uint32_t a_ph = 0;
             uint32_t seq = 0;                       // logit MMAs issued so far by this CTA
             TR_DECL(7);
             // logit contraction of task `seq` into S buffer seq % kSBufs (operands and buffer are known to be ready)
             auto mma1 = [&](bool last_of_strip) {
                 const uint32_t sb = seq % kSBufs, bst = seq % kBStages;
+                const uint32_t b_lo = b_lo0 + bst * (uint32_t)(kBBytes >> 4);
                 tc_fence_after();
                 if (elect_one()) {
                 if (SBF16) {
@@ -432,8 +435,8 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                     for (int db = 0; db < 2; ++db) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t adesc = umma_desc_sw128(sA_u + db * 16384 + ks * 32, 16, 1024);
-                            const uint64_t bdesc = umma_desc_sw128(sB_u + bst * kBBytes + db * 8192 + ks * 32, 16, 1024);
+                            const uint64_t adesc = umma_desc_pack(a_lo + (uint32_t)(db * (16384 >> 4) + ks * 2), d_hi);
+                            const uint64_t bdesc = umma_desc_pack(b_lo + (uint32_t)(db * (8192 >> 4) + ks * 2), d_hi);
                             tc_mma_ss_f16(tmem_base + sb * kTaskN, adesc, bdesc, idesc1, (db | ks) ? 1u : 0u);
                         }
                     }
@@ -443,8 +446,8 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                     for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t adesc = umma_desc_sw128(sA_u + kb * 16384 + ks * 32, 16, 1024);
-                            const uint64_t bdesc = umma_desc_sw128(sB_u + bst * kBBytes + kb * 8192 + ks * 32, 16, 1024);
+                            const uint64_t adesc = umma_desc_pack(a_lo + (uint32_t)(kb * (16384 >> 4) + ks * 2), d_hi);
+                            const uint64_t bdesc = umma_desc_pack(b_lo + (uint32_t)(kb * (8192 >> 4) + ks * 2), d_hi);
                             tc_mma_ss_tf32(tmem_base + sb * kTaskN, adesc, bdesc, idesc1, (kb | ks) ? 1u : 0u);
                         }
                     }
@@ -462,6 +465,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                     mbar_wait(&bars->a_full, a_ph, fail, 6);
                     TR_LAP(1);                                                      // [1] waiting for A
                     a_ph ^= 1u;
+#pragma unroll 1
                     for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
                         mbar_wait(&bars->full_b[seq % kBStages], (seq / kBStages) & 1u, fail, 7);
                         TR_LAP(2);                                                  // [2] waiting for the z block
@@ -482,12 +486,14 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
         // dependency between the two streams goes through an mbarrier, so they need no ordering between them.
         constexpr uint32_t idesc2 = umma_idesc_bf16(kTile, kD, 0, 1);
         const uint32_t sB_u = smem_u32(sB);
+        const uint32_t vb_lo0 = umma_desc_lo(sB_u, 8192), vd_hi = umma_desc_hi_sw128(1024);
         uint32_t q = 0;
         for (int s = s_begin; s < s_end; ++s) {
             const int2 strip = strips[s];
             // gradient accumulator of this strip: the epilogue drains the other one while this strip's MMAs run
             const uint32_t sk = (uint32_t)(s - s_begin), acc = sk & 1u;
             const uint32_t dz_tmem = tmem_base + kDzCol + acc * (uint32_t)kD;
+#pragma unroll 1
             for (int ti = strip.x; ti < strip.y; ++ti, ++q) {
                 const uint32_t sbq = q % kSBufs, bstq = q % kBStages;
                 const bool first = ti == strip.x, last = ti + 1 == strip.y;
@@ -500,7 +506,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                         // MN-major bf16 B: 64-element (128 B) atoms along d at LBO = 8 KiB, 8-row K groups at SBO = 1 KiB,
                         // 16 sample rows (2 KiB) per K step.  A = packed bf16 G: columns [0,16) hold task columns 0..31,
                         // columns [32,48) hold task columns 32..63 (each epilogue half overwrites its own S columns).
-                        const uint64_t bdesc = umma_desc_sw128(sB_u + bstq * kBBytes + ks * 2048, 8192, 1024);
+                        const uint64_t bdesc = umma_desc_pack(vb_lo0 + bstq * (uint32_t)(kBBytes >> 4) + (uint32_t)(ks * (2048 >> 4)), vd_hi);
                         const uint32_t a_col = (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u;
                         tc_mma_ts_f16(dz_tmem, tmem_base + sbq * kTaskN + a_col, bdesc, idesc2,
                                       (first && ks == 0) ? 0u : 1u);
@@ -547,7 +553,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             negc = qs > 0.f ? __fdiv_rn(negc, qs) : negc;
         }
         const f2 negc2 = pack2(negc, negc), k2c2 = pack2(addc, addc);
-        const uint32_t sD_s = smem_u32(sD);
+        const uint32_t sD_s = smem_u32(sD), task_slot_s = smem_u32(task_slot);
         uint32_t seq = 0;
         f2 rowsum[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
         // Backward: the flush of a strip's gradient accumulator is DEFERRED by one strip.  Waiting for the strip's last value
@@ -584,15 +590,19 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
             const int2 strip = strips[s];
             int row_block = -1;
             float rni = 0.f;
-            for (int ti = strip.x; ti < strip.y; ++ti, ++seq) {
-                if ((int)(seq & 1u) != group) continue;
+            // this group's tasks only: every other one, starting at the first whose sequence number has the group's parity
+            const uint32_t seq_end = seq + (uint32_t)(strip.y - strip.x);
+            for (seq += (seq ^ (uint32_t)group) & 1u; seq < seq_end; seq += 2) {
                 const uint32_t dst = seq % kDStages, sb = seq % kSBufs;
                 // fills of a stage seen by this group: every fill (even stage count) or every other one (odd)
                 const uint32_t my_fill = (kDStages & 1) ? (seq / kDStages) >> 1 : seq / kDStages;
                 TR_LAP(0);
                 mbar_wait(&bars->full_d[dst][group], my_fill & 1u, fail, 10);
                 TR_LAP(1);                                                          // [1] waiting for the tile
-                const int4 task = task_slot[dst];
+                int4 task;                            // the record travelling with the stage: one LDS.128 by shared address
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(task.x), "=r"(task.y), "=r"(task.z), "=r"(task.w)
+                             : "r"(task_slot_s + dst * 16u));
                 const int gi = task.x * kTile + r;
                 const bool row_ok = gi < m;
                 const int gj0 = task.y * kTaskN;
@@ -643,6 +653,7 @@ sweep_tc_kernel(const int4 *__restrict__ tasks, const int2 *__restrict__ strips,
                 TR_LAP(4);                                                          // [4] weights, exp, sums / G, arrive
                 TR_COUNT(6);
             }
+            seq = seq_end;
             TR_LAP(0);
             // strip flush: both groups hold partial results for the strip's row block
             const int gi = (row_block < 0 ? 0 : row_block) * kTile + r;
