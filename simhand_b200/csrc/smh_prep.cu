@@ -33,6 +33,9 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
     const int m = 2 * n;
     const bool has_joints = in.j1_dev != nullptr;         // optional on the materialised-weights path
     uint32_t bound_bits = 0u;                             // running max of D(row, sample 0) over this warp's rows
+    // positive-pair extrema of this warp's rows (lane 0): combined per block, two atomics per block instead of two per row
+    // (16384 atomics on two addresses serialised in the L2 were most of this kernel's time)
+    uint32_t pmax_w = 0u, pmin_inv_w = 0u;
     for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < mp; row += gridDim.x * warps_per_block) {
         float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
         float jx = 0.f, jy = 0.f;
@@ -151,22 +154,27 @@ __global__ void __launch_bounds__(256) prep_kernel(smh_inputs_t in, int n, int d
                 posd[k] = dk;
                 uint32_t b = __float_as_uint(dk);
                 if (b <= 0x7f800000u) {     // non-negative, not NaN
-                    atomicMax(&stats->pmax_bits, b);
-                    atomicMax(&stats->pmin_inv, 0x7fffffffu - b);
+                    pmax_w = max(pmax_w, b);
+                    pmin_inv_w = max(pmin_inv_w, 0x7fffffffu - b);
                 } else {
                     atomicOr(&stats->flags, SMH_FLAG_NONFINITE);
                 }
             }
         }
     }
-    // one atomic per block for the distance bound
-    __shared__ uint32_t wb[8];
-    if (lane == 0) wb[threadIdx.x >> 5] = bound_bits;
+    // one atomic per block and quantity (distance bound, positive-pair max, inverted positive-pair min; 0 = nothing seen)
+    __shared__ uint32_t wb[3][8];
+    if (lane == 0) {
+        wb[0][threadIdx.x >> 5] = bound_bits;
+        wb[1][threadIdx.x >> 5] = pmax_w;
+        wb[2][threadIdx.x >> 5] = pmin_inv_w;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t v = wb[0];
-        for (int w = 1; w < warps_per_block; ++w) v = max(v, wb[w]);
-        if (v != 0u) atomicMax(&stats->dbound_bits, v);
+    if (threadIdx.x < 3) {
+        uint32_t v = wb[threadIdx.x][0];
+        for (int w = 1; w < warps_per_block; ++w) v = max(v, wb[threadIdx.x][w]);
+        uint32_t *dst = threadIdx.x == 0 ? &stats->dbound_bits : (threadIdx.x == 1 ? &stats->pmax_bits : &stats->pmin_inv);
+        if (v != 0u) atomicMax(dst, v);
     }
 }
 
