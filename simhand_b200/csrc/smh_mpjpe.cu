@@ -98,13 +98,18 @@ constexpr unsigned kFmaSqrtMask = SMH_MPJPE_FMA_SQRT_MASK;
 #define SMH_MPJPE_EXACT_CTAS 2                  // resident CTAs per SM of the exact form (124 registers)
 #endif
 
-template <int MODE, bool APPROX = false>
-__device__ __forceinline__ f2 joint_pair(const f2 ax, const f2 ay, const float *__restrict__ col, int p)
+// squared distances of joints (2p, 2p+1) of one pair of samples
+__device__ __forceinline__ f2 joint_x(const f2 ax, const f2 ay, const float *__restrict__ col, int p)
 {
     const float4 b = *reinterpret_cast<const float4 *>(col + 4 * p);   // (bx_2p, bx_2p+1, by_2p, by_2p+1)
     f2 dx = sub2(ax, pack2(b.x, b.y));
     f2 dy = sub2(ay, pack2(b.z, b.w));
-    f2 x = fma2(dy, dy, mul2(dx, dx));
+    return fma2(dy, dy, mul2(dx, dx));
+}
+template <int MODE, bool APPROX = false>
+__device__ __forceinline__ f2 joint_pair(const f2 ax, const f2 ay, const float *__restrict__ col, int p)
+{
+    f2 x = joint_x(ax, ay, col, p);
     if (APPROX) {
         if ((kFmaSqrtMask >> p) & 1u) return sqrt2_fma_pipe(x);
         float x0, x1;
@@ -133,7 +138,12 @@ __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10
         // pairs (9 FADD2 + 2 FADD instead of 4 FADD2 + 14 FADD: the kernel is as much issue- as pipe-bound)
         f2 acc = joint_pair<MODE, true>(ax[0], ay[0], col, 0);
 #pragma unroll
-        for (int p = 1; p < 10; ++p) acc = add2(acc, joint_pair<MODE, true>(ax[p], ay[p], col, p));
+        for (int p = 1; p < 10; ++p) {
+            if ((kFmaSqrtMask >> p) & 1u)
+                acc = sqrt2_fma_pipe_acc(joint_x(ax[p], ay[p], col, p), acc);      // the sum rides on the chain's last FMA
+            else
+                acc = add2(acc, joint_pair<MODE, true>(ax[p], ay[p], col, p));
+        }
         const float2 b20 = *reinterpret_cast<const float2 *>(col + 40);
         const float dx20 = __fsub_rn(ax20, b20.x), dy20 = __fsub_rn(ay20, b20.y);
         const float x20 = __fmaf_rn(dy20, dy20, __fmul_rn(dx20, dx20));
@@ -169,7 +179,9 @@ __device__ __forceinline__ float mpjpe_one(const f2 (&ax)[10], const f2 (&ay)[10
 // Q16: the tile is stored as 16-bit fixed point q = round(D * qscale) = round(s * qscale / 21) (SMH_DIMS_Q16_TILES) and
 // vmax_bits tracks the exact fp32 sum s (the caller divides the tile maximum by 21).  The rounding to integer rides on
 // the FMA pipe: fma(s, qscale / 21, 2^23) has q in its low mantissa bits.
-template <int MODE, int UN, int NCOLS, bool Q16>
+// RAGGED: the tile reaches past row / column m (padding rows are zeros: their distances must not enter the maximum); a full
+// tile skips the per-column bounds test (a compare and a select per pair of a kernel bound by its dispatch port).
+template <int MODE, int UN, int NCOLS, bool Q16, bool RAGGED = true>
 __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, void *__restrict__ tile_out, int I,
                                                 int J, int m, const float *cs, int cs0, int col0,
                                                 uint32_t &vmax_bits, float qscale)
@@ -201,7 +213,7 @@ __device__ __forceinline__ void mpjpe_tile_body(const float *__restrict__ jp, vo
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             dv[u] = mpjpe_one<MODE, Q16>(ax, ay, ax20, ay20, cs + (c0 - cs0 + u) * kJP, div21);
-            if (row_ok && (c0 + u) < col_limit) vmax_bits = max(vmax_bits, __float_as_uint(dv[u]));
+            if (!RAGGED || (row_ok && (c0 + u) < col_limit)) vmax_bits = max(vmax_bits, __float_as_uint(dv[u]));
         }
 #pragma unroll
         for (int u = 0; u < UN; u += 4) {
@@ -318,15 +330,19 @@ __device__ __forceinline__ uint32_t mpjpe_item(const int2 *__restrict__ tiles, c
     if (Q16) {
         // one body: the approximate square roots take any input (sqrt(+0) = +0, non-finite values end up as NaN / inf in
         // the maximum and flag the step), so neither the IEEE path nor the guarded redo exists for the 16-bit image
-        mpjpe_tile_body<2, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+        if ((ij.y + 1) * kTile > m || (ij.x + 1) * kTile > m)
+            mpjpe_tile_body<2, 4, kPerThread, Q16, true>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+        else
+            mpjpe_tile_body<2, 4, kPerThread, Q16, false>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
         return block_max(vmax_bits);
     }
     if (slow)
         mpjpe_tile_body<0, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
-    else if (ij.x == ij.y || (ij.y + 1) * kTile > m)
+    else if (ij.x == ij.y || (ij.y + 1) * kTile > m || (ij.x + 1) * kTile > m)
         mpjpe_tile_body<1, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);   // zero distances
-    else
-        mpjpe_tile_body<2, 4, kPerThread, Q16>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
+    else            // off the diagonal and inside m in both directions (measured: dropping the bounds test here, as the 16-bit
+                    // form does, is 1 % slower -- 928 vs 917 us -- the exact form schedules better with it)
+        mpjpe_tile_body<2, 4, kPerThread, Q16, true>(jp, tile_out, ij.x, ij.y, m, cs, cs0, col0, vmax_bits, qscale);
     uint32_t bmax = block_max(vmax_bits);
     if (!slow && bmax > 0x7f800000u) {
         // a coincident joint in an off-diagonal tile: the unguarded form produced NaN somewhere; redo it guarded

@@ -126,7 +126,8 @@ __global__ void selftest_divw(uint64_t *out)
 }
 
 // 4: sqrt_fma_pipe / sqrt2_fma_pipe (the MUFU-free square root of the 16-bit tile image) against the correctly rounded
-// double sqrt for x = 0 and every float in [2^-101, FLT_MAX]: out[1] = values off by more than 7.5e-7 relative (or a
+// double sqrt for x = 0 and every float in [2^-101, FLT_MAX]: out[1] = values off by more than 7.5e-7 relative (8.0e-7 for
+// the accumulating form sqrt2_fma_pipe_acc; or a
 // non-zero result for x = 0, or the two forms disagreeing), out[3] = largest relative error in units of 1e-9
 __global__ void selftest_sqrt_fma_pipe(uint64_t *out)
 {
@@ -135,14 +136,17 @@ __global__ void selftest_sqrt_fma_pipe(uint64_t *out)
     for (uint64_t b = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= hi + 1; b += (uint64_t)gridDim.x * blockDim.x) {
         const float x = (b == hi + 1) ? 0.f : __uint_as_float((uint32_t)b);
         const float a = sqrt_fma_pipe(x);
-        float p0, p1;
+        float p0, p1, q0, q1;
         unpack2(sqrt2_fma_pipe(pack2(x, x)), p0, p1);
+        unpack2(sqrt2_fma_pipe_acc(pack2(x, x), pack2(0.f, 0.f)), q0, q1);        // the accumulating form, same bound
         const double r = sqrt((double)x);
         const double rel = r > 0.0 ? fabs((double)a - r) / r : (a == 0.f ? 0.0 : 1.0);
         const uint64_t u = (uint64_t)(rel * 1e9);
         ++tested;
         if (u > mx) mx = u;
-        if (rel > 7.5e-7 || __float_as_uint(p0) != __float_as_uint(a) || __float_as_uint(p1) != __float_as_uint(a)) {
+        const double relq = r > 0.0 ? fabs((double)q0 - r) / r : (q0 == 0.f ? 0.0 : 1.0);
+        if (rel > 7.5e-7 || relq > 8.0e-7 || q0 != q1 || __float_as_uint(p0) != __float_as_uint(a) ||
+            __float_as_uint(p1) != __float_as_uint(a)) {
             ++bad;
             if (b < first) first = b;
         }

@@ -39,6 +39,37 @@ def model_sqrt_fma_pipe(x):
     return _fma(g, r, g)
 
 
+def model_sqrt_fma_pipe_acc(x, acc):
+    """sqrt2_fma_pipe_acc: the last step takes the running sum as its addend (r' = 1 + r from the constant 1 + c2)."""
+    magic, c1, c2 = _constants()
+    x = np.ascontiguousarray(x, dtype=f32)
+    s = x.view(np.uint32) >> np.uint32(1)
+    y = (np.uint32(magic) - s).view(f32)
+    nh = (np.uint32((magic + 0x7F800000) & 0xFFFFFFFF) - s).view(f32)
+    g = x * y
+    r = _fma(g, nh, np.full_like(x, c1))
+    g = _fma(g, r, g)
+    nh = _fma(nh, r, nh)
+    r = _fma(g, nh, np.full_like(x, f32(1.0) + c2))
+    return _fma(g, r, np.ascontiguousarray(acc, dtype=f32))
+
+
+def test_accumulating_form_bound():
+    bits = np.arange(0x3F800000, 0x40800000, 3, dtype=np.uint32)
+    x = np.concatenate([bits.view(f32), np.exp2(np.random.default_rng(2).uniform(-100, 126, 1_000_000)).astype(f32)])
+    with np.errstate(over="ignore"):
+        g = model_sqrt_fma_pipe_acc(x, np.zeros_like(x))
+    ref = np.sqrt(x.astype(np.float64))
+    rel = (g.astype(np.float64) - ref) / ref
+    assert np.abs(rel).max() < 8.0e-7, np.abs(rel).max()
+    assert abs(rel.mean()) < 2e-7
+    # with a running sum: acc + sqrt(x) to fp32 rounding of the sum
+    acc = np.full_like(x[:1000], 123.456)
+    out = model_sqrt_fma_pipe_acc(x[:1000], acc)
+    want = acc.astype(np.float64) + np.sqrt(x[:1000].astype(np.float64))
+    assert np.abs(out - want).max() <= 1.2e-7 * np.abs(want).max() + 8e-7 * np.sqrt(x[:1000]).max()
+
+
 def test_negated_half_seed_is_exact():
     magic, _, _ = _constants()
     x = np.random.default_rng(0).uniform(1e-12, 1e12, 100000).astype(f32)
