@@ -47,16 +47,19 @@ def main():
         top = sorted(stalls.items(), key=lambda kv: -kv[1])[:7]
         print("   stalls per issue: " + ", ".join(f"{k} {v:.2f}" for k, v in top))
         src = page(rep, "source")
-        # one table per kernel: a "Kernel Name" row, a header row, then one row per instruction
+        # a "Kernel Name" row, a header row, then one row per instruction; a kernel can come with a second, identical table
+        # (another view of the same code): the first table of the kernel the raw page names is used.
+        norm = lambda n: re.sub(r"\(bool\)|smh::|\s", "", n).split("(")[0]  # noqa: E731
         starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"] + [len(src)]
-        want = int(rep.rsplit("@", 1)[1]) if "@" in rep and len(starts) > 2 else 0
-        src = src[starts[want]:starts[want + 1]]
-        h = src[1]
+        mine = [(a, b) for a, b in zip(starts[:-1], starts[1:]) if norm(src[a][1]) == norm(d.get("Kernel Name", ""))]
+        mine = mine[:1] if mine else [(starts[0], starts[1])]
+        h = src[mine[0][0] + 1]
         ix = {n: i for i, n in enumerate(h)}
+        src = [r for a, b in mine for r in src[a:b]]
         reasons = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
         samples, by_op, execd = collections.Counter(), collections.defaultdict(collections.Counter), collections.Counter()
-        for r in src[2:]:
-            if len(r) < len(h) or not r[ix["Source"]].strip():
+        for r in src:
+            if len(r) < len(h) or not r[ix["Source"]].strip() or r[ix["# Samples"]] == "# Samples":
                 continue
             op = re.sub(r"^@!?U?P\d\s+", "", r[ix["Source"]].strip()).split()[0]
             samples[op] += int(r[ix["# Samples"]] or 0)

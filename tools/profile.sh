@@ -13,6 +13,6 @@ ncu --set full --clock-control none --import-source on -k regex:"mpjpe_kernel|sw
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
     -k regex:"mpjpe_kernel<(\(bool\))?0|sweep_tc_kernel<(\(bool\))?[01], (\(bool\))?1, (\(bool\))?0" -c 3 \
     -o gpurun_out/r02_prof_exact -f python bench.py --steps 2 --warmup 3 > gpurun_out/r02_ncu_full_bench_exact.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"head_" -s 8 -c 4 \
+[ -n "$SKIP_HEAD" ] || ncu --set full --clock-control none --import-source on -k regex:"head_" -s 8 -c 4 \
     -o gpurun_out/r02_prof_head -f python tools/bench_head.py > gpurun_out/r02_ncu_full_head.log 2>&1
 ls -la gpurun_out | tail -20
