@@ -353,8 +353,10 @@ typedef struct smh_head_bwd {
 int smh_head_forward(const smh_head_t *head, void *stream);
 int smh_head_backward(const smh_head_t *head, const smh_head_bwd_t *bwd, void *stream);
 
-/* device self-tests used by tests/ (exhaustive exact-sqrt / exact-division checks, tcgen05 tile
- * checks).  out_dev receives test-specific counters. */
+/* device self-tests used by tests/.  out_dev receives out[0] = values tested, out[1] = failures, out[2] = first failing input
+ * bits, out[3] = worst case.  which: 0 exact sqrt, 1 packed exact sqrt, 2 exact x / 21, 3 exact weight division (out[3] in
+ * ulp, all against the IEEE intrinsics over the whole domain); 4 the MUFU-free square root of the 16-bit tile image against
+ * the double-precision sqrt (bound 7.5e-7 relative, 8.0e-7 for the accumulating form; out[3] in units of 1e-9). */
 int smh_selftest(int which, uint64_t *out_dev, int64_t out_words, void *stream);
 
 /* diagnostic: one tcgen05 tile S = A B^T (tf32) and dZ = bf16(S) Z_B (bf16 value operand, MN-major) on staged
