@@ -40,7 +40,9 @@ def _ncu_traffic(kernel: str):
     profiles/ (tools/ncu_summary.py output of a `ncu --set full` capture of this same command); None if absent."""
     import glob
     import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_summary*.txt")), key=os.path.getmtime)
+    # by name, newest round first (file times mean nothing after a checkout); `kernel` carries the template argument that
+    # tells the 16-bit-image instantiation ("mpjpe_kernel<1,") from the exact one ("mpjpe_kernel<0,")
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_summary*.txt")))
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for path in reversed(files):
         total, inside, found = 0.0, False, 0
@@ -396,7 +398,7 @@ def run_ours(args):
                 xu_peak = xu_nominal
                 src = f"nominal: 148 SMs x 16 MUFU lanes/clk x {f_clk:.0f} MHz (median SM clock under load)"
             t_mpjpe = kern["mpjpe_kernel"] * 1e-3
-            traffic = _ncu_traffic("mpjpe_kernel")
+            traffic = _ncu_traffic("mpjpe_kernel<0," if exact else "mpjpe_kernel<1,")
             executed = 21.0 * tiles * 128 * 128 / t_mpjpe / 1e9            # sqrt one rank's launch evaluates / its duration
             step_ms = (ms_exact if exact else ms_total) / steps
             return dict(
@@ -407,8 +409,9 @@ def run_ours(args):
                       "Gop/s per GPU: approximate sqrt (relaxed-weights mode), 21 per pair the launch evaluates -- 19 of them one "
                       "MUFU.SQRT each, 2 on the FMA pipe (sqrt2_fma_pipe)"),
                 frac=executed / xu_peak,
-                xu_pipe_frac=(executed if exact else executed * 19.0 / 21.0) / xu_peak, traffic=(traffic or {}).get("bytes") if (world == 1 and not exact) else None,
-                traffic_source=(traffic or {}).get("source") if (world == 1 and not exact) else None,
+                xu_pipe_frac=(executed if exact else executed * 19.0 / 21.0) / xu_peak,
+                traffic=(traffic or {}).get("bytes") if world == 1 else None,
+                traffic_source=(traffic or {}).get("source") if world == 1 else None,
                 peak_source=src,
                 units_per_launch=f"{tiles:.0f} tiles x 16384 unordered pairs per rank (symmetry: D_ij == D_ji bitwise)",
                 algorithmic_frac=(21.0 * m * m / world / t_mpjpe / 1e9) / xu_peak,
