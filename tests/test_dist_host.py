@@ -109,3 +109,20 @@ def test_host_pipeline_and_step_flags_without_gpu(monkeypatch):
         ops.make_weighting("cubic", "mpjpe")
     with pytest.raises(ValueError):
         ops.make_weighting("linear", "l1")
+
+
+def test_bench_reads_ncu_traffic_of_the_right_instantiation():
+    """bench.py's roofline.traffic comes from the committed ncu summaries: the 16-bit-image kernel and the exact kernel are
+    told apart by their template argument, whatever the files' times are after a checkout."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("smh_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    relaxed, exact = bench._ncu_traffic("mpjpe_kernel<1,"), bench._ncu_traffic("mpjpe_kernel<0,")
+    assert relaxed and exact
+    assert relaxed["source"].endswith("r02_ncu_summary.txt") and exact["source"].endswith("r02_ncu_summary_exact.txt")
+    # 8256 tiles of 32 KiB resp. 64 KiB written once; part of it is still in the L2 when the kernel ends
+    assert 0.6 * 8256 * 32768 < relaxed["bytes"] < 1.1 * 8256 * 32768
+    assert 0.6 * 8256 * 65536 < exact["bytes"] < 1.1 * 8256 * 65536
